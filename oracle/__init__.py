@@ -1,0 +1,156 @@
+"""ctypes wrapper of the CPU oracle (oracle/mpl_oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this
+package; nothing under mpl_ros_b200/ does.  See oracle/mpl_oracle.h for the parity pin statement.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+WAYPOINT_DTYPE = np.dtype([("pos", "f8", 3), ("vel", "f8", 3), ("acc", "f8", 3), ("jrk", "f8", 3),
+                           ("yaw", "f8"), ("t", "f8"), ("control", "i4"), ("enable_t", "i4")], align=True)
+RESULT_DTYPE = np.dtype([("status", "i4"), ("n_seg", "i4"), ("cost", "f8"), ("pops", "i4"), ("n_nodes", "i4"),
+                         ("n_open", "i4"), ("n_closed", "i4"), ("n_prims", "i8"), ("n_samples", "i8"),
+                         ("n_valid", "i8"), ("pop_hash", "u8"), ("closed_hash", "u8")], align=True)
+TRACE_DTYPE = np.dtype([("verdict", "i4"), ("n", "i4"), ("n_tested", "i4"), ("block_idx", "i4"), ("cost", "f8"),
+                        ("succ", "f8", 13), ("key", "i4", 16)], align=True)
+NODE_DTYPE = np.dtype([("state", "f8", 13), ("t", "f8"), ("g", "f8"), ("h", "f8"), ("key", "i4", 16),
+                       ("opened", "i4"), ("closed", "i4")], align=True)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "mpl_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_map_create.restype = C.c_void_p
+        L.orc_map_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        L.orc_map_destroy.argtypes = [C.c_void_p]
+        L.orc_map_free_unknown.argtypes = [C.c_void_p]
+        L.orc_map_float_to_int.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_planner_create.restype = C.c_void_p
+        L.orc_planner_create.argtypes = [C.c_int]
+        L.orc_planner_destroy.argtypes = [C.c_void_p]
+        L.orc_planner_set_map.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_planner_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.orc_planner_set_controls.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_get_actions.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_get_seg_states.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_get_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_get_pop_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_get_succ_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_plan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def make_waypoints(n=1):
+    return np.zeros(n, dtype=WAYPOINT_DTYPE)
+
+
+class OracleMap:
+    def __init__(self, origin, dim, data, res):
+        origin = np.ascontiguousarray(origin, dtype=np.float64)
+        dim = np.ascontiguousarray(dim, dtype=np.int32)
+        data = np.ascontiguousarray(data, dtype=np.int8)
+        assert data.size == int(np.prod(dim))
+        self.ndim = len(dim)
+        self.h = lib().orc_map_create(self.ndim, _ptr(dim), _ptr(origin), float(res), _ptr(data))
+
+    def free_unknown(self):
+        lib().orc_map_free_unknown(self.h)
+
+    def float_to_int(self, pt):
+        pt = np.ascontiguousarray(pt, dtype=np.float64)
+        pn = np.zeros(3, dtype=np.int32)
+        idx = lib().orc_map_float_to_int(self.h, _ptr(pt), _ptr(pn))
+        return pn[:self.ndim].copy(), idx
+
+    def __del__(self):
+        try:
+            lib().orc_map_destroy(self.h)
+        except Exception:
+            pass
+
+
+class OraclePlanner:
+    """Mirrors the reference setters (planner_base.h:179-265) over the oracle."""
+
+    def __init__(self, dim):
+        self.dim = dim
+        self.h = lib().orc_planner_create(dim)
+        self._map = None
+        self.nU = 0
+
+    def __del__(self):
+        try:
+            lib().orc_planner_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_map(self, m):
+        self._map = m
+        lib().orc_planner_set_map(self.h, m.h)
+
+    def set_param(self, key, v):
+        assert lib().orc_planner_set_param(self.h, key.encode(), float(v)) == 0, key
+
+    def set_controls(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        self.nU = U.shape[0]
+        lib().orc_planner_set_controls(self.h, _ptr(U), U.shape[0], U.shape[1])
+
+    def plan(self, start, goal):
+        res = np.zeros(1, dtype=RESULT_DTYPE)
+        lib().orc_plan(self.h, _ptr(start), _ptr(goal), _ptr(res))
+        return res[0]
+
+    def actions(self, n_seg):
+        a = np.zeros(max(n_seg, 1), dtype=np.int32)
+        n = lib().orc_get_actions(self.h, _ptr(a), a.size)
+        return a[:n]
+
+    def seg_states(self, n_seg):
+        s = np.zeros((max(n_seg, 1), 13), dtype=np.float64)
+        n = lib().orc_get_seg_states(self.h, _ptr(s), s.shape[0])
+        return s[:n]
+
+    def nodes(self, n_nodes):
+        a = np.zeros(max(n_nodes, 1), dtype=NODE_DTYPE)
+        n = lib().orc_get_nodes(self.h, _ptr(a), a.size)
+        return a[:n]
+
+    def pop_keys(self, pops):
+        a = np.zeros((max(pops, 1), 16), dtype=np.int32)
+        n = lib().orc_get_pop_keys(self.h, _ptr(a), a.shape[0])
+        return a[:n]
+
+    def succ_trace(self, curr):
+        rows = np.zeros(self.nU, dtype=TRACE_DTYPE)
+        lib().orc_get_succ_trace(self.h, _ptr(curr), _ptr(rows), rows.size)
+        return rows
+
+    def plan_batch(self, starts, goals, nthreads=1, max_seg=0):
+        n = len(starts)
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        acts = np.full((n, max_seg), -1, dtype=np.int32) if max_seg > 0 else None
+        lib().orc_plan_batch(self.h, _ptr(starts), _ptr(goals), n, nthreads, _ptr(res),
+                             _ptr(acts) if acts is not None else None, max_seg)
+        return res, acts

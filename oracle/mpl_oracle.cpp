@@ -1,0 +1,741 @@
+/*
+ * mpl_oracle.cpp — CPU ORACLE: restatement of the reference A* hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may load this.
+ * The product (mpl_ros_b200/) never links or calls it.
+ *
+ * Every function cites the reference lines it follows.  Abbreviations (all under
+ * /root/reference/motion_primitive_library/include/):
+ *   pr = mpl_basis/primitive.h      wp = mpl_basis/waypoint.h     mt = mpl_basis/math.h
+ *   mu = mpl_collision/map_util.h   eb = mpl_planner/common/env_base.h
+ *   em = mpl_planner/env/env_map.h  gs = mpl_planner/common/graph_search.h
+ *   ss = mpl_planner/common/state_space.h   pb = mpl_planner/common/planner_base.h
+ *
+ * Build: g++ -O2 -std=c++17 -ffp-contract=off (mirrors the reference's -O2, no -march, no
+ * fast-math: MPL/CMakeLists.txt:5-8) — no FMA contraction, IEEE double everywhere.
+ *
+ * Arithmetic is written in the SAME operation order as the reference expressions (all six
+ * polynomial terms, power() by repeated multiplication, division by res, std::round).
+ *
+ * Assumptions about absent third-party code (see mpl_oracle.h): Eigen >= 3.2 semantics for
+ * `vec / scalar` (element-wise IEEE division) — only reached in rayTrace (mu:117-134);
+ * Boost d_ary_heap sift rules as documented at struct Heap below.
+ */
+#include "mpl_oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+const double kInf = std::numeric_limits<double>::infinity();
+
+/* ------------------------------------------------------------------ control bits, control.h:10-20 */
+enum { USE_POS = 1, USE_VEL = 2, USE_ACC = 4, USE_JRK = 8, USE_YAW = 16 };
+enum { C_VEL = 1, C_ACC = 3, C_JRK = 7, C_SNP = 15 };
+
+struct WP {  // waypoint.h:22-58
+  double pos[3] = {0, 0, 0}, vel[3] = {0, 0, 0}, acc[3] = {0, 0, 0}, jrk[3] = {0, 0, 0};
+  double yaw = 0, t = 0;
+  int control = 0;
+  bool enable_t = false;
+};
+
+WP from_c(const orc_waypoint &w) {
+  WP r;
+  for (int i = 0; i < 3; i++) { r.pos[i] = w.pos[i]; r.vel[i] = w.vel[i]; r.acc[i] = w.acc[i]; r.jrk[i] = w.jrk[i]; }
+  r.yaw = w.yaw; r.t = w.t; r.control = w.control; r.enable_t = w.enable_t != 0;
+  return r;
+}
+
+/* ------------------------------------------------------------------ lattice key, wp:92-125
+ * The reference folds these ints through boost::hash_combine and compares the 64-bit results
+ * (wp:132-135); we keep the int tuple itself (equivalent up to hash collisions).            */
+struct Key {
+  int32_t v[15];
+  int32_t n = 0;
+  bool operator==(const Key &o) const { return n == o.n && std::memcmp(v, o.v, sizeof(int32_t) * n) == 0; }
+};
+
+Key make_key(const WP &w, int dim) {
+  Key k;
+  std::memset(k.v, 0, sizeof(k.v));
+  for (int i = 0; i < dim; i++) {
+    if (w.control & USE_POS) k.v[k.n++] = (int)std::round(w.pos[i] / 0.01);
+    if (w.control & USE_VEL) k.v[k.n++] = (int)std::round(w.vel[i] / 0.1);
+    if (w.control & USE_ACC) k.v[k.n++] = (int)std::round(w.acc[i] / 0.1);
+    if (w.control & USE_JRK) k.v[k.n++] = (int)std::round(w.jrk[i] / 0.1);
+  }
+  if (w.control & USE_YAW) k.v[k.n++] = (int)std::round(w.yaw / 0.1);
+  if (w.enable_t) k.v[k.n++] = (int)std::round(w.t / 0.1);
+  return k;
+}
+
+/* 64-bit mixing hash of the int tuple: shared definition with the CUDA side (mplb key hash),
+ * used for pop_hash / closed_hash parity and as std::unordered_map hasher. */
+uint64_t key_hash(const Key &k) {
+  uint64_t h = 0x243F6A8885A308D3ull;
+  for (int i = 0; i < k.n; i++) {
+    h ^= (uint64_t)(uint32_t)k.v[i];
+    h *= 0x9E3779B97F4A7C15ull;
+    h ^= h >> 32;
+  }
+  h ^= h >> 30; h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 27; h *= 0x94D049BB133111EBull;
+  h ^= h >> 31;
+  return h;
+}
+struct KeyHasher { size_t operator()(const Key &k) const { return (size_t)key_hash(k); } };
+
+/* ------------------------------------------------------------------ math.h:197-205 */
+double power(double t, int n) {
+  double tn = 1;
+  while (n > 0) { tn *= t; n--; }
+  return tn;
+}
+
+/* math.h:117-131 restricted to what the grid path reaches (quartic/cubic never on ACC/JRK/SNP grids:
+ * a = 0 always, b = c0/6 = 0 always because c0 = 0 for every control constructor pr:35-52). */
+std::vector<double> solve4(double a, double b, double c, double d, double e) {
+  std::vector<double> ts;
+  if (a != 0 || b != 0) {
+    std::fprintf(stderr, "oracle: quartic/cubic extrema not on the grid path (a=%g b=%g)\n", a, b);
+    return ts;
+  }
+  if (c != 0) {  // quad, math.h:22-33
+    double p = d * d - 4 * c * e;
+    if (p < 0) return ts;
+    ts.push_back((-d - std::sqrt(p)) / (2 * c));
+    ts.push_back((-d + std::sqrt(p)) / (2 * c));
+    return ts;
+  } else if (d != 0) {
+    ts.push_back(-e / d);
+    return ts;
+  }
+  return ts;
+}
+
+/* ------------------------------------------------------------------ Primitive1D, pr:21-198 */
+struct Prim1D {
+  double c[6] = {0, 0, 0, 0, 0, 0};
+  double p(double t) const {  // pr:128-131
+    return c[0] / 120 * power(t, 5) + c[1] / 24 * power(t, 4) + c[2] / 6 * power(t, 3) + c[3] / 2 * t * t + c[4] * t + c[5];
+  }
+  double v(double t) const {  // pr:134-137
+    return c[0] / 24 * power(t, 4) + c[1] / 6 * power(t, 3) + c[2] / 2 * t * t + c[3] * t + c[4];
+  }
+  double a(double t) const {  // pr:140-142
+    return c[0] / 6 * power(t, 3) + c[1] / 2 * t * t + c[2] * t + c[3];
+  }
+  double j(double t) const { return c[0] / 2 * t * t + c[1] * t + c[2]; }  // pr:145
+  std::vector<double> extrema_v(double t) const {  // pr:152-162
+    std::vector<double> roots = solve4(0, c[0] / 6, c[1] / 2, c[2], c[3]);
+    std::vector<double> ts;
+    for (double it : roots) {
+      if (it > 0 && it < t) ts.push_back(it);
+      else if (it >= t) break;
+    }
+    return ts;
+  }
+  std::vector<double> extrema_a(double t) const {  // pr:169-179
+    std::vector<double> roots = solve4(0, 0, c[0] / 2, c[1], c[2]);
+    std::vector<double> ts;
+    for (double it : roots) {
+      if (it > 0 && it < t) ts.push_back(it);
+      else if (it >= t) break;
+    }
+    return ts;
+  }
+  std::vector<double> extrema_j(double t) const {  // pr:186-193
+    std::vector<double> ts;
+    if (c[0] != 0) {
+      double t_sol = -c[1] * 2 / c[0];
+      if (t_sol > 0 && t_sol < t) ts.push_back(t_sol);
+    }
+    return ts;
+  }
+  double J(double t, int control) const {  // pr:92-122 (yaw variants share the branch)
+    int cc = control & 15;
+    if (cc == C_VEL)
+      return c[0] * c[0] / 5184 * power(t, 9) + c[0] * c[1] / 576 * power(t, 8) +
+             (c[1] * c[1] / 252 + c[0] * c[2] / 168) * power(t, 7) + (c[0] * c[3] / 72 + c[1] * c[2] / 36) * power(t, 6) +
+             (c[2] * c[2] / 20 + c[0] * c[4] / 60 + c[1] * c[3] / 15) * power(t, 5) +
+             (c[2] * c[3] / 4 + c[1] * c[4] / 12) * power(t, 4) + (c[3] * c[3] / 3 + c[2] * c[4] / 3) * power(t, 3) +
+             c[3] * c[4] * t * t + c[4] * c[4] * t;
+    else if (cc == C_ACC)
+      return c[0] * c[0] / 252 * power(t, 7) + c[0] * c[1] / 36 * power(t, 6) +
+             (c[1] * c[1] / 20 + c[0] * c[2] / 15) * power(t, 5) + (c[0] * c[3] / 12 + c[1] * c[2] / 4) * power(t, 4) +
+             (c[2] * c[2] / 3 + c[1] * c[3] / 3) * power(t, 3) + c[2] * c[3] * t * t + c[3] * c[3] * t;
+    else if (cc == C_JRK)
+      return c[0] * c[0] / 20 * power(t, 5) + c[0] * c[1] / 4 * power(t, 4) + (c[1] * c[1] + c[0] * c[2]) / 3 * power(t, 3) +
+             c[1] * c[2] * t * t + c[2] * c[2] * t;
+    else if (cc == C_SNP)
+      return c[0] * c[0] / 3 * power(t, 3) + c[0] * c[1] * t * t + c[1] * c[1] * t;
+    return 0;
+  }
+};
+
+/* ------------------------------------------------------------------ Primitive<Dim>, pr:205-431 */
+struct Prim {
+  int dim = 3;
+  double T = 0;
+  int control = 0;
+  Prim1D ax[3];
+
+  Prim() {}
+  Prim(const WP &p, const double *u, double t, int dim_) : dim(dim_), T(t), control(p.control) {  // pr:220-256
+    int cc = control & 15;
+    for (int i = 0; i < dim; i++) {
+      double *c = ax[i].c;
+      if (cc == C_SNP) { c[1] = u[i]; c[2] = p.jrk[i]; c[3] = p.acc[i]; c[4] = p.vel[i]; c[5] = p.pos[i]; }       // pr:50-52
+      else if (cc == C_JRK) { c[2] = u[i]; c[3] = p.acc[i]; c[4] = p.vel[i]; c[5] = p.pos[i]; }                   // pr:44-46
+      else if (cc == C_ACC) { c[3] = u[i]; c[4] = p.vel[i]; c[5] = p.pos[i]; }                                    // pr:40
+      else if (cc == C_VEL) { c[4] = u[i]; c[5] = p.pos[i]; }                                                     // pr:36
+    }
+  }
+  WP evaluate(double t) const {  // pr:321-331 (yaw controls are out of scope: use_yaw never set here)
+    WP p;
+    p.control = control;
+    for (int k = 0; k < dim; k++) {
+      p.pos[k] = ax[k].p(t);
+      p.vel[k] = ax[k].v(t);
+      p.acc[k] = ax[k].a(t);
+      p.jrk[k] = ax[k].j(t);
+    }
+    return p;
+  }
+  double max_vel(int k) const {  // pr:353-363
+    std::vector<double> ts = ax[k].extrema_v(T);
+    double m = std::max(std::abs(ax[k].v(0)), std::abs(ax[k].v(T)));
+    for (double it : ts)
+      if (it > 0 && it < T) { double v = std::abs(ax[k].v(it)); m = v > m ? v : m; }
+    return m;
+  }
+  double max_acc(int k) const {  // pr:369-379
+    std::vector<double> ts = ax[k].extrema_a(T);
+    double m = std::max(std::abs(ax[k].a(0)), std::abs(ax[k].a(T)));
+    for (double it : ts)
+      if (it > 0 && it < T) { double a = std::abs(ax[k].a(it)); m = a > m ? a : m; }
+    return m;
+  }
+  double max_jrk(int k) const {  // pr:384-394
+    std::vector<double> ts = ax[k].extrema_j(T);
+    double m = std::max(std::abs(ax[k].j(0)), std::abs(ax[k].j(T)));
+    for (double it : ts)
+      if (it > 0 && it < T) { double j = std::abs(ax[k].j(it)); m = j > m ? j : m; }
+    return m;
+  }
+  double J(int ctl) const {  // pr:403-407
+    double j = 0;
+    for (int k = 0; k < dim; k++) j += ax[k].J(T, ctl);
+    return j;
+  }
+};
+
+bool validate_xxx(const Prim &pr, double max, int which) {  // pr:483-496
+  if (max <= 0) return true;
+  for (int i = 0; i < pr.dim; i++) {
+    if (which == C_VEL && pr.max_vel(i) > max) return false;
+    else if (which == C_ACC && pr.max_acc(i) > max) return false;
+    else if (which == C_JRK && pr.max_jrk(i) > max) return false;
+  }
+  return true;
+}
+
+bool validate_primitive(const Prim &pr, double mv, double ma, double mj) {  // pr:449-475 (non-yaw branches)
+  int cc = pr.control;
+  if (cc == C_ACC) return validate_xxx(pr, mv, C_VEL);
+  else if (cc == C_JRK) return validate_xxx(pr, mv, C_VEL) && validate_xxx(pr, ma, C_ACC);
+  else if (cc == C_SNP) return validate_xxx(pr, mv, C_VEL) && validate_xxx(pr, ma, C_ACC) && validate_xxx(pr, mj, C_JRK);
+  return true;  // VEL and everything else: pr:473-474
+}
+
+/* ------------------------------------------------------------------ MapUtil, mu:20-314 */
+struct Map {
+  int dim = 3;
+  int nd[3] = {1, 1, 1};
+  double origin[3] = {0, 0, 0};
+  double res = 1;
+  std::vector<int8_t> data;
+
+  int index(const int *pn) const {  // mu:33-41
+    return dim == 2 ? pn[0] + nd[0] * pn[1] : pn[0] + nd[0] * pn[1] + nd[0] * nd[1] * pn[2];
+  }
+  bool outside(const int *pn) const {  // mu:51-55
+    for (int i = 0; i < dim; i++)
+      if (pn[i] < 0 || pn[i] >= nd[i]) return true;
+    return false;
+  }
+  bool occupied(const int *pn) const { return outside(pn) ? false : data[index(pn)] == 100; }  // mu:48,64-69
+  bool is_free(const int *pn) const {  // mu:44,57-62
+    if (outside(pn)) return false;
+    int8_t v = data[index(pn)];
+    return v < 100 && v >= 0;
+  }
+  void float_to_int(const double *pt, int *pn) const {  // mu:103-108
+    for (int i = 0; i < dim; i++) pn[i] = (int)std::round((pt[i] - origin[i]) / res - 0.5);
+  }
+  void free_unknown() {  // mu:259-276
+    for (auto &v : data)
+      if (v == -1) v = 0;
+  }
+  /* mu:117-134; returns true iff some traced cell is occupied (what em:38-42 asks). */
+  bool ray_hits_occupied(const double *pt1, const double *pt2) const {
+    double diff[3], q = 0;
+    for (int i = 0; i < dim; i++) {
+      diff[i] = pt2[i] - pt1[i];
+      double a = std::abs(diff[i] / res);
+      if (i == 0 || a > q) q = a;  // lpNorm<Infinity>
+    }
+    int max_diff = (int)(q / 0.8);
+    double s = 1.0 / max_diff;
+    double step[3];
+    for (int i = 0; i < dim; i++) step[i] = diff[i] * s;
+    for (int n = 1; n < max_diff; n++) {
+      double pt[3];
+      int pn[3] = {0, 0, 0};
+      for (int i = 0; i < dim; i++) pt[i] = pt1[i] + step[i] * n;
+      float_to_int(pt, pn);
+      if (outside(pn)) break;
+      if (data[index(pn)] == 100) return true;
+    }
+    return false;
+  }
+};
+
+/* ------------------------------------------------------------------ Boost d_ary_heap<arity<2>, mutable_<true>>
+ * Restated from Boost.Heap's published algorithm (boost/heap/d_ary_heap.hpp, stable since 1.49):
+ *   push      : append, sift UP while cmp(parent, x)  (parent strictly worse than x)
+ *   pop       : swap(front, back), drop back, sift DOWN the new front
+ *   sift down : best child = std::max_element over the (<= 2) children w.r.t. cmp (FIRST of equal
+ *               maxima, i.e. the left child on ties); swap unless cmp(best child, x) (child strictly
+ *               worse than x) — so on a tie the element still moves down
+ *   increase  : sift UP from the element's position (gs:133 calls increase after lowering f)
+ * cmp = compare_pair (ss:15-27): cmp(a,b) true iff a is WORSE than b:
+ *   a.f == b.f ? min(g_a,rhs_a) > min(g_b,rhs_b) : a.f > b.f ; g is read through the node pointer
+ *   at comparison time (rhs stays +inf in A*).                                                     */
+struct Node {
+  WP coord;
+  Key key;
+  double g = kInf, h = kInf;
+  bool opened = false, closed = false;
+  int heap_entry = -1;  // handle
+  std::vector<int> pred_node;  // gs:100-102 (node ids instead of coords; hm_ lookup is by key either way)
+  std::vector<double> pred_cost;
+  std::vector<int> pred_act;
+};
+
+struct Heap {
+  struct Entry { double f; int node; int pos; };
+  std::vector<Entry> entries;  // stable storage (the std::list of the mutable heap)
+  std::vector<int> q;          // heap order: entry ids
+  const std::vector<Node> *nodes = nullptr;
+
+  bool worse(int ea, int eb) const {
+    const Entry &a = entries[ea], &b = entries[eb];
+    if (a.f == b.f) return (*nodes)[a.node].g > (*nodes)[b.node].g;
+    return a.f > b.f;
+  }
+  void place(int pos, int e) { q[pos] = e; entries[e].pos = pos; }
+  void sift_up(int pos) {
+    while (pos != 0) {
+      int parent = (pos - 1) / 2;
+      if (worse(q[parent], q[pos])) {
+        int a = q[parent], b = q[pos];
+        place(parent, b); place(pos, a);
+        pos = parent;
+      } else return;
+    }
+  }
+  void sift_down(int pos) {
+    int n = (int)q.size();
+    while (2 * pos + 1 < n) {
+      int c = 2 * pos + 1;
+      if (c + 1 < n && worse(q[c], q[c + 1])) c = c + 1;  // max_element: later one only if strictly better
+      if (!worse(q[c], q[pos])) {
+        int a = q[c], b = q[pos];
+        place(pos, a); place(c, b);
+        pos = c;
+      } else return;
+    }
+  }
+  int push(double f, int node) {
+    int e = (int)entries.size();
+    entries.push_back({f, node, (int)q.size()});
+    q.push_back(e);
+    sift_up((int)q.size() - 1);
+    return e;
+  }
+  int top_node() const { return entries[q[0]].node; }
+  void pop() {
+    int last = q.back();
+    q.pop_back();
+    if (q.empty()) return;
+    place(0, last);
+    sift_down(0);
+  }
+  void increase(int e, double f) { entries[e].f = f; sift_up(entries[e].pos); }
+  bool empty() const { return q.empty(); }
+};
+
+/* ------------------------------------------------------------------ planner (env_map + env_base + Astar) */
+struct Planner {
+  int dim = 3;
+  Map *map = nullptr;
+  // env_base defaults eb:368-392; planner defaults pb:337-339
+  double w = 10.0, tol_pos = 0.5, tol_vel = -1.0, tol_acc = -1.0;
+  double v_max = -1.0, a_max = -1.0, j_max = -1.0, yaw_max = -1.0, dt = 1.0;
+  double eps = 1.0;
+  int max_num = -1;
+  std::vector<std::vector<double>> U;
+  WP goal;
+
+  // state of the last plan
+  std::vector<Node> nodes;
+  std::unordered_map<Key, int, KeyHasher> hm;
+  Heap heap;
+  std::vector<int> pop_order;
+  std::vector<int> traj_actions;
+  std::vector<int> traj_nodes;  // parent node of each segment
+  orc_result last;
+
+  /* em:25-45 */
+  bool is_goal(const WP &s) const {
+    double m = 0;
+    for (int i = 0; i < dim; i++) m = std::max(m, std::abs(s.pos[i] - goal.pos[i]));
+    bool goaled = m <= tol_pos;
+    if (goaled && tol_vel >= 0) {
+      m = 0;
+      for (int i = 0; i < dim; i++) m = std::max(m, std::abs(s.vel[i] - goal.vel[i]));
+      goaled = m <= tol_vel;
+    }
+    if (goaled && tol_acc >= 0) {
+      m = 0;
+      for (int i = 0; i < dim; i++) m = std::max(m, std::abs(s.acc[i] - goal.acc[i]));
+      goaled = m <= tol_acc;
+    }
+    if (goaled && map->ray_hits_occupied(s.pos, goal.pos)) return false;
+    return goaled;
+  }
+
+  /* eb:46-64, heur_ignore_dynamics_ = true (default eb:368), no prior trajectory */
+  double get_heur(const WP &s, const Key &skey) const {
+    if (make_key(goal, dim) == skey) return 0;
+    double m = 0;
+    for (int i = 0; i < dim; i++) m = std::max(m, std::abs(s.pos[i] - goal.pos[i]));
+    if (v_max > 0) return w * m / v_max;
+    return w * m;
+  }
+
+  /* em:90-132, plain map (no potential map, no search region, no yaw) */
+  double traverse(const Prim &pr, orc_prim_trace *tr, int64_t *n_samples) const {
+    double max_v = 0;
+    for (int i = 0; i < dim; i++)
+      if (pr.max_vel(i) > max_v) max_v = pr.max_vel(i);
+    int n = std::max(5, (int)std::ceil(max_v * pr.T / map->res));
+    double c = 0;
+    double dts = pr.T / n;
+    int tested = 0;
+    if (tr) { tr->n = n; tr->block_idx = -1; }
+    for (double t = 0; t < pr.T; t += dts) {
+      WP pt = pr.evaluate(t);
+      int pn[3] = {0, 0, 0};
+      map->float_to_int(pt.pos, pn);
+      tested++;
+      if (map->outside(pn)) {
+        if (tr) tr->n_tested = tested;
+        *n_samples += tested;
+        return kInf;
+      }
+      if (map->data[map->index(pn)] == 100) {
+        if (tr) { tr->n_tested = tested; tr->block_idx = map->index(pn); }
+        *n_samples += tested;
+        return kInf;
+      }
+    }
+    if (tr) tr->n_tested = tested;
+    *n_samples += tested;
+    return c;
+  }
+
+  /* em:147-172.  Emits rows for every u when `trace` is given; succ lists hold only the entries the
+   * reference pushes (self-loops and dyn-rejects produce none). */
+  void get_succ(const WP &curr, std::vector<WP> &succ, std::vector<double> &cost, std::vector<int> &act,
+                orc_prim_trace *trace, int64_t *n_samples) const {
+    succ.clear(); cost.clear(); act.clear();
+    Key ck = make_key(curr, dim);
+    for (size_t i = 0; i < U.size(); i++) {
+      Prim pr(curr, U[i].data(), dt, dim);
+      WP tn = pr.evaluate(dt);
+      Key tk = make_key(tn, dim);
+      orc_prim_trace *tr = trace ? &trace[i] : nullptr;
+      if (tr) {
+        std::memset(tr, 0, sizeof(*tr));
+        tr->block_idx = -1;
+        for (int k = 0; k < 3; k++) { tr->succ[k] = tn.pos[k]; tr->succ[3 + k] = tn.vel[k]; tr->succ[6 + k] = tn.acc[k]; tr->succ[9 + k] = tn.jrk[k]; }
+        tr->succ[12] = tn.yaw;
+        for (int k = 0; k < tk.n; k++) tr->key[k] = tk.v[k];
+        tr->key[15] = tk.n;
+      }
+      if (tk == ck) { if (tr) tr->verdict = 0; continue; }
+      if (!validate_primitive(pr, v_max, a_max, j_max)) { if (tr) tr->verdict = 1; continue; }
+      tn.t = curr.t + dt;
+      succ.push_back(tn);
+      bool same = true;
+      for (int k = 0; k < dim; k++) same = same && (curr.pos[k] == tn.pos[k]);
+      double c = same ? 0 : traverse(pr, tr, n_samples);
+      if (!std::isinf(c)) c += pr.J(pr.control) + w * dt;  // eb:343-345
+      if (tr) { tr->verdict = std::isinf(c) ? 2 : (same ? 4 : 3); tr->cost = c; }
+      cost.push_back(c);
+      act.push_back((int)i);
+    }
+  }
+
+  int plan(const WP &start, const WP &goal_) {
+    nodes.clear(); hm.clear(); heap = Heap(); pop_order.clear(); traj_actions.clear(); traj_nodes.clear();
+    std::memset(&last, 0, sizeof(last));
+    last.cost = kInf;
+    heap.nodes = &nodes;
+    // pb:283-287
+    int pn[3] = {0, 0, 0};
+    map->float_to_int(start.pos, pn);
+    if (!map->is_free(pn)) { last.status = 1; return 1; }
+    goal = goal_;  // eb:295-298
+    // gs:44
+    if (is_goal(start)) { last.status = 5; last.cost = 0; return 5; }
+    // gs:47-60
+    {
+      Node n0;
+      n0.coord = start;
+      n0.key = make_key(start, dim);
+      n0.g = 0;
+      n0.h = eps == 0 ? 0 : get_heur(start, n0.key);
+      n0.opened = true;
+      nodes.push_back(n0);
+      hm[n0.key] = 0;
+      nodes[0].heap_entry = heap.push(nodes[0].g + eps * nodes[0].h, 0);
+    }
+    int expand_iteration = 0;
+    int curr = -1;
+    std::vector<WP> succ; std::vector<double> scost; std::vector<int> sact;
+    uint64_t pop_hash = 0xCBF29CE484222325ull, closed_hash = 0;
+    int n_closed = 0;
+    int status = 0;
+    while (true) {
+      expand_iteration++;
+      curr = heap.top_node();
+      heap.pop();
+      uint64_t kh = key_hash(nodes[curr].key);
+      pop_hash = (pop_hash ^ kh) * 0x100000001B3ull;
+      if (!nodes[curr].closed) { n_closed++; closed_hash += kh; }
+      nodes[curr].closed = true;
+      pop_order.push_back(curr);
+      last.n_prims += (int64_t)U.size();
+      WP cw = nodes[curr].coord;
+      get_succ(cw, succ, scost, sact, nullptr, &last.n_samples);
+      for (size_t s = 0; s < succ.size(); s++) {
+        if (std::isinf(scost[s])) continue;  // gs:81
+        last.n_valid++;
+        Key sk = make_key(succ[s], dim);
+        auto it = hm.find(sk);
+        int sid;
+        if (it == hm.end()) {  // gs:84-88
+          sid = (int)nodes.size();
+          Node nn;
+          nn.coord = succ[s];
+          nn.key = sk;
+          nn.h = eps == 0 ? 0 : get_heur(succ[s], sk);
+          nodes.push_back(nn);
+          hm[sk] = sid;
+        } else sid = it->second;
+        Node &sn = nodes[sid];
+        sn.pred_node.push_back(curr);  // gs:100-102
+        sn.pred_cost.push_back(scost[s]);
+        sn.pred_act.push_back(sact[s]);
+        double tentative = nodes[curr].g + scost[s];
+        if (tentative < sn.g) {  // gs:107-141
+          sn.g = tentative;
+          double fval = sn.g + eps * sn.h;
+          if (sn.opened && !sn.closed) heap.increase(sn.heap_entry, fval);
+          else { sn.heap_entry = heap.push(fval, sid); nodes[sid].opened = true; }
+        }
+      }
+      if (is_goal(nodes[curr].coord)) break;                                             // gs:146
+      if (max_num > 0 && expand_iteration >= max_num) { status = 2; break; }             // gs:149-154
+      if (heap.empty()) { status = 3; break; }                                           // gs:157-161
+    }
+    last.pops = expand_iteration;
+    last.n_nodes = (int)nodes.size();
+    last.n_open = (int)heap.q.size();
+    last.n_closed = n_closed;
+    last.pop_hash = pop_hash;
+    last.closed_hash = closed_hash;
+    if (status != 0) { last.status = status; return status; }
+    // recoverTraj gs:369-455
+    bool found = false;
+    int c = curr;
+    std::vector<int> acts, parents;
+    while (!nodes[c].pred_node.empty()) {
+      int min_id = -1;
+      double min_rhs = kInf, min_g = kInf;
+      const Node &cn = nodes[c];
+      for (size_t i = 0; i < cn.pred_node.size(); i++) {
+        double pg = nodes[cn.pred_node[i]].g;
+        if (min_rhs > pg + cn.pred_cost[i]) { min_rhs = pg + cn.pred_cost[i]; min_g = pg; min_id = (int)i; }
+        else if (!std::isinf(cn.pred_cost[i]) && min_rhs == pg + cn.pred_cost[i]) {
+          if (min_g < pg) { min_g = pg; min_id = (int)i; }
+        }
+      }
+      if (min_id >= 0) {
+        acts.push_back(cn.pred_act[min_id]);
+        c = cn.pred_node[min_id];
+        parents.push_back(c);
+      } else break;
+      if (nodes[c].key == nodes[0].key) { found = true; break; }  // gs:433 (start_key, hash equality)
+    }
+    if (!found) { last.status = 4; return 4; }
+    std::reverse(acts.begin(), acts.end());
+    std::reverse(parents.begin(), parents.end());
+    traj_actions = acts;
+    traj_nodes = parents;
+    last.n_seg = (int)acts.size();
+    last.cost = nodes[curr].g;  // gs:179
+    last.status = 0;
+    return 0;
+  }
+};
+
+}  // namespace
+
+/* ================================================================== C interface */
+extern "C" {
+
+void *orc_map_create(int dim, const int32_t *ndim, const double *origin, double res, const int8_t *data) {
+  Map *m = new Map();
+  m->dim = dim;
+  size_t n = 1;
+  for (int i = 0; i < dim; i++) { m->nd[i] = ndim[i]; m->origin[i] = origin[i]; n *= (size_t)ndim[i]; }
+  m->res = res;
+  m->data.assign(data, data + n);  // mu:84-90 deep copy
+  return m;
+}
+void orc_map_destroy(void *map) { delete (Map *)map; }
+void orc_map_free_unknown(void *map) { ((Map *)map)->free_unknown(); }
+int orc_map_float_to_int(void *map, const double *pt, int32_t *pn) {
+  Map *m = (Map *)map;
+  int p[3] = {0, 0, 0};
+  m->float_to_int(pt, p);
+  for (int i = 0; i < m->dim; i++) pn[i] = p[i];
+  return m->outside(p) ? -1 : m->index(p);
+}
+
+void *orc_planner_create(int dim) { Planner *p = new Planner(); p->dim = dim; return p; }
+void orc_planner_destroy(void *p) { delete (Planner *)p; }
+void orc_planner_set_map(void *p, void *map) { ((Planner *)p)->map = (Map *)map; }
+int orc_planner_set_param(void *pp, const char *key, double v) {
+  Planner *p = (Planner *)pp;
+  std::string k(key);
+  if (k == "v_max") p->v_max = v; else if (k == "a_max") p->a_max = v; else if (k == "j_max") p->j_max = v;
+  else if (k == "yaw_max") p->yaw_max = v; else if (k == "dt") p->dt = v; else if (k == "w") p->w = v;
+  else if (k == "epsilon") p->eps = v; else if (k == "max_num") p->max_num = (int)v;
+  else if (k == "tol_pos") p->tol_pos = v; else if (k == "tol_vel") p->tol_vel = v; else if (k == "tol_acc") p->tol_acc = v;
+  else return -1;
+  return 0;
+}
+void orc_planner_set_controls(void *pp, const double *U, int n, int udim) {
+  Planner *p = (Planner *)pp;
+  p->U.clear();
+  for (int i = 0; i < n; i++) p->U.emplace_back(U + (size_t)i * udim, U + (size_t)(i + 1) * udim);
+}
+
+int orc_plan(void *pp, const orc_waypoint *start, const orc_waypoint *goal, orc_result *out) {
+  Planner *p = (Planner *)pp;
+  int st = p->plan(from_c(*start), from_c(*goal));
+  if (out) *out = p->last;
+  return st;
+}
+int orc_get_actions(void *pp, int32_t *actions, int cap) {
+  Planner *p = (Planner *)pp;
+  int n = (int)p->traj_actions.size();
+  for (int i = 0; i < n && i < cap; i++) actions[i] = p->traj_actions[i];
+  return n;
+}
+static void pack_state(const WP &w, double *s) {
+  for (int k = 0; k < 3; k++) { s[k] = w.pos[k]; s[3 + k] = w.vel[k]; s[6 + k] = w.acc[k]; s[9 + k] = w.jrk[k]; }
+  s[12] = w.yaw;
+}
+int orc_get_seg_states(void *pp, double *states13, int cap) {
+  Planner *p = (Planner *)pp;
+  int n = (int)p->traj_nodes.size();
+  for (int i = 0; i < n && i < cap; i++) pack_state(p->nodes[p->traj_nodes[i]].coord, states13 + 13 * (size_t)i);
+  return n;
+}
+int orc_get_nodes(void *pp, orc_node *out, int cap) {
+  Planner *p = (Planner *)pp;
+  int n = (int)p->nodes.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    const Node &nd = p->nodes[i];
+    std::memset(&out[i], 0, sizeof(orc_node));
+    pack_state(nd.coord, out[i].state);
+    out[i].t = nd.coord.t; out[i].g = nd.g; out[i].h = nd.h;
+    for (int k = 0; k < nd.key.n; k++) out[i].key[k] = nd.key.v[k];
+    out[i].key[15] = nd.key.n;
+    out[i].opened = nd.opened; out[i].closed = nd.closed;
+  }
+  return n;
+}
+int orc_get_pop_keys(void *pp, int32_t *keys16, int cap) {
+  Planner *p = (Planner *)pp;
+  int n = (int)p->pop_order.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    const Key &k = p->nodes[p->pop_order[i]].key;
+    int32_t *row = keys16 + 16 * (size_t)i;
+    std::memset(row, 0, 16 * sizeof(int32_t));
+    for (int j = 0; j < k.n; j++) row[j] = k.v[j];
+    row[15] = k.n;
+  }
+  return n;
+}
+int orc_get_succ_trace(void *pp, const orc_waypoint *curr, orc_prim_trace *rows, int cap) {
+  Planner *p = (Planner *)pp;
+  int n = (int)p->U.size();
+  if (cap < n) return n;
+  std::vector<WP> succ; std::vector<double> c; std::vector<int> a;
+  int64_t ns = 0;
+  p->get_succ(from_c(*curr), succ, c, a, rows, &ns);
+  return n;
+}
+
+int orc_plan_batch(void *pp, const orc_waypoint *starts, const orc_waypoint *goals, int n, int nthreads,
+                   orc_result *results, int32_t *actions, int max_seg) {
+  Planner *base = (Planner *)pp;
+  if (nthreads < 1) nthreads = 1;
+  auto worker = [&](int tid) {
+    Planner local;  // same parameters, private search state
+    local.dim = base->dim; local.map = base->map; local.w = base->w; local.tol_pos = base->tol_pos;
+    local.tol_vel = base->tol_vel; local.tol_acc = base->tol_acc; local.v_max = base->v_max; local.a_max = base->a_max;
+    local.j_max = base->j_max; local.yaw_max = base->yaw_max; local.dt = base->dt; local.eps = base->eps;
+    local.max_num = base->max_num; local.U = base->U;
+    for (int i = tid; i < n; i += nthreads) {
+      local.plan(from_c(starts[i]), from_c(goals[i]));
+      results[i] = local.last;
+      if (actions) {
+        int ns = (int)local.traj_actions.size();
+        for (int k = 0; k < max_seg; k++) actions[(size_t)i * max_seg + k] = k < ns ? local.traj_actions[k] : -1;
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; t++) th.emplace_back(worker, t);
+  for (auto &t : th) t.join();
+  return 0;
+}
+
+}  // extern "C"

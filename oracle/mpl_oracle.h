@@ -1,0 +1,99 @@
+/*
+ * mpl_oracle.h — C interface of the CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * The oracle is a plain-array, Eigen/Boost-free restatement of the reference's A* hot path
+ * (sikang/mpl_ros @155014c, motion_primitive_library @547ddcd).  It exists only so that
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs can
+ * check and time the reference algorithm.  Nothing under mpl_ros_b200/ may include, link or
+ * call it.
+ *
+ * Parity pin: MPL/README.md:200-202 (closed set 615, T = 35, J(VEL) = 36.75, J(ACC) = 1.5 on
+ * MPL/data/corridor.yaml with MPL/test/test_planner_2d.cpp:29-62 parameters) — checked by
+ * tests/test_oracle_kat.py.  Everything else (3D, |U| = 27, JRK) is pinned only through this
+ * restatement: "parity unpinned by the reference's own tests" for those configs.
+ *
+ * Third-party pieces that are NOT under /root/reference and are restated from their published
+ * behaviour: Boost.Heap d_ary_heap<arity 2, mutable> (sift rules, see heap section of the .cpp),
+ * Boost.Unordered (keyed here by the integer lattice tuple instead of boost::hash_combine),
+ * Eigen fixed-size vector arithmetic (element-wise IEEE ops, lpNorm<Infinity> = max |x_i|).
+ * Versions are unpinned upstream (apt libeigen3-dev / libboost-dev, MPL/wercker.yml:10).
+ */
+#ifndef MPL_ORACLE_H
+#define MPL_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same field order as the product's mplb_waypoint (include/mplb.h) so tests can share buffers. */
+typedef struct orc_waypoint {
+  double pos[3], vel[3], acc[3], jrk[3];
+  double yaw, t;
+  int32_t control;  /* Control::Control bit pattern, control.h:10-20 */
+  int32_t enable_t; /* waypoint.h:57 */
+} orc_waypoint;
+
+typedef struct orc_result {
+  int32_t status; /* 0 ok, 1 start not free, 2 max expand, 3 queue empty, 4 traceback failed, 5 start is goal */
+  int32_t n_seg;
+  double cost;      /* PlannerBase::traj_cost_ (goal g) or +inf */
+  int32_t pops;     /* expand_iteration, graph_search.h:64,177 */
+  int32_t n_nodes;  /* hm_.size() */
+  int32_t n_open;   /* pq_.size() at return */
+  int32_t n_closed; /* nodes with iterationclosed */
+  int64_t n_prims;  /* (popped state, u) pairs entering env_map.h:155 */
+  int64_t n_samples;/* voxel samples tested by env_map.h:99 loops (early exit respected) */
+  int64_t n_valid;  /* finite-cost successors (graph_search.h:81 passes) */
+  uint64_t pop_hash;/* order-dependent hash over popped lattice keys */
+  uint64_t closed_hash; /* order-independent hash over closed lattice keys */
+} orc_result;
+
+/* One row of the per-primitive trace of env_map::get_succ (env_map.h:147-172). */
+typedef struct orc_prim_trace {
+  int32_t verdict;   /* 0 self-loop, 1 dyn-reject, 2 collide/outside, 3 valid, 4 valid (pos unchanged, no collision test) */
+  int32_t n;         /* sample divisor n of env_map.h:95 (0 if not sampled) */
+  int32_t n_tested;  /* samples tested before return */
+  int32_t block_idx; /* linear voxel index of the blocking sample, -1 if outside / none */
+  double cost;       /* succ_cost entry (inf for verdict 2; 0 for verdicts 0/1 which emit no entry) */
+  double succ[13];   /* pos3 vel3 acc3 jrk3 yaw of tn */
+  int32_t key[16];   /* lattice key ints of tn, key[15] = count */
+} orc_prim_trace;
+
+typedef struct orc_node {
+  double state[13]; /* pos3 vel3 acc3 jrk3 yaw — stored coord (first discoverer) */
+  double t;
+  double g, h;
+  int32_t key[16];  /* key[15] = count */
+  int32_t opened, closed;
+} orc_node;
+
+void *orc_map_create(int dim, const int32_t *ndim, const double *origin, double res, const int8_t *data);
+void orc_map_destroy(void *map);
+void orc_map_free_unknown(void *map);
+int orc_map_float_to_int(void *map, const double *pt, int32_t *pn); /* returns linear index or -1 if outside */
+
+void *orc_planner_create(int dim);
+void orc_planner_destroy(void *p);
+void orc_planner_set_map(void *p, void *map);
+/* keys: "v_max" "a_max" "j_max" "yaw_max" "dt" "w" "epsilon" "max_num" "tol_pos" "tol_vel" "tol_acc" */
+int orc_planner_set_param(void *p, const char *key, double v);
+void orc_planner_set_controls(void *p, const double *U, int n, int udim);
+
+int orc_plan(void *p, const orc_waypoint *start, const orc_waypoint *goal, orc_result *out);
+/* getters for the last orc_plan on this planner */
+int orc_get_actions(void *p, int32_t *actions, int cap);                 /* returns n_seg */
+int orc_get_seg_states(void *p, double *states13, int cap);              /* n_seg rows of 13 doubles (parent coord per segment) */
+int orc_get_nodes(void *p, orc_node *nodes, int cap);                    /* returns n_nodes (hash-map iteration, unordered) */
+int orc_get_pop_keys(void *p, int32_t *keys16, int cap);                 /* rows of 16 ints in pop order; returns pops */
+int orc_get_succ_trace(void *p, const orc_waypoint *curr, orc_prim_trace *rows, int cap); /* returns |U| */
+
+/* Batch: plans i = 0..n-1 striped over nthreads std::threads (one plan per thread at a time;
+ * the reference itself is single-threaded per plan). actions may be NULL. */
+int orc_plan_batch(void *p, const orc_waypoint *starts, const orc_waypoint *goals, int n, int nthreads,
+                   orc_result *results, int32_t *actions, int max_seg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
