@@ -1,0 +1,174 @@
+/*
+ * mplb.h — C ABI of the B200-native motion-primitive lattice planner (libmplb.so).
+ *
+ * This is the drop-in boundary for ONE path of sikang/mpl_ros: the A* wavefront
+ *   PlannerBase::plan -> GraphSearch::Astar -> env_map::get_succ -> Primitive -> traverse_primitive -> MapUtil
+ * The reference has no FFI layer; the seam is the C++ class surface that mpl_test_node compiles against
+ * (PlannerBase / MapPlanner / MapUtil).  Each entry point below cites the reference interface it replaces
+ * (paths relative to /root/reference/motion_primitive_library/).  The header-compatible C++ shim that puts
+ * the reference's class names back on top of this ABI is include/mpl_b200/map_planner.hpp; the binding a
+ * maintainer adds at a ROS site is shown in INTEGRATION.md.
+ *
+ * Conventions: plain C types, caller-owned buffers, no exceptions, every function returns an int status
+ * (MPLB_OK = 0) unless noted; nothing is printed unless the planner was created verbose.  A planner handle
+ * is not re-entrant (like the reference's PlannerBase, env_base.h:402-404); distinct planners may share one
+ * map as long as nobody mutates it.  There is NO CPU fallback: every call that needs the device fails with
+ * MPLB_ERR_CUDA when no CUDA device / sm_100 kernel image is usable.
+ */
+#ifndef MPLB_H
+#define MPLB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library-level status codes (return values) */
+#define MPLB_OK 0
+#define MPLB_ERR_ARG -1      /* bad argument / unsupported configuration (message in mplb_last_error) */
+#define MPLB_ERR_CUDA -2     /* CUDA runtime error or no device */
+#define MPLB_ERR_STATE -3    /* call order problem (no map, no controls, no retained plan ...) */
+#define MPLB_ERR_NOMEM -4    /* search arena does not fit in device memory */
+
+/* ---- per-plan status (mplb_result.status); 0-4 are the reference's outcomes */
+#define MPLB_PLAN_OK 0               /* trajectory found                       planner_base.h:324 */
+#define MPLB_PLAN_START_NOT_FREE 1   /* "[PlannerBase] start is not free!"     planner_base.h:283-287 */
+#define MPLB_PLAN_MAX_EXPAND 2       /* "MaxExpandStep [%d] Reached"           graph_search.h:149-154 */
+#define MPLB_PLAN_QUEUE_EMPTY 3      /* "Priority queue is empty"              graph_search.h:157-161 */
+#define MPLB_PLAN_TRACEBACK_FAILED 4 /* recoverTraj returned false             graph_search.h:414-431,180-181 */
+#define MPLB_PLAN_START_IS_GOAL 5    /* Astar returned 0 before searching; plan() is true, traj untouched graph_search.h:44 */
+#define MPLB_PLAN_KEY_RANGE 7        /* a state left the packable lattice range (|vel| >> v_max, far outside map) */
+#define MPLB_PLAN_NOMEM 8            /* node arena exhausted at the largest tier that fits the device */
+
+/* Control::Control bit patterns, include/mpl_basis/control.h:10-20 */
+#define MPLB_CONTROL_VEL 1
+#define MPLB_CONTROL_ACC 3
+#define MPLB_CONTROL_JRK 7
+#define MPLB_CONTROL_SNP 15
+
+/* Waypoint<Dim>, include/mpl_basis/waypoint.h:22-58 (Dim = 2 uses the first two components). */
+typedef struct mplb_waypoint {
+  double pos[3], vel[3], acc[3], jrk[3];
+  double yaw, t;
+  int32_t control;  /* the 5-bit use_pos..use_yaw union */
+  int32_t enable_t; /* must be 0 (time-indexed keys are not on this path) */
+} mplb_waypoint;
+
+/* Outcome of one plan.  cost = PlannerBase::traj_cost_ (goal g, graph_search.h:179) or +inf. */
+typedef struct mplb_result {
+  int32_t status;
+  int32_t n_seg;       /* number of primitives in the trajectory (Trajectory::segs.size()) */
+  double cost;
+  int32_t pops;        /* StateSpace::expand_iteration_ = getExpandedNum(), planner_base.h:148 */
+  int32_t n_nodes;     /* hm_.size() */
+  int32_t n_open;      /* pq_.size() at return = getOpenSet().size() */
+  int32_t n_closed;    /* getCloseSet().size() */
+  int64_t n_prims;     /* primitive expansions: (popped state, u) pairs entering env_map.h:155 */
+  int64_t n_samples;   /* voxel samples the reference loop env_map.h:99 tests (early exit respected) */
+  int64_t n_valid;     /* finite-cost successors (graph_search.h:81 passes) */
+  uint64_t pop_hash;   /* order-dependent hash of popped lattice keys (parity artefact) */
+  uint64_t closed_hash;/* order-independent hash of closed lattice keys (parity artefact) */
+} mplb_result;
+
+/* One (state, u) row of env_map::get_succ, env_map.h:147-172 (parity artefact + micro-benchmark output). */
+typedef struct mplb_prim_trace {
+  int32_t verdict;   /* 0 self-loop, 1 dyn-reject, 2 collide/outside, 3 valid, 4 valid with pos unchanged */
+  int32_t n;         /* sample divisor of env_map.h:95 (0 when not sampled) */
+  int32_t n_tested;  /* samples the reference loop tests before returning */
+  int32_t block_idx; /* linear voxel index of the blocking sample, -1 if outside or none */
+  double cost;       /* succ_cost entry (+inf for verdict 2, 0 for verdicts 0/1 which emit no entry) */
+  double succ[13];   /* pos3 vel3 acc3 jrk3 yaw of the end state tn */
+  int32_t key[16];   /* lattice ints of tn (waypoint.h:92-125 order), key[15] = count */
+} mplb_prim_trace;
+
+/* One search node (State<Coord>, state_space.h:36-70) of a retained single plan. */
+typedef struct mplb_node {
+  double state[13];  /* stored coord = first discoverer's state (graph_search.h:84-88) */
+  double g, h;
+  int32_t key[16];   /* key[15] = count */
+  int32_t opened, closed;
+  int32_t parent;    /* best predecessor node index (-1 for start) under recoverTraj's rule */
+  int32_t action;    /* index into U of the edge parent -> this */
+} mplb_node;
+
+typedef struct mplb_map mplb_map;
+typedef struct mplb_planner mplb_planner;
+
+const char *mplb_last_error(void);
+int mplb_device_count(void);
+/* cumulative count of this library's kernel launches in the calling process (bench `gpu_launches`). */
+int64_t mplb_launch_count(void);
+
+/* ---- MapUtil<Dim>, include/mpl_collision/map_util.h */
+/* setMap (map_util.h:84-90): deep-copies host data (int8, x fastest) and uploads it to the current device. */
+int mplb_map_create(int dim, const int32_t *ndim, const double *origin, double res, const int8_t *data, mplb_map **out);
+/* Same, but `dev_data` already lives on the current device (e.g. the receive buffer of an NCCL broadcast);
+ * it is copied device-to-device on `stream` (a cudaStream_t passed as void*, NULL = default stream). */
+int mplb_map_create_from_device(int dim, const int32_t *ndim, const double *origin, double res, const void *dev_data,
+                                void *stream, mplb_map **out);
+int mplb_map_free_unknown(mplb_map *m);                    /* freeUnknown, map_util.h:259-276 */
+int mplb_map_dilate(mplb_map *m, const int32_t *ns, int n);/* dilate, map_util.h:221-257; ns = n rows of Dim ints */
+int mplb_map_get_info(const mplb_map *m, int32_t *dim, int32_t *ndim, double *origin, double *res); /* getDim/getOrigin/getRes */
+int mplb_map_get_data(const mplb_map *m, int8_t *out, size_t cap);                                   /* getMap, map_util.h:25 */
+void mplb_map_destroy(mplb_map *m);
+
+/* ---- PlannerBase<Dim,Coord> / MapPlanner<Dim>, include/mpl_planner/common/planner_base.h, planner/map_planner.h */
+int mplb_planner_create(int dim, int verbose, mplb_planner **out); /* MapPlanner ctor, src/mpl_planner/map_planner.cpp:6-11 */
+void mplb_planner_destroy(mplb_planner *p);
+int mplb_planner_set_map(mplb_planner *p, mplb_map *m);            /* setMapUtil, map_planner.cpp:14-18 (shared, not copied) */
+
+enum mplb_param {
+  MPLB_V_MAX = 0,   /* setVmax   planner_base.h:179  default -1 (env_base.h:380) — must be > 0 here */
+  MPLB_A_MAX = 1,   /* setAmax   :185 */
+  MPLB_J_MAX = 2,   /* setJmax   :191 */
+  MPLB_YAW_MAX = 3, /* setYawmax :197 (accepted, unused: yaw controls are out of scope) */
+  MPLB_DT = 4,      /* setDt     :209 default 1.0 */
+  MPLB_W = 5,       /* setW      :215 default 10 */
+  MPLB_EPSILON = 6, /* setEpsilon:227 default 1 */
+  MPLB_MAX_NUM = 7, /* setMaxNum :241 default -1 */
+  MPLB_TOL_POS = 8, /* setTol    :255-265 */
+  MPLB_TOL_VEL = 9,
+  MPLB_TOL_ACC = 10,
+  MPLB_T_MAX = 11,  /* setTmax   :203 (accepted, ignored exactly like env_map::is_goal does, env_map.h:25-45) */
+  MPLB_MEM_FRACTION = 100 /* fraction of free device memory the search arenas may take (default 0.6) */
+};
+int mplb_planner_set_param(mplb_planner *p, int key, double value);
+/* setU (planner_base.h:246): n rows of udim (= Dim) doubles; the row index is the action id. */
+int mplb_planner_set_controls(mplb_planner *p, const double *U, int n, int udim);
+
+/* plan (planner_base.h:275-325).  Returns MPLB_OK when the call itself worked; the reference's bool is
+ * (out->status == MPLB_PLAN_OK || out->status == MPLB_PLAN_START_IS_GOAL).  The search state of this plan
+ * stays on the device until the next plan/plan_batch on this handle, for the getters below. */
+int mplb_plan(mplb_planner *p, const mplb_waypoint *start, const mplb_waypoint *goal, mplb_result *out);
+
+/* Batch of independent plans on one map (north-star extension; each entry behaves exactly like mplb_plan).
+ * HOST buffers: starts/goals [n]; results [n]; actions [n*max_seg] int32 (trajectory action ids, -1 padded;
+ * may be NULL); seg_states [n*max_seg*13] doubles (stored coord of each segment's parent node, the argument
+ * of env_base::forward_action, env_base.h:228-231; may be NULL).  Plans whose n_seg > max_seg report the
+ * true n_seg and only the first max_seg entries. */
+int mplb_plan_batch(mplb_planner *p, const mplb_waypoint *starts, const mplb_waypoint *goals, int n,
+                    mplb_result *results, int32_t *actions, double *seg_states, int max_seg);
+/* Same with DEVICE buffers on the planner's device; asynchronous launches are ordered on `stream`
+ * (cudaStream_t as void*, NULL = default) and the call returns after the batch has completed. */
+int mplb_plan_batch_device(mplb_planner *p, const void *d_starts, const void *d_goals, int n, void *d_results,
+                           void *d_actions, void *d_seg_states, int max_seg, void *stream);
+
+/* Result getters of the retained single plan (two-call pattern: pass cap = 0 to get the size). */
+int mplb_get_actions(mplb_planner *p, int32_t *actions, int cap);      /* returns n_seg; recoverTraj graph_search.h:369-455 */
+int mplb_get_seg_states(mplb_planner *p, double *states13, int cap);   /* returns n_seg */
+int mplb_get_nodes(mplb_planner *p, mplb_node *nodes, int cap);        /* returns n_nodes; hm_ iteration (unordered) */
+int mplb_get_pop_log(mplb_planner *p, int32_t *node_ids, int cap);     /* returns pops; expanded_nodes_ order, env_map.h:154 */
+int mplb_get_open(mplb_planner *p, int32_t *node_ids, int cap);        /* returns n_open; pq_ iteration */
+
+/* env_map::get_succ (env_map.h:147-172) for n arbitrary states: rows [n * |U|]. HOST buffers. */
+int mplb_expand(mplb_planner *p, const mplb_waypoint *states, int n, mplb_prim_trace *rows);
+
+/* Timing/diagnostics of the last batch on this planner: ms = device time of the search kernels (CUDA events on
+ * the launch stream), launches = kernels launched, tiers = arena tiers used. Any pointer may be NULL. */
+int mplb_last_batch_stats(mplb_planner *p, double *kernel_ms, int32_t *launches, int32_t *tiers);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

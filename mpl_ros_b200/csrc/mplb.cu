@@ -1,0 +1,807 @@
+/*
+ * mplb.cu — host runtime + C ABI of libmplb.so (see include/mplb.h).
+ *
+ * Host side of the drop-in boundary: map objects (MapUtil, map_util.h), planner objects
+ * (PlannerBase / MapPlanner, planner_base.h, map_planner.cpp:6-18), batch orchestration over arena tiers,
+ * and result getters.  All compute runs in the sm_100a kernels of mplb_search.cuh; there is no CPU path.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mplb.h"
+#include "mplb_search.cuh"
+
+using namespace mplb;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(MPLB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+
+template <typename T>
+struct DevBuf { /* grow-only device buffer */
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t reserve(size_t want) {
+    if (want <= n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+    if (e == cudaSuccess) n = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+/* ------------------------------------------------------------------ map kernels */
+__global__ void k_free_unknown(int8_t *g, size_t n) { /* mu:259-276 */
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    if (g[i] == -1) g[i] = 0;
+}
+
+/* mu:221-257: out = in; every neighbour offset of an occupied cell becomes occupied (writes race benignly: same value) */
+__global__ void k_dilate(const int8_t *in, int8_t *out, int dim, int nx, int ny, int nz, const int *ns, int n_ns) {
+  size_t total = (size_t)nx * ny * nz;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    if (in[i] != 100) continue;
+    int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((size_t)nx * ny));
+    for (int k = 0; k < n_ns; k++) {
+      int xx = x + ns[k * dim], yy = y + ns[k * dim + 1], zz = dim == 3 ? z + ns[k * dim + 2] : 0;
+      if (xx < 0 || xx >= nx || yy < 0 || yy >= ny || zz < 0 || zz >= nz) continue;
+      out[(size_t)xx + (size_t)nx * yy + (size_t)nx * ny * zz] = 100;
+    }
+  }
+}
+
+/* Pack occupancy (value == 100, mu:48) into 64-bit bricks: 4x4x4 voxels (3D) / 8x8 cells (2D) per word. */
+__global__ void k_build_bricks(const int8_t *g, unsigned long long *bricks, int dim, int nx, int ny, int nz, int bx, int by,
+                               int bz) {
+  size_t nb = (size_t)bx * by * bz;
+  for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
+    int ix = (int)(b % bx), iy = (int)((b / bx) % by), iz = (int)(b / ((size_t)bx * by));
+    unsigned long long w = 0;
+    if (dim == 3) {
+      for (int bit = 0; bit < 64; bit++) {
+        int x = ix * 4 + (bit & 3), y = iy * 4 + ((bit >> 2) & 3), z = iz * 4 + (bit >> 4);
+        if (x < nx && y < ny && z < nz && g[(size_t)x + (size_t)nx * y + (size_t)nx * ny * z] == 100) w |= 1ull << bit;
+      }
+    } else {
+      for (int bit = 0; bit < 64; bit++) {
+        int x = ix * 8 + (bit & 7), y = iy * 8 + (bit >> 3);
+        if (x < nx && y < ny && g[(size_t)x + (size_t)nx * y] == 100) w |= 1ull << bit;
+      }
+    }
+    bricks[b] = w;
+  }
+}
+
+}  // namespace
+
+/* ================================================================== objects */
+struct mplb_map {
+  int dim = 3;
+  int nd[3] = {1, 1, 1};
+  int bd[3] = {1, 1, 1};
+  double origin[3] = {0, 0, 0};
+  double res = 1;
+  size_t ncell = 0, nbrick = 0;
+  int device = 0;
+  int8_t *d_grid = nullptr;
+  unsigned long long *d_bricks = nullptr;
+  unsigned long long version = 0;
+
+  int rebuild_bricks(cudaStream_t s) {
+    int blocks = (int)std::min<size_t>((nbrick + 255) / 256, 148 * 16);
+    k_build_bricks<<<blocks, 256, 0, s>>>(d_grid, d_bricks, dim, nd[0], nd[1], nd[2], bd[0], bd[1], bd[2]);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    version++;
+    return MPLB_OK;
+  }
+};
+
+struct mplb_planner {
+  int dim = 3;
+  int verbose = 0;
+  int device = 0;
+  mplb_map *map = nullptr;
+  /* env_base defaults eb:368-392, planner defaults pb:337-339 */
+  double v_max = -1, a_max = -1, j_max = -1, yaw_max = -1, dt = 1.0, w = 10.0, eps = 1.0;
+  double tol_pos = 0.5, tol_vel = -1, tol_acc = -1, t_max = INFINITY;
+  int max_num = -1;
+  double mem_fraction = 0.6;
+  std::vector<double> U; /* nU x 3 */
+  int nU = 0;
+
+  /* device-side configuration, rebuilt when dirty */
+  bool dirty = true;
+  int cfg_control = 0;
+  unsigned long long cfg_map_version = ~0ull;
+  DevCfg cfg;
+  DevBuf<double> d_U, d_ttab;
+  DevBuf<int> d_toff, d_tcnt;
+  int kfields = 0;
+
+  /* scratch */
+  DevBuf<unsigned char> arena;
+  DevBuf<int> d_ctrl; /* [0] work counter, [1] overflow count */
+  DevBuf<int> d_work, d_over, d_slot;
+  DevBuf<mplb_waypoint> d_starts, d_goals;
+  DevBuf<mplb_result> d_results;
+  DevBuf<int> d_actions;
+  DevBuf<double> d_segs;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  /* last batch */
+  double last_ms = 0;
+  int last_launches = 0, last_tiers = 0;
+  /* retained single plan */
+  bool retained = false;
+  mplb_result ret_result;
+  int ret_cap = 0, ret_ns = 0, ret_slot = 0;
+  size_t ret_stride = 0, ret_off_state = 0, ret_off_heap = 0, ret_off_poplog = 0;
+  std::vector<int> ret_actions;
+  std::vector<double> ret_segs;
+};
+
+namespace {
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Layout {
+  size_t off_state, off_heap, off_table, off_poplog, stride;
+  int tsize_max;
+};
+
+Layout make_layout(int cap, int ns, int nU) {
+  Layout L;
+  int ts = 1024;
+  while ((long long)ts < 2ll * (cap + nU)) ts <<= 1;
+  L.tsize_max = ts;
+  size_t o = 0;
+  o += align_up((size_t)cap * sizeof(NodeHot), 256);
+  L.off_state = o;
+  o += align_up((size_t)cap * ns * sizeof(double), 256);
+  L.off_heap = o;
+  o += align_up((size_t)cap * sizeof(HeapEnt), 256);
+  L.off_table = o;
+  o += align_up((size_t)ts * sizeof(unsigned long long), 256);
+  L.off_poplog = o;
+  o += align_up((size_t)cap * sizeof(int), 256);
+  L.stride = o;
+  return L;
+}
+
+int control_order(int control) {
+  switch (control) {
+    case MPLB_CONTROL_VEL: return 1;
+    case MPLB_CONTROL_ACC: return 2;
+    case MPLB_CONTROL_JRK: return 3;
+    case MPLB_CONTROL_SNP: return 4;
+    default: return 0;
+  }
+}
+
+int bits_for(long long range) {
+  int b = 1;
+  while ((1ll << b) < range) b++;
+  return b;
+}
+
+/* Build the device configuration: control table, sample-time tables (em:95-99), key packing. */
+int build_cfg(mplb_planner *p, int control) {
+  if (!p->map) return fail(MPLB_ERR_STATE, "planner has no map (setMapUtil not called)");
+  if (p->nU <= 0) return fail(MPLB_ERR_STATE, "planner has no control set (setU not called)");
+  if (p->nU > MPLB_MAXU) return fail(MPLB_ERR_ARG, "more than 128 controls are not supported");
+  int ord = control_order(control);
+  if (ord == 0) return fail(MPLB_ERR_ARG, "unsupported control flag on the start waypoint (yaw controls are out of scope)");
+  if (p->map->dim != p->dim) return fail(MPLB_ERR_ARG, "map dimension does not match planner dimension");
+  if (!(p->dt > 0)) return fail(MPLB_ERR_ARG, "dt must be > 0");
+  if (ord >= 2 && !(p->v_max > 0))
+    return fail(MPLB_ERR_ARG, "v_max must be > 0 for ACC/JRK/SNP controls (the sample divisor of env_map.h:95 is unbounded otherwise)");
+  if (p->tol_vel >= 0 && ord < 2) return fail(MPLB_ERR_ARG, "tol_vel >= 0 needs a control order with velocity in the state");
+  if (p->tol_acc >= 0 && ord < 3) return fail(MPLB_ERR_ARG, "tol_acc >= 0 needs a control order with acceleration in the state");
+  if (!p->dirty && p->cfg_control == control && p->cfg_map_version == p->map->version) return MPLB_OK;
+
+  mplb_map *m = p->map;
+  DevCfg &c = p->cfg;
+  std::memset(&c, 0, sizeof(c));
+  c.dim = p->dim; c.ord = ord; c.control = control; c.nU = p->nU; c.ns = p->dim * ord;
+  c.max_num = p->max_num;
+  c.dt = p->dt; c.w = p->w; c.eps = p->eps; c.v_max = p->v_max; c.a_max = p->a_max; c.j_max = p->j_max;
+  c.tol_pos = p->tol_pos; c.tol_vel = p->tol_vel; c.tol_acc = p->tol_acc;
+  for (int i = 0; i < 3; i++) { c.nd[i] = m->nd[i]; c.bd[i] = m->bd[i]; c.origin[i] = m->origin[i]; }
+  c.res = m->res;
+  c.grid = m->d_grid;
+  c.bricks = m->d_bricks;
+
+  /* controls */
+  CUDA_TRY(p->d_U.reserve((size_t)p->nU * 3));
+  CUDA_TRY(cudaMemcpy(p->d_U.p, p->U.data(), (size_t)p->nU * 3 * sizeof(double), cudaMemcpyHostToDevice));
+  c.U = p->d_U.p;
+  double umax = 0;
+  for (double u : p->U) umax = std::max(umax, std::fabs(u));
+  double vmax_eff = ord >= 2 ? p->v_max : umax;
+
+  /* sample-time tables: exactly the reference loop `for (t = 0; t < T; t += T/n)` for every divisor n */
+  int n_hi = std::max(5, (int)std::ceil(vmax_eff * p->dt / m->res)) + 1;
+  if (n_hi > 4096) return fail(MPLB_ERR_ARG, "v_max*dt/res is too large (more than 4096 samples per primitive)");
+  std::vector<double> ttab;
+  std::vector<int> toff(n_hi + 1, 0), tcnt(n_hi + 1, 0);
+  for (int n = 5; n <= n_hi; n++) {
+    toff[n] = (int)ttab.size();
+    double dts = p->dt / n;
+    int cnt = 0;
+    for (double t = 0; t < p->dt; t += dts) { ttab.push_back(t); cnt++; }
+    tcnt[n] = cnt;
+  }
+  CUDA_TRY(p->d_ttab.reserve(ttab.size()));
+  CUDA_TRY(p->d_toff.reserve(toff.size()));
+  CUDA_TRY(p->d_tcnt.reserve(tcnt.size()));
+  CUDA_TRY(cudaMemcpy(p->d_ttab.p, ttab.data(), ttab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(p->d_toff.p, toff.data(), toff.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(p->d_tcnt.p, tcnt.data(), tcnt.size() * sizeof(int), cudaMemcpyHostToDevice));
+  c.ttab = p->d_ttab.p; c.toff = p->d_toff.p; c.tcnt = p->d_tcnt.p; c.n_hi = n_hi;
+
+  /* key packing: field f = axis*ord + d; pos fields cover the map plus a margin (end states are not collision
+   * tested at t = T, em:99), derivative fields cover their dynamic bound (validated primitives, pr:449-496). */
+  double margin = std::max(2.0, 2.0 * vmax_eff * p->dt);
+  double bounds[4] = {0, p->v_max, p->a_max, p->j_max};
+  int bitpos = 0;
+  for (int ax = 0; ax < p->dim; ax++) {
+    for (int d = 0; d < ord; d++) {
+      int f = ax * ord + d;
+      long long lo, hi;
+      if (d == 0) {
+        lo = (long long)std::floor((m->origin[ax] - margin) / 0.01) - 2;
+        hi = (long long)std::ceil((m->origin[ax] + m->nd[ax] * m->res + margin) / 0.01) + 2;
+      } else {
+        double B = bounds[d] > 0 ? bounds[d] : 100.0;
+        hi = (long long)std::ceil(B / 0.1) + 2;
+        lo = -hi;
+      }
+      int bits = bits_for(hi - lo + 1);
+      if (bits > 31) return fail(MPLB_ERR_ARG, "lattice key field too wide");
+      int word = bitpos / 64;
+      if ((bitpos % 64) + bits > 64) { word++; bitpos = word * 64; }
+      if (word > 1) return fail(MPLB_ERR_ARG, "lattice key does not fit 128 bits for this map / bounds");
+      c.koff[f] = (int)lo; c.kbits[f] = (unsigned char)bits; c.kshift[f] = (unsigned char)(bitpos % 64);
+      c.kword[f] = (unsigned char)word;
+      bitpos += bits;
+    }
+  }
+  p->kfields = p->dim * ord;
+  p->cfg_control = control;
+  p->cfg_map_version = m->version;
+  p->dirty = false;
+  return MPLB_OK;
+}
+
+template <int DIM, int ORD>
+int launch_batch(const DevCfg &c, const BatchArgs &a, int grid, cudaStream_t s) {
+  size_t smem = sizeof(PlanSmem<DIM, ORD>);
+  auto kern = astar_batch_kernel<DIM, ORD>;
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, MPLB_NT, smem, s>>>(c, a);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MPLB_OK;
+}
+
+template <int DIM, int ORD>
+int resident_ctas(int device) {
+  int per_sm = 0, sms = 0;
+  size_t smem = sizeof(PlanSmem<DIM, ORD>);
+  auto kern = astar_batch_kernel<DIM, ORD>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MPLB_NT, smem) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+  return per_sm * sms;
+}
+
+#define DISPATCH(dim, ord, CALL)                                                              \
+  do {                                                                                        \
+    if (dim == 2 && ord == 1) { CALL(2, 1); } else if (dim == 2 && ord == 2) { CALL(2, 2); }  \
+    else if (dim == 2 && ord == 3) { CALL(2, 3); } else if (dim == 2 && ord == 4) { CALL(2, 4); } \
+    else if (dim == 3 && ord == 1) { CALL(3, 1); } else if (dim == 3 && ord == 2) { CALL(3, 2); } \
+    else if (dim == 3 && ord == 3) { CALL(3, 3); } else { CALL(3, 4); }                       \
+  } while (0)
+
+/* Core: device-resident batch over arena tiers. */
+int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoint *d_goals, int n, mplb_result *d_results,
+              int *d_actions, double *d_segs, int max_seg, int control, bool retain, cudaStream_t s) {
+  int rc = build_cfg(p, control);
+  if (rc != MPLB_OK) return rc;
+  const DevCfg &c = p->cfg;
+  p->retained = false;
+  if (!p->ev0) { CUDA_TRY(cudaEventCreate(&p->ev0)); CUDA_TRY(cudaEventCreate(&p->ev1)); }
+  CUDA_TRY(p->d_ctrl.reserve(2));
+  CUDA_TRY(p->d_over.reserve((size_t)n));
+  CUDA_TRY(p->d_work.reserve((size_t)n));
+  if (retain) CUDA_TRY(p->d_slot.reserve((size_t)n));
+
+  int resident = 0;
+#define RES_CALL(D, O) resident = resident_ctas<D, O>(p->device)
+  DISPATCH(c.dim, c.ord, RES_CALL);
+  if (resident <= 0) return fail(MPLB_ERR_CUDA, "no resident CTA for the search kernel (is this an sm_100 device?)");
+
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = (size_t)((double)(free_b + p->arena.n) * p->mem_fraction);
+
+  int n_work = n;
+  bool identity = true;
+  int cap = 32768;
+  p->last_launches = 0; p->last_tiers = 0;
+  CUDA_TRY(cudaEventRecord(p->ev0, s));
+  while (n_work > 0) {
+    Layout L = make_layout(cap, c.ns, c.nU);
+    int slots = std::min(n_work, resident);
+    if ((size_t)slots * L.stride > budget) slots = (int)(budget / L.stride);
+    if (slots <= 0) { /* nothing larger fits: the remaining plans report NOMEM (their overflow status is rewritten) */
+      std::vector<int> ids(n_work);
+      CUDA_TRY(cudaMemcpyAsync(ids.data(), p->d_work.p, n_work * sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      for (int id : ids) {
+        int st = MPLB_PLAN_NOMEM;
+        CUDA_TRY(cudaMemcpyAsync(&d_results[id].status, &st, sizeof(int), cudaMemcpyHostToDevice, s));
+      }
+      CUDA_TRY(cudaStreamSynchronize(s));
+      break;
+    }
+    if (p->arena.n < (size_t)slots * L.stride) {
+      CUDA_TRY(cudaStreamSynchronize(s));
+      if (p->arena.reserve((size_t)slots * L.stride) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MPLB_ERR_NOMEM, "cannot allocate the search arena");
+      }
+    }
+    CUDA_TRY(cudaMemsetAsync(p->d_ctrl.p, 0, 2 * sizeof(int), s));
+    BatchArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.starts = d_starts; a.goals = d_goals; a.results = d_results; a.actions = d_actions; a.seg_states = d_segs;
+    a.max_seg = max_seg; a.work = identity ? nullptr : p->d_work.p; a.n_work = n_work;
+    a.work_counter = p->d_ctrl.p; a.arena = p->arena.p; a.stride = L.stride; a.cap = cap; a.tsize_max = L.tsize_max;
+    a.off_state = L.off_state; a.off_heap = L.off_heap; a.off_table = L.off_table; a.off_poplog = L.off_poplog;
+    a.want_poplog = retain ? 1 : 0; a.slot_of_plan = retain ? p->d_slot.p : nullptr;
+    a.overflow_count = p->d_ctrl.p + 1; a.overflow_list = p->d_over.p;
+#define LAUNCH_CALL(D, O) rc = launch_batch<D, O>(c, a, slots, s)
+    DISPATCH(c.dim, c.ord, LAUNCH_CALL);
+    if (rc != MPLB_OK) return rc;
+    p->last_launches++; p->last_tiers++;
+    int n_over = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n_over, p->d_ctrl.p + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (retain && n == 1 && n_over == 0) {
+      p->ret_cap = cap; p->ret_ns = c.ns; p->ret_stride = L.stride; p->ret_off_state = L.off_state;
+      p->ret_off_heap = L.off_heap; p->ret_off_poplog = L.off_poplog;
+    }
+    if (n_over == 0) break;
+    /* next tier: overflowed plans restart from scratch (the search is deterministic) with 8x the arena */
+    std::swap(p->d_work, p->d_over);
+    n_work = n_over;
+    identity = false;
+    if (cap > (1 << 27)) { cap = 1 << 30; continue; }
+    cap *= 8;
+  }
+  CUDA_TRY(cudaEventRecord(p->ev1, s));
+  CUDA_TRY(cudaEventSynchronize(p->ev1));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+  p->last_ms = ms;
+  return MPLB_OK;
+}
+
+int set_device_of(int device) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess) return -1;
+  if (cur != device && cudaSetDevice(device) != cudaSuccess) return -1;
+  return 0;
+}
+
+int map_alloc(int dim, const int32_t *ndim, const double *origin, double res, mplb_map **out) {
+  if (!out || !ndim || !origin) return fail(MPLB_ERR_ARG, "null argument");
+  if (dim != 2 && dim != 3) return fail(MPLB_ERR_ARG, "dim must be 2 or 3");
+  if (!(res > 0)) return fail(MPLB_ERR_ARG, "resolution must be > 0");
+  mplb_map *m = new mplb_map();
+  m->dim = dim;
+  m->res = res;
+  size_t n = 1;
+  for (int i = 0; i < dim; i++) {
+    if (ndim[i] <= 0) { delete m; return fail(MPLB_ERR_ARG, "map dimensions must be positive"); }
+    m->nd[i] = ndim[i];
+    m->origin[i] = origin[i];
+    n *= (size_t)ndim[i];
+  }
+  if (n > 0x7fffffffull) { delete m; return fail(MPLB_ERR_ARG, "more than 2^31-1 cells (the reference indexes cells with int, map_util.h:33-41)"); }
+  m->ncell = n;
+  if (dim == 3) { m->bd[0] = (m->nd[0] + 3) / 4; m->bd[1] = (m->nd[1] + 3) / 4; m->bd[2] = (m->nd[2] + 3) / 4; }
+  else { m->bd[0] = (m->nd[0] + 7) / 8; m->bd[1] = (m->nd[1] + 7) / 8; m->bd[2] = 1; }
+  m->nbrick = (size_t)m->bd[0] * m->bd[1] * m->bd[2];
+  if (cudaGetDevice(&m->device) != cudaSuccess) { delete m; return fail(MPLB_ERR_CUDA, "no CUDA device (libmplb has no CPU path)"); }
+  if (cudaMalloc((void **)&m->d_grid, n) != cudaSuccess || cudaMalloc((void **)&m->d_bricks, m->nbrick * 8) != cudaSuccess) {
+    std::string e = cudaGetErrorString(cudaGetLastError());
+    if (m->d_grid) cudaFree(m->d_grid);
+    delete m;
+    return fail(MPLB_ERR_CUDA, "cudaMalloc(map): " + e);
+  }
+  *out = m;
+  return MPLB_OK;
+}
+
+}  // namespace
+
+/* ================================================================== C ABI */
+extern "C" {
+
+const char *mplb_last_error(void) { return g_err.c_str(); }
+
+int mplb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int64_t mplb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int mplb_map_create(int dim, const int32_t *ndim, const double *origin, double res, const int8_t *data, mplb_map **out) {
+  if (!data) return fail(MPLB_ERR_ARG, "null map data");
+  mplb_map *m = nullptr;
+  int rc = map_alloc(dim, ndim, origin, res, &m);
+  if (rc != MPLB_OK) return rc;
+  if (cudaMemcpy(m->d_grid, data, m->ncell, cudaMemcpyHostToDevice) != cudaSuccess) {
+    std::string e = cudaGetErrorString(cudaGetLastError());
+    mplb_map_destroy(m);
+    return fail(MPLB_ERR_CUDA, "cudaMemcpy(map): " + e);
+  }
+  rc = m->rebuild_bricks(0);
+  if (rc != MPLB_OK) { mplb_map_destroy(m); return rc; }
+  CUDA_TRY(cudaStreamSynchronize(0));
+  *out = m;
+  return MPLB_OK;
+}
+
+int mplb_map_create_from_device(int dim, const int32_t *ndim, const double *origin, double res, const void *dev_data,
+                                void *stream, mplb_map **out) {
+  if (!dev_data) return fail(MPLB_ERR_ARG, "null device map data");
+  mplb_map *m = nullptr;
+  int rc = map_alloc(dim, ndim, origin, res, &m);
+  if (rc != MPLB_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemcpyAsync(m->d_grid, dev_data, m->ncell, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+    std::string e = cudaGetErrorString(cudaGetLastError());
+    mplb_map_destroy(m);
+    return fail(MPLB_ERR_CUDA, "cudaMemcpyAsync(map d2d): " + e);
+  }
+  rc = m->rebuild_bricks(s);
+  if (rc != MPLB_OK) { mplb_map_destroy(m); return rc; }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  *out = m;
+  return MPLB_OK;
+}
+
+int mplb_map_free_unknown(mplb_map *m) {
+  if (!m) return fail(MPLB_ERR_ARG, "null map");
+  if (set_device_of(m->device)) return fail(MPLB_ERR_CUDA, "cannot select the map's device");
+  int blocks = (int)std::min<size_t>((m->ncell + 255) / 256, 148 * 16);
+  k_free_unknown<<<blocks, 256>>>(m->d_grid, m->ncell);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  int rc = m->rebuild_bricks(0);
+  if (rc != MPLB_OK) return rc;
+  CUDA_TRY(cudaStreamSynchronize(0));
+  return MPLB_OK;
+}
+
+int mplb_map_dilate(mplb_map *m, const int32_t *ns, int n) {
+  if (!m || (n > 0 && !ns)) return fail(MPLB_ERR_ARG, "null argument");
+  if (n <= 0) return MPLB_OK;
+  if (set_device_of(m->device)) return fail(MPLB_ERR_CUDA, "cannot select the map's device");
+  int8_t *tmp = nullptr;
+  int *d_ns = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&tmp, m->ncell));
+  CUDA_TRY(cudaMalloc((void **)&d_ns, (size_t)n * m->dim * sizeof(int)));
+  CUDA_TRY(cudaMemcpy(d_ns, ns, (size_t)n * m->dim * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(tmp, m->d_grid, m->ncell, cudaMemcpyDeviceToDevice));
+  int blocks = (int)std::min<size_t>((m->ncell + 255) / 256, 148 * 16);
+  k_dilate<<<blocks, 256>>>(tmp, m->d_grid, m->dim, m->nd[0], m->nd[1], m->nd[2], d_ns, n);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  int rc = m->rebuild_bricks(0);
+  CUDA_TRY(cudaStreamSynchronize(0));
+  cudaFree(tmp);
+  cudaFree(d_ns);
+  return rc;
+}
+
+int mplb_map_get_info(const mplb_map *m, int32_t *dim, int32_t *ndim, double *origin, double *res) {
+  if (!m) return fail(MPLB_ERR_ARG, "null map");
+  if (dim) *dim = m->dim;
+  for (int i = 0; i < m->dim; i++) { if (ndim) ndim[i] = m->nd[i]; if (origin) origin[i] = m->origin[i]; }
+  if (res) *res = m->res;
+  return MPLB_OK;
+}
+
+int mplb_map_get_data(const mplb_map *m, int8_t *out, size_t cap) {
+  if (!m || !out) return fail(MPLB_ERR_ARG, "null argument");
+  if (cap < m->ncell) return fail(MPLB_ERR_ARG, "output buffer smaller than the map");
+  if (set_device_of(m->device)) return fail(MPLB_ERR_CUDA, "cannot select the map's device");
+  CUDA_TRY(cudaMemcpy(out, m->d_grid, m->ncell, cudaMemcpyDeviceToHost));
+  return MPLB_OK;
+}
+
+void mplb_map_destroy(mplb_map *m) {
+  if (!m) return;
+  if (m->d_grid) cudaFree(m->d_grid);
+  if (m->d_bricks) cudaFree(m->d_bricks);
+  delete m;
+}
+
+int mplb_planner_create(int dim, int verbose, mplb_planner **out) {
+  if (!out) return fail(MPLB_ERR_ARG, "null argument");
+  if (dim != 2 && dim != 3) return fail(MPLB_ERR_ARG, "dim must be 2 or 3");
+  mplb_planner *p = new mplb_planner();
+  p->dim = dim;
+  p->verbose = verbose;
+  if (cudaGetDevice(&p->device) != cudaSuccess) { delete p; return fail(MPLB_ERR_CUDA, "no CUDA device (libmplb has no CPU path)"); }
+  if (verbose) std::printf("[MapPlanner] PLANNER VERBOSE ON\n");
+  *out = p;
+  return MPLB_OK;
+}
+
+void mplb_planner_destroy(mplb_planner *p) {
+  if (!p) return;
+  p->d_U.release(); p->d_ttab.release(); p->d_toff.release(); p->d_tcnt.release(); p->arena.release();
+  p->d_ctrl.release(); p->d_work.release(); p->d_over.release(); p->d_slot.release(); p->d_starts.release();
+  p->d_goals.release(); p->d_results.release(); p->d_actions.release(); p->d_segs.release();
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
+  delete p;
+}
+
+int mplb_planner_set_map(mplb_planner *p, mplb_map *m) {
+  if (!p || !m) return fail(MPLB_ERR_ARG, "null argument");
+  if (m->dim != p->dim) return fail(MPLB_ERR_ARG, "map dimension does not match planner dimension");
+  if (m->device != p->device) return fail(MPLB_ERR_ARG, "map and planner live on different devices");
+  p->map = m;
+  p->dirty = true;
+  p->retained = false;
+  return MPLB_OK;
+}
+
+int mplb_planner_set_param(mplb_planner *p, int key, double v) {
+  if (!p) return fail(MPLB_ERR_ARG, "null planner");
+  switch (key) {
+    case MPLB_V_MAX: p->v_max = v; break;
+    case MPLB_A_MAX: p->a_max = v; break;
+    case MPLB_J_MAX: p->j_max = v; break;
+    case MPLB_YAW_MAX: p->yaw_max = v; break;
+    case MPLB_DT: p->dt = v; break;
+    case MPLB_W: p->w = v; break;
+    case MPLB_EPSILON: p->eps = v; break;
+    case MPLB_MAX_NUM: p->max_num = (int)v; break;
+    case MPLB_TOL_POS: p->tol_pos = v; break;
+    case MPLB_TOL_VEL: p->tol_vel = v; break;
+    case MPLB_TOL_ACC: p->tol_acc = v; break;
+    case MPLB_T_MAX: p->t_max = v; break;
+    case MPLB_MEM_FRACTION:
+      if (!(v > 0 && v <= 0.95)) return fail(MPLB_ERR_ARG, "mem fraction must be in (0, 0.95]");
+      p->mem_fraction = v;
+      break;
+    default: return fail(MPLB_ERR_ARG, "unknown parameter key");
+  }
+  p->dirty = true;
+  if (p->verbose) std::printf("[PlannerBase] set param %d: %f\n", key, v);
+  return MPLB_OK;
+}
+
+int mplb_planner_set_controls(mplb_planner *p, const double *U, int n, int udim) {
+  if (!p || !U) return fail(MPLB_ERR_ARG, "null argument");
+  if (n <= 0 || n > MPLB_MAXU) return fail(MPLB_ERR_ARG, "control set must have 1..128 rows");
+  if (udim != p->dim) return fail(MPLB_ERR_ARG, "control rows must have Dim entries (yaw controls are out of scope)");
+  p->U.assign((size_t)n * 3, 0.0);
+  for (int i = 0; i < n; i++)
+    for (int k = 0; k < udim; k++) p->U[(size_t)i * 3 + k] = U[(size_t)i * udim + k];
+  p->nU = n;
+  p->dirty = true;
+  return MPLB_OK;
+}
+
+int mplb_plan_batch_device(mplb_planner *p, const void *d_starts, const void *d_goals, int n, void *d_results,
+                           void *d_actions, void *d_seg_states, int max_seg, void *stream) {
+  if (!p || !d_starts || !d_goals || !d_results) return fail(MPLB_ERR_ARG, "null argument");
+  if (n <= 0) return MPLB_OK;
+  if ((d_actions || d_seg_states) && max_seg <= 0) return fail(MPLB_ERR_ARG, "max_seg must be > 0 when trajectories are requested");
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  cudaStream_t s = (cudaStream_t)stream;
+  int control = 0; /* the control mode is a property of the start waypoint (waypoint.h:46-55) */
+  CUDA_TRY(cudaMemcpyAsync(&control, (const char *)d_starts + offsetof(mplb_waypoint, control), sizeof(int),
+                           cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return run_batch(p, (const mplb_waypoint *)d_starts, (const mplb_waypoint *)d_goals, n, (mplb_result *)d_results,
+                   (int *)d_actions, (double *)d_seg_states, max_seg, control, false, s);
+}
+
+static int plan_batch_host(mplb_planner *p, const mplb_waypoint *starts, const mplb_waypoint *goals, int n,
+                           mplb_result *results, int32_t *actions, double *seg_states, int max_seg, bool retain) {
+  if (!p || !starts || !goals || !results) return fail(MPLB_ERR_ARG, "null argument");
+  if (n <= 0) return MPLB_OK;
+  if ((actions || seg_states) && max_seg <= 0) return fail(MPLB_ERR_ARG, "max_seg must be > 0 when trajectories are requested");
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  for (int i = 0; i < n; i++) {
+    if (starts[i].control != starts[0].control) return fail(MPLB_ERR_ARG, "all starts of a batch must share one control mode");
+    if (starts[i].enable_t) return fail(MPLB_ERR_ARG, "enable_t waypoints are not supported");
+  }
+  cudaStream_t s = 0;
+  CUDA_TRY(p->d_starts.reserve(n));
+  CUDA_TRY(p->d_goals.reserve(n));
+  CUDA_TRY(p->d_results.reserve(n));
+  if (actions) CUDA_TRY(p->d_actions.reserve((size_t)n * max_seg));
+  if (seg_states) CUDA_TRY(p->d_segs.reserve((size_t)n * max_seg * 13));
+  CUDA_TRY(cudaMemcpyAsync(p->d_starts.p, starts, (size_t)n * sizeof(mplb_waypoint), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(p->d_goals.p, goals, (size_t)n * sizeof(mplb_waypoint), cudaMemcpyHostToDevice, s));
+  int rc = run_batch(p, p->d_starts.p, p->d_goals.p, n, p->d_results.p, actions ? p->d_actions.p : nullptr,
+                     seg_states ? p->d_segs.p : nullptr, max_seg, starts[0].control, retain, s);
+  if (rc != MPLB_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(results, p->d_results.p, (size_t)n * sizeof(mplb_result), cudaMemcpyDeviceToHost, s));
+  if (actions) CUDA_TRY(cudaMemcpyAsync(actions, p->d_actions.p, (size_t)n * max_seg * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (seg_states)
+    CUDA_TRY(cudaMemcpyAsync(seg_states, p->d_segs.p, (size_t)n * max_seg * 13 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (int i = 0; i < n; i++)
+    if (results[i].status == MPLB_INTERNAL_BADCTRL) return fail(MPLB_ERR_ARG, "a start waypoint has a different control mode");
+  return MPLB_OK;
+}
+
+int mplb_plan_batch(mplb_planner *p, const mplb_waypoint *starts, const mplb_waypoint *goals, int n, mplb_result *results,
+                    int32_t *actions, double *seg_states, int max_seg) {
+  return plan_batch_host(p, starts, goals, n, results, actions, seg_states, max_seg, false);
+}
+
+int mplb_plan(mplb_planner *p, const mplb_waypoint *start, const mplb_waypoint *goal, mplb_result *out) {
+  if (!p || !start || !goal || !out) return fail(MPLB_ERR_ARG, "null argument");
+  const int max_seg = 4096;
+  p->ret_actions.assign(max_seg, -1);
+  p->ret_segs.assign((size_t)max_seg * 13, 0.0);
+  int rc = plan_batch_host(p, start, goal, 1, out, p->ret_actions.data(), p->ret_segs.data(), max_seg, true);
+  if (rc != MPLB_OK) return rc;
+  p->ret_result = *out;
+  p->ret_slot = 0;
+  CUDA_TRY(cudaMemcpy(&p->ret_slot, p->d_slot.p, sizeof(int), cudaMemcpyDeviceToHost));
+  p->retained = true;
+  if (p->verbose) {
+    if (out->status == MPLB_PLAN_START_NOT_FREE) std::printf("[PlannerBase] start is not free!\n");
+    else if (out->status == MPLB_PLAN_MAX_EXPAND) std::printf("MaxExpandStep [%d] Reached!!!!!!\n\n", p->max_num);
+    else if (out->status == MPLB_PLAN_QUEUE_EMPTY) std::printf("Priority queue is empty!!!!!!\n\n");
+    else if (out->status == MPLB_PLAN_OK) std::printf("Reached Goal !!!!!!\n\nExpand [%d] nodes!\n", out->pops);
+    if (out->status != MPLB_PLAN_OK && out->status != MPLB_PLAN_START_IS_GOAL) std::printf("[PlannerBase] Cannot find a traj!\n");
+  }
+  return MPLB_OK;
+}
+
+int mplb_get_actions(mplb_planner *p, int32_t *actions, int cap) {
+  if (!p || !p->retained) return fail(MPLB_ERR_STATE, "no retained plan");
+  int n = p->ret_result.n_seg;
+  for (int i = 0; i < n && i < cap && actions; i++) actions[i] = p->ret_actions[i];
+  return n;
+}
+
+int mplb_get_seg_states(mplb_planner *p, double *states13, int cap) {
+  if (!p || !p->retained) return fail(MPLB_ERR_STATE, "no retained plan");
+  int n = p->ret_result.n_seg;
+  for (int i = 0; i < n && i < cap && states13; i++) std::memcpy(states13 + (size_t)i * 13, &p->ret_segs[(size_t)i * 13], 13 * sizeof(double));
+  return n;
+}
+
+int mplb_get_nodes(mplb_planner *p, mplb_node *nodes, int cap) {
+  if (!p || !p->retained) return fail(MPLB_ERR_STATE, "no retained plan");
+  int n = p->ret_result.n_nodes;
+  if (!nodes || cap <= 0) return n;
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  int m = std::min(n, cap);
+  std::vector<NodeHot> hot(m);
+  std::vector<double> st((size_t)m * p->ret_ns);
+  unsigned char *base = p->arena.p + (size_t)p->ret_slot * p->ret_stride;
+  CUDA_TRY(cudaMemcpy(hot.data(), base, (size_t)m * sizeof(NodeHot), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(st.data(), base + p->ret_off_state, (size_t)m * p->ret_ns * sizeof(double), cudaMemcpyDeviceToHost));
+  const DevCfg &c = p->cfg;
+  for (int i = 0; i < m; i++) {
+    mplb_node &o = nodes[i];
+    std::memset(&o, 0, sizeof(o));
+    for (int d = 0; d < c.ord; d++)
+      for (int ax = 0; ax < c.dim; ax++) o.state[d * 3 + ax] = st[(size_t)i * p->ret_ns + d * c.dim + ax];
+    o.g = hot[i].g; o.h = hot[i].h;
+    for (int f = 0; f < c.ns; f++) {
+      unsigned long long wv = c.kword[f] ? hot[i].k1 : hot[i].k0;
+      unsigned long long v = (wv >> c.kshift[f]) & ((1ull << c.kbits[f]) - 1ull);
+      o.key[f] = (int)((long long)v + c.koff[f]);
+    }
+    o.key[15] = c.ns;
+    o.opened = (hot[i].flags & 1) ? 1 : 0;
+    o.closed = (hot[i].flags & 2) ? 1 : 0;
+    o.parent = hot[i].parent;
+    o.action = hot[i].action;
+  }
+  return n;
+}
+
+int mplb_get_pop_log(mplb_planner *p, int32_t *node_ids, int cap) {
+  if (!p || !p->retained) return fail(MPLB_ERR_STATE, "no retained plan");
+  int n = std::min(p->ret_result.pops, p->ret_cap);
+  if (!node_ids || cap <= 0) return n;
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  unsigned char *base = p->arena.p + (size_t)p->ret_slot * p->ret_stride;
+  CUDA_TRY(cudaMemcpy(node_ids, base + p->ret_off_poplog, (size_t)std::min(n, cap) * sizeof(int), cudaMemcpyDeviceToHost));
+  return n;
+}
+
+int mplb_get_open(mplb_planner *p, int32_t *node_ids, int cap) {
+  if (!p || !p->retained) return fail(MPLB_ERR_STATE, "no retained plan");
+  int n = p->ret_result.n_open;
+  if (!node_ids || cap <= 0) return n;
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  int m = std::min(n, cap);
+  std::vector<HeapEnt> h(m);
+  unsigned char *base = p->arena.p + (size_t)p->ret_slot * p->ret_stride;
+  CUDA_TRY(cudaMemcpy(h.data(), base + p->ret_off_heap, (size_t)m * sizeof(HeapEnt), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < m; i++) node_ids[i] = h[i].node;
+  return n;
+}
+
+int mplb_expand(mplb_planner *p, const mplb_waypoint *states, int n, mplb_prim_trace *rows) {
+  if (!p || !states || !rows) return fail(MPLB_ERR_ARG, "null argument");
+  if (n <= 0) return MPLB_OK;
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  int rc = build_cfg(p, states[0].control);
+  if (rc != MPLB_OK) return rc;
+  const DevCfg &c = p->cfg;
+  mplb_waypoint *d_s = nullptr;
+  mplb_prim_trace *d_r = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d_s, (size_t)n * sizeof(mplb_waypoint)));
+  CUDA_TRY(cudaMalloc((void **)&d_r, (size_t)n * c.nU * sizeof(mplb_prim_trace)));
+  CUDA_TRY(cudaMemcpy(d_s, states, (size_t)n * sizeof(mplb_waypoint), cudaMemcpyHostToDevice));
+  int grid = std::min(n, 148 * 8);
+#define EXPAND_CALL(D, O)                                                                                   \
+  do {                                                                                                      \
+    size_t smem = sizeof(PlanSmem<D, O>);                                                                   \
+    auto kern = expand_trace_kernel<D, O>;                                                                  \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    kern<<<grid, MPLB_NT, smem>>>(c, d_s, n, d_r);                                                          \
+  } while (0)
+  DISPATCH(c.dim, c.ord, EXPAND_CALL);
+  g_launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(rows, d_r, (size_t)n * c.nU * sizeof(mplb_prim_trace), cudaMemcpyDeviceToHost);
+  cudaFree(d_s);
+  cudaFree(d_r);
+  if (e != cudaSuccess) return fail(MPLB_ERR_CUDA, std::string("expand: ") + cudaGetErrorString(e));
+  return MPLB_OK;
+}
+
+int mplb_last_batch_stats(mplb_planner *p, double *kernel_ms, int32_t *launches, int32_t *tiers) {
+  if (!p) return fail(MPLB_ERR_ARG, "null planner");
+  if (kernel_ms) *kernel_ms = p->last_ms;
+  if (launches) *launches = p->last_launches;
+  if (tiers) *tiers = p->last_tiers;
+  return MPLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,359 @@
+"""Python mirror of the reference's operator surface for the hot path, over the C ABI (include/mplb.h).
+
+Class and method names follow the reference so that tests read like MPL/test/test_planner_2d.cpp and
+mpl_test_node/src/map_planner_node.cpp:
+  MapUtil        motion_primitive_library/include/mpl_collision/map_util.h:20-314
+  Waypoint       include/mpl_basis/waypoint.h:22-58
+  Primitive      include/mpl_basis/primitive.h:205-431   (coefficient rows only; built from (parent, U[a], dt))
+  Trajectory     include/mpl_basis/trajectory.h:42-57,250-292
+  MapPlanner     include/mpl_planner/planner/map_planner.h:20-125 over PlannerBase (common/planner_base.h)
+Everything numerical happens in libmplb.so on the GPU; this file only marshals buffers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MplbError, PARAM, check, lib, ptr  # noqa: F401
+from .maps import ACC, JRK, SNP, VEL  # noqa: F401
+
+PLAN_OK, PLAN_START_NOT_FREE, PLAN_MAX_EXPAND, PLAN_QUEUE_EMPTY, PLAN_TRACEBACK_FAILED, PLAN_START_IS_GOAL = range(6)
+
+
+class Waypoint:
+    """waypoint.h:22-58.  `control` is the 5-bit union of use_pos..use_yaw (control.h:10-20)."""
+
+    def __init__(self, dim, control=0):
+        self.dim = dim
+        self.pos = np.zeros(dim)
+        self.vel = np.zeros(dim)
+        self.acc = np.zeros(dim)
+        self.jrk = np.zeros(dim)
+        self.yaw = 0.0
+        self.t = 0.0
+        self.control = control
+        self.enable_t = False
+
+    def _flag(bit):  # noqa: N805
+        def get(self):
+            return bool(self.control & bit)
+
+        def set_(self, v):
+            self.control = (self.control | bit) if v else (self.control & ~bit)
+        return property(get, set_)
+
+    use_pos, use_vel, use_acc, use_jrk, use_yaw = _flag(1), _flag(2), _flag(4), _flag(8), _flag(16)
+
+    def to_record(self, rec):
+        d = self.dim
+        rec["pos"][:d], rec["vel"][:d], rec["acc"][:d], rec["jrk"][:d] = self.pos, self.vel, self.acc, self.jrk
+        rec["yaw"], rec["t"], rec["control"], rec["enable_t"] = self.yaw, self.t, self.control, int(self.enable_t)
+        return rec
+
+
+def waypoints_array(n):
+    return np.zeros(n, dtype=_lib.WAYPOINT_DTYPE)
+
+
+class Primitive:
+    """primitive.h:205-256: per-axis coefficient rows, highest order first, from (parent state, u, dt)."""
+
+    def __init__(self, dim, control, state13, u, t):
+        self.dim, self.control, self.t_ = dim, control, float(t)
+        order = {VEL: 1, ACC: 2, JRK: 3, SNP: 4}[control]
+        self.coeffs = np.zeros((dim, 6))
+        for k in range(dim):
+            p, v, a, j = state13[k], state13[3 + k], state13[6 + k], state13[9 + k]
+            row = {1: (0, 0, 0, 0, u[k], p), 2: (0, 0, 0, u[k], v, p), 3: (0, 0, u[k], a, v, p),
+                   4: (0, u[k], j, a, v, p)}[order]
+            self.coeffs[k] = row
+
+    def t(self):
+        return self.t_
+
+    def evaluate(self, t):
+        """pos/vel/acc/jrk at t (primitive.h:128-145,321-331), float64 numpy (host convenience only)."""
+        out = Waypoint(self.dim, self.control)
+        for k in range(self.dim):
+            c = self.coeffs[k]
+            out.pos[k] = c[0] / 120 * t ** 5 + c[1] / 24 * t ** 4 + c[2] / 6 * t ** 3 + c[3] / 2 * t * t + c[4] * t + c[5]
+            out.vel[k] = c[0] / 24 * t ** 4 + c[1] / 6 * t ** 3 + c[2] / 2 * t * t + c[3] * t + c[4]
+            out.acc[k] = c[0] / 6 * t ** 3 + c[1] / 2 * t * t + c[2] * t + c[3]
+            out.jrk[k] = c[0] / 2 * t * t + c[1] * t + c[2]
+        return out
+
+
+class Trajectory:
+    """trajectory.h:42-57: piecewise primitives with cumulative taus."""
+
+    def __init__(self, segs=()):
+        self.segs = list(segs)
+        self.taus = [0.0]
+        for pr in self.segs:
+            self.taus.append(pr.t() + self.taus[-1])
+        self.total_t_ = self.taus[-1]
+
+    def getTotalTime(self):
+        return self.total_t_
+
+    def getPrimitives(self):
+        return self.segs
+
+    def getWaypoints(self):  # trajectory.h:277-289
+        ws = []
+        if not self.segs:
+            return ws
+        t = 0.0
+        for seg in self.segs:
+            w = seg.evaluate(0.0)
+            w.t = t
+            ws.append(w)
+            t += seg.t()
+        w = self.segs[-1].evaluate(self.segs[-1].t())
+        w.t = t
+        ws.append(w)
+        return ws
+
+
+class MapUtil:
+    """map_util.h:20-314 — the grid lives on the GPU (int8 cells + occupancy bit-bricks)."""
+
+    def __init__(self, dim):
+        self.dim = dim
+        self._h = None
+
+    def setMap(self, ori, dim, map_, res):  # map_util.h:84-90
+        self._destroy()
+        ori = np.ascontiguousarray(ori, dtype=np.float64)
+        nd = np.ascontiguousarray(dim, dtype=np.int32)
+        data = np.ascontiguousarray(map_, dtype=np.int8).reshape(-1)
+        if data.size != int(np.prod(nd.astype(np.int64))):
+            raise MplbError("map data size does not match dim")
+        h = C.c_void_p()
+        check(lib().mplb_map_create(self.dim, ptr(nd), ptr(ori), float(res), ptr(data), C.byref(h)))
+        self._h = h
+
+    def setMapFromDevice(self, ori, dim, dev_ptr, res, stream=None):
+        """Adopt a grid that already sits in device memory (e.g. after an NCCL broadcast)."""
+        self._destroy()
+        ori = np.ascontiguousarray(ori, dtype=np.float64)
+        nd = np.ascontiguousarray(dim, dtype=np.int32)
+        h = C.c_void_p()
+        check(lib().mplb_map_create_from_device(self.dim, ptr(nd), ptr(ori), float(res), C.c_void_p(int(dev_ptr)),
+                                                C.c_void_p(int(stream) if stream else None), C.byref(h)))
+        self._h = h
+
+    def freeUnknown(self):  # map_util.h:259-276
+        check(lib().mplb_map_free_unknown(self._h))
+
+    def dilate(self, ns):  # map_util.h:221-257
+        ns = np.ascontiguousarray(ns, dtype=np.int32).reshape(-1, self.dim)
+        check(lib().mplb_map_dilate(self._h, ptr(ns), ns.shape[0]))
+
+    def _info(self):
+        d = C.c_int32()
+        nd = np.zeros(3, dtype=np.int32)
+        ori = np.zeros(3, dtype=np.float64)
+        res = C.c_double()
+        check(lib().mplb_map_get_info(self._h, C.byref(d), ptr(nd), ptr(ori), C.byref(res)))
+        return nd[:self.dim].copy(), ori[:self.dim].copy(), res.value
+
+    def getRes(self):
+        return self._info()[2]
+
+    def getDim(self):
+        return self._info()[0]
+
+    def getOrigin(self):
+        return self._info()[1]
+
+    def getMap(self):  # map_util.h:25
+        nd = self.getDim()
+        out = np.zeros(int(np.prod(nd.astype(np.int64))), dtype=np.int8)
+        check(lib().mplb_map_get_data(self._h, ptr(out), out.size))
+        return out
+
+    def _destroy(self):
+        if self._h is not None:
+            lib().mplb_map_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+
+class OccMapUtil(MapUtil):
+    def __init__(self):
+        super().__init__(2)
+
+
+class VoxelMapUtil(MapUtil):
+    def __init__(self):
+        super().__init__(3)
+
+
+class MapPlanner:
+    """MapPlanner<Dim> (map_planner.h:20-125) / PlannerBase<Dim, Waypoint<Dim>> (planner_base.h:18-345)."""
+
+    def __init__(self, dim, verbose=False):
+        self.dim = dim
+        h = C.c_void_p()
+        check(lib().mplb_planner_create(dim, int(verbose), C.byref(h)))
+        self._h = h
+        self.map_util_ = None
+        self.U_ = None
+        self.dt_ = 1.0
+        self._last = None
+        self._control = None
+        self.traj_cost_ = None
+        self._initialized = False
+
+    def __del__(self):
+        try:
+            lib().mplb_planner_destroy(self._h)
+        except Exception:
+            pass
+
+    # ---- setters (planner_base.h:170-265, map_planner.cpp:14-18)
+    def setMapUtil(self, map_util):
+        check(lib().mplb_planner_set_map(self._h, map_util._h))
+        self.map_util_ = map_util
+
+    def _set(self, key, v):
+        check(lib().mplb_planner_set_param(self._h, PARAM[key], float(v)))
+
+    def setVmax(self, v): self._set("v_max", v)
+    def setAmax(self, a): self._set("a_max", a)
+    def setJmax(self, j): self._set("j_max", j)
+    def setYawmax(self, y): self._set("yaw_max", y)
+    def setTmax(self, t): self._set("t_max", t)
+    def setW(self, w): self._set("w", w)
+    def setEpsilon(self, e): self._set("epsilon", e)
+    def setMaxNum(self, n): self._set("max_num", n)
+    def setMemFraction(self, f): self._set("mem_fraction", f)
+
+    def setDt(self, dt):
+        self._set("dt", dt)
+        self.dt_ = float(dt)
+
+    def setTol(self, tol_pos, tol_vel=-1, tol_acc=-1):  # planner_base.h:255-265
+        self._set("tol_pos", tol_pos)
+        self._set("tol_vel", tol_vel)
+        self._set("tol_acc", tol_acc)
+
+    def setU(self, U):  # planner_base.h:246
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        check(lib().mplb_planner_set_controls(self._h, ptr(U), U.shape[0], U.shape[1]))
+        self.U_ = U
+
+    def initialized(self):
+        return self._initialized
+
+    # ---- plan (planner_base.h:275-325)
+    def plan(self, start, goal):
+        s, g = start, goal
+        if isinstance(start, Waypoint):
+            s = waypoints_array(1)
+            start.to_record(s[0])
+        if isinstance(goal, Waypoint):
+            g = waypoints_array(1)
+            goal.to_record(g[0])
+        res = np.zeros(1, dtype=_lib.RESULT_DTYPE)
+        check(lib().mplb_plan(self._h, ptr(s), ptr(g), ptr(res)))
+        self._last = res[0]
+        self._control = int(s["control"][0])
+        self._initialized = True
+        self.traj_cost_ = float(res[0]["cost"])
+        return int(res[0]["status"]) in (PLAN_OK, PLAN_START_IS_GOAL)
+
+    def result(self):
+        return self._last
+
+    def getTrajCost(self):
+        return self.traj_cost_
+
+    def getExpandedNum(self):  # planner_base.h:148
+        return int(self._last["pops"])
+
+    def getActions(self):
+        n = check(lib().mplb_get_actions(self._h, None, 0))
+        a = np.zeros(max(n, 1), dtype=np.int32)
+        check(lib().mplb_get_actions(self._h, ptr(a), a.size))
+        return a[:n]
+
+    def getSegStates(self):
+        n = check(lib().mplb_get_seg_states(self._h, None, 0))
+        s = np.zeros((max(n, 1), 13), dtype=np.float64)
+        check(lib().mplb_get_seg_states(self._h, ptr(s), s.shape[0]))
+        return s[:n]
+
+    def getTraj(self):  # planner_base.h:28 + recoverTraj graph_search.h:369-455
+        if self._last is None or int(self._last["status"]) != PLAN_OK:
+            return Trajectory()
+        acts, st = self.getActions(), self.getSegStates()
+        return Trajectory([Primitive(self.dim, self._control, st[i], self.U_[acts[i]], self.dt_) for i in range(len(acts))])
+
+    def getNodes(self):
+        n = check(lib().mplb_get_nodes(self._h, None, 0))
+        a = np.zeros(max(n, 1), dtype=_lib.NODE_DTYPE)
+        check(lib().mplb_get_nodes(self._h, ptr(a), a.size))
+        return a[:n]
+
+    def getPopLog(self):
+        n = check(lib().mplb_get_pop_log(self._h, None, 0))
+        a = np.zeros(max(n, 1), dtype=np.int32)
+        check(lib().mplb_get_pop_log(self._h, ptr(a), a.size))
+        return a[:n]
+
+    def getCloseSet(self):  # planner_base.h:84-91 (unordered positions of closed nodes)
+        nodes = self.getNodes()
+        return nodes["state"][nodes["closed"] != 0][:, :self.dim]
+
+    def getOpenSet(self):  # planner_base.h:77-81
+        n = check(lib().mplb_get_open(self._h, None, 0))
+        ids = np.zeros(max(n, 1), dtype=np.int32)
+        check(lib().mplb_get_open(self._h, ptr(ids), ids.size))
+        return self.getNodes()["state"][ids[:n]][:, :self.dim]
+
+    def getExpandedNodes(self):  # planner_base.h:140 (expanded_nodes_, pop order)
+        return self.getNodes()["state"][self.getPopLog()][:, :self.dim]
+
+    # ---- batch (north-star extension; every entry behaves like plan())
+    def plan_batch(self, starts, goals, max_seg=0, want_states=False):
+        n = len(starts)
+        res = np.zeros(n, dtype=_lib.RESULT_DTYPE)
+        acts = np.full((n, max_seg), -1, dtype=np.int32) if max_seg > 0 else None
+        segs = np.zeros((n, max_seg, 13), dtype=np.float64) if (max_seg > 0 and want_states) else None
+        check(lib().mplb_plan_batch(self._h, ptr(starts), ptr(goals), n, ptr(res), ptr(acts), ptr(segs), max_seg))
+        return res, acts, segs
+
+    def plan_batch_device(self, d_starts, d_goals, n, d_results, d_actions=0, d_segs=0, max_seg=0, stream=0):
+        """All pointers are device addresses (ints), e.g. torch tensor .data_ptr()."""
+        vp = lambda x: C.c_void_p(int(x)) if x else None  # noqa: E731
+        check(lib().mplb_plan_batch_device(self._h, vp(d_starts), vp(d_goals), n, vp(d_results), vp(d_actions), vp(d_segs),
+                                           max_seg, vp(stream)))
+
+    def last_batch_stats(self):
+        ms, l, t = C.c_double(), C.c_int32(), C.c_int32()
+        check(lib().mplb_last_batch_stats(self._h, C.byref(ms), C.byref(l), C.byref(t)))
+        return dict(kernel_ms=ms.value, launches=l.value, tiers=t.value)
+
+    def expand(self, states):
+        """env_map::get_succ rows for arbitrary states (env_map.h:147-172): array [n, |U|] of trace records."""
+        n = len(states)
+        rows = np.zeros((n, self.U_.shape[0]), dtype=_lib.TRACE_DTYPE)
+        check(lib().mplb_expand(self._h, ptr(states), n, ptr(rows)))
+        return rows
+
+
+class OccMapPlanner(MapPlanner):  # map_planner.h:122
+    def __init__(self, verbose=False):
+        super().__init__(2, verbose)
+
+
+class VoxelMapPlanner(MapPlanner):  # map_planner.h:125
+    def __init__(self, verbose=False):
+        super().__init__(3, verbose)

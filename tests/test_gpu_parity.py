@@ -1,0 +1,178 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle, bit-exact.
+
+Bar (BASELINE.json north_star): identical voxel indices / free-occupied decisions and expanded-node sets;
+costs and waypoint states are compared for exact equality here (tolerance 0), which is stricter than the
+1e-6 relative the north_star allows.
+"""
+import numpy as np
+import pytest
+
+import oracle
+import mpl_ros_b200 as mp
+from mpl_ros_b200 import maps
+from helpers import load_config
+from helpers_gpu import RESULT_FIELDS, assert_results_equal, make_pair, waypoint_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _nodes_by_key(nodes):
+    return {tuple(n["key"][:n["key"][15]]): n for n in nodes}
+
+
+@pytest.mark.parametrize("name", ["corridor", "simple", "skir"])
+def test_single_plan_parity(name):
+    """Reference-shaped single plans: test_planner_2d.cpp (corridor KAT), map_planner_node test.launch (simple),
+    test.launch.skir (skir).  Everything observable is compared: counters, pop order, every node, the trajectory."""
+    m, dim, params, U, start, goal = load_config(name)
+    pl, op = make_pair(m, dim, params, U)
+    sg, so = waypoint_pair(start, mp.ACC)
+    gg, go = waypoint_pair(goal, mp.ACC)
+    ok = pl.plan(sg, gg)
+    ro = op.plan(so, go)
+    rg = pl.result()
+    assert ok and ro["status"] == 0
+    assert_results_equal(rg, ro, name)
+    if name == "corridor":  # MPL/README.md:200-202
+        assert rg["n_closed"] == 615 and rg["n_seg"] == 35 and rg["cost"] == 351.5
+    # pop order = expanded_nodes_ order (env_map.h:154)
+    gn = pl.getNodes()
+    pop_keys_gpu = gn["key"][pl.getPopLog()]
+    assert np.array_equal(pop_keys_gpu, op.pop_keys(ro["pops"]))
+    # every node of the hash map: stored coord (first discoverer), g, h, flags
+    on = _nodes_by_key(op.nodes(ro["n_nodes"]))
+    gnk = _nodes_by_key(gn)
+    assert set(on) == set(gnk)
+    for k, a in gnk.items():
+        b = on[k]
+        assert np.array_equal(a["state"], b["state"]), k
+        assert a["g"] == b["g"] and a["h"] == b["h"] and a["opened"] == b["opened"] and a["closed"] == b["closed"], k
+    # trajectory: actions and the stored parent states (forward_action arguments, env_base.h:228-231)
+    assert np.array_equal(pl.getActions(), op.actions(ro["n_seg"]))
+    assert np.array_equal(pl.getSegStates(), op.seg_states(ro["n_seg"]))
+    # reference-style getters
+    assert len(pl.getCloseSet()) == ro["n_closed"] and len(pl.getOpenSet()) == ro["n_open"]
+    traj = pl.getTraj()
+    assert traj.getTotalTime() == ro["n_seg"] * params["dt"]
+    assert len(traj.getWaypoints()) == ro["n_seg"] + 1
+
+
+@pytest.mark.parametrize("name", ["corridor", "simple", "skir"])
+def test_expand_trace_parity(name):
+    """env_map::get_succ row by row (verdict, sample divisor, samples tested, blocking voxel index, cost, end
+    state, lattice key) on every state the oracle's search touched."""
+    m, dim, params, U, start, goal = load_config(name)
+    pl, op = make_pair(m, dim, params, U)
+    sg, so = waypoint_pair(start, mp.ACC)
+    gg, go = waypoint_pair(goal, mp.ACC)
+    ro = op.plan(so, go)
+    nodes = op.nodes(ro["n_nodes"])[:600]
+    sts_g, sts_o = waypoint_pair(nodes["state"][:, 0:dim], mp.ACC, vel=nodes["state"][:, 3:3 + dim])
+    rows = pl.expand(sts_g)
+    for i in range(len(nodes)):
+        tr = op.succ_trace(sts_o[i:i + 1])
+        for f in ("verdict", "n", "n_tested", "block_idx", "cost", "succ", "key"):
+            assert np.array_equal(rows[i][f], tr[f]), (name, i, f, rows[i][f], tr[f])
+
+
+def _levine_case(which):
+    m = maps.levine256() if which == "levine256" else maps.load_fixture("levine")
+    U = maps.make_U(1.0, 1, 3)
+    params = dict(v_max=2.0, a_max=1.0, dt=1.0, tol_pos=0.5)
+    return m, U, params
+
+
+@pytest.mark.parametrize("which,n", [("levine", 48), ("levine256", 48)])
+def test_batch_parity_levine(which, n):
+    """BASELINE configs[1] shape (3D, |U| = 27, random free-voxel start/goal pairs, unreachable pairs kept)."""
+    m, U, params = _levine_case(which)
+    pl, op = make_pair(m, 3, params, U)
+    S, G = maps.sample_queries(m, n, seed=0)
+    sg, so = waypoint_pair(S, mp.ACC)
+    gg, go = waypoint_pair(G, mp.ACC)
+    rg, ag, segs = pl.plan_batch(sg, gg, max_seg=64, want_states=True)
+    ro, ao = op.plan_batch(so, go, nthreads=8, max_seg=64)
+    assert set(np.unique(ro["status"])) <= {0, 3}
+    for i in range(n):
+        assert_results_equal(rg[i], ro[i], (which, i))
+    assert np.array_equal(ag, ao)
+
+
+def test_edge_cases():
+    m, dim, params, U, start, goal = load_config("simple")
+    pl, op = make_pair(m, dim, params, U)
+    free = m.int_to_float([145, 45, 0])
+    # occupied start -> "start is not free" (planner_base.h:283-287)
+    occ_idx = int(np.flatnonzero(m.data == 100)[1000])
+    d = m.dim.astype(np.int64)
+    occ = m.int_to_float([occ_idx % d[0], (occ_idx // d[0]) % d[1], occ_idx // (d[0] * d[1])])
+    cases = [(occ, goal, 1), ([-5.0, 0.0, 0.0], goal, 1),          # occupied / outside start
+             (free, free + 0.2, 5),                                   # start already in the goal region (graph_search.h:44)
+             (start, goal, 0)]
+    for s, g, want in cases:
+        sg, so = waypoint_pair(s, mp.ACC)
+        gg, go = waypoint_pair(g, mp.ACC)
+        ok = pl.plan(sg, gg)
+        ro = op.plan(so, go)
+        assert ro["status"] == want, (s, g, ro["status"])
+        assert_results_equal(pl.result(), ro)
+        assert ok == (want in (0, 5))
+    # MaxExpandStep (graph_search.h:149-154)
+    pl.setMaxNum(50)
+    op.set_param("max_num", 50)
+    sg, so = waypoint_pair(start, mp.ACC)
+    gg, go = waypoint_pair(goal, mp.ACC)
+    assert not pl.plan(sg, gg)
+    ro = op.plan(so, go)
+    assert ro["status"] == 2 and ro["pops"] == 50
+    assert_results_equal(pl.result(), ro)
+
+
+def test_nonzero_start_velocity_and_epsilon():
+    m, dim, params, U, start, goal = load_config("skir")
+    for eps in (1.0, 2.0, 0.0):
+        p2 = dict(params, epsilon=eps)
+        pl, op = make_pair(m, dim, p2, U)
+        sg, so = waypoint_pair(start, mp.ACC, vel=[1.0, 0.0, 0.0])
+        gg, go = waypoint_pair(goal, mp.ACC)
+        pl.plan(sg, gg)
+        ro = op.plan(so, go)
+        assert_results_equal(pl.result(), ro, eps)
+        if eps <= 1.0:  # with an inflated heuristic only the cost/closed set are pinned, see DESIGN.md
+            assert np.array_equal(pl.getActions(), op.actions(ro["n_seg"]))
+
+
+def test_jrk_control_2d():
+    """JRK control on a grid (exercised upstream by MPL/test/test_planner_2d_with_prior_traj.cpp:80-84, u = 0.5)."""
+    m, dim, params, U, start, goal = load_config("corridor")
+    params = dict(v_max=1.0, a_max=1.0, j_max=1.0, dt=1.0, max_num=4000)
+    pl, op = make_pair(m, dim, params, U)
+    sg, so = waypoint_pair(start, mp.JRK)
+    gg, go = waypoint_pair(goal, mp.JRK)
+    pl.plan(sg, gg)
+    ro = op.plan(so, go)
+    assert_results_equal(pl.result(), ro)
+    assert np.array_equal(pl.getActions(), op.actions(ro["n_seg"]))
+
+
+def test_map_ops():
+    m = maps.load_fixture("simple")
+    data = m.data.copy()
+    data[::7] = -1  # sprinkle unknown cells
+    mu = mp.VoxelMapUtil()
+    mu.setMap(m.origin, m.dim, data, m.res)
+    assert np.array_equal(mu.getMap(), data)
+    mu.freeUnknown()
+    want = np.where(data == -1, 0, data)
+    assert np.array_equal(mu.getMap(), want)
+    ns = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0]], dtype=np.int32)  # map_planner_node.cpp:75-86 style
+    mu.dilate(ns)
+    g = want.reshape(tuple(int(x) for x in m.dim[::-1]))
+    out = g.copy()
+    occ = g == 100
+    out[:, :, 1:][occ[:, :, :-1]] = 100
+    out[:, :, :-1][occ[:, :, 1:]] = 100
+    out[:, 1:, :][occ[:, :-1, :]] = 100
+    out[:, :-1, :][occ[:, 1:, :]] = 100
+    assert np.array_equal(mu.getMap(), out.reshape(-1))
+    assert mu.getRes() == m.res and np.array_equal(mu.getDim(), m.dim) and np.array_equal(mu.getOrigin(), m.origin)
