@@ -1,0 +1,98 @@
+"""Multi-GPU sharding of a query batch: one process per GPU, torch.distributed for the plumbing.
+
+The path shards by query (plans are independent and read-only on the map).  There are exactly
+two collectives: one broadcast of the voxel grid per map, and one gather of fixed-stride result records per
+batch.  No other data-path communication exists; within one plan there is nothing to shard.
+
+Works with backend "nccl" (GPU tensors, NVLink/NVSwitch) and "gloo" (CPU tensors; used by the CPU tests with a
+stand-in planner, since libmplb has no CPU path).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def shard_indices(n, rank, world):
+    """Query i goes to rank i mod world (static striping: neighbouring queries have unrelated cost)."""
+    return np.arange(rank, n, world)
+
+
+def broadcast_map(origin, dim, res, data, device, src=0):
+    """Rank `src` supplies the map; every rank returns (origin, dim, res, grid tensor on `device`).
+    One broadcast of a small header and one of the int8 grid."""
+    rank = dist.get_rank()
+    hdr = torch.zeros(8, dtype=torch.float64, device=device)
+    if rank == src:
+        nd = len(dim)
+        hdr[0] = nd
+        hdr[1:1 + nd] = torch.as_tensor(np.asarray(origin, dtype=np.float64))
+        hdr[4:4 + nd] = torch.as_tensor(np.asarray(dim, dtype=np.float64))
+        hdr[7] = res
+    dist.broadcast(hdr, src)
+    h = hdr.cpu().numpy()
+    nd = int(h[0])
+    origin, dimv, res = h[1:1 + nd].copy(), h[4:4 + nd].astype(np.int32), float(h[7])
+    ncell = int(np.prod(dimv.astype(np.int64)))
+    if rank == src:
+        grid = torch.as_tensor(np.ascontiguousarray(data, dtype=np.int8).reshape(-1)).to(device)
+    else:
+        grid = torch.empty(ncell, dtype=torch.int8, device=device)
+    dist.broadcast(grid, src)
+    return origin, dimv, res, grid
+
+
+def gather_results(local_results, local_actions, n_total, max_seg, device, dst=0):
+    """Gather per-rank result records (and action rows) to rank `dst`, restoring global query order.
+    local_results: numpy structured array (RESULT_DTYPE) for queries shard_indices(n_total, rank, world).
+    Returns (results[n_total], actions[n_total, max_seg]) on dst, (None, None) elsewhere."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    per = (n_total + world - 1) // world
+    rec = _lib.RESULT_DTYPE.itemsize
+    row = rec + 4 * max_seg
+    buf = np.zeros((per, row), dtype=np.uint8)
+    k = len(local_results)
+    buf[:k, :rec] = local_results.view(np.uint8).reshape(k, rec)
+    if max_seg:
+        buf[:k, rec:] = np.ascontiguousarray(local_actions, dtype=np.int32).view(np.uint8).reshape(k, 4 * max_seg)
+    t = torch.as_tensor(buf).to(device)
+    outs = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, outs, dst)  # NCCL: grouped send/recv to dst; gloo: native gather
+    if rank != dst:
+        return None, None
+    results = np.zeros(n_total, dtype=_lib.RESULT_DTYPE)
+    actions = np.full((n_total, max_seg), -1, dtype=np.int32)
+    for r in range(world):
+        idx = shard_indices(n_total, r, world)
+        b = outs[r].cpu().numpy()[:len(idx)]
+        results[idx] = np.ascontiguousarray(b[:, :rec]).view(_lib.RESULT_DTYPE).reshape(-1)
+        if max_seg:
+            actions[idx] = np.ascontiguousarray(b[:, rec:]).view(np.int32).reshape(len(idx), max_seg)
+    return results, actions
+
+
+class ShardedBatchPlanner:
+    """plan_batch over all ranks of the default process group.
+
+    `make_planner(origin, dim, res, grid_tensor)` builds this rank's planner on its device from the broadcast
+    grid (on GPU: MapUtil.setMapFromDevice + MapPlanner; the CPU tests pass a stand-in)."""
+
+    def __init__(self, make_planner, device):
+        self.make_planner = make_planner
+        self.device = device
+        self.planner = None
+
+    def set_map(self, origin=None, dim=None, res=None, data=None, src=0):
+        o, d, r, grid = broadcast_map(origin, dim, res, data, self.device, src)
+        self._grid = grid  # keep the receive buffer alive until the planner has copied it
+        self.planner = self.make_planner(o, d, r, grid)
+        return o, d, r
+
+    def plan_batch(self, starts, goals, max_seg=64, dst=0):
+        """starts/goals: full arrays on every rank (host, WAYPOINT_DTYPE). Each rank plans its stripe."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        idx = shard_indices(len(starts), rank, world)
+        res, acts, _ = self.planner.plan_batch(np.ascontiguousarray(starts[idx]), np.ascontiguousarray(goals[idx]),
+                                               max_seg=max_seg)
+        return gather_results(res, acts, len(starts), max_seg, self.device, dst)
