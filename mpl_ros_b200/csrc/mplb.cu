@@ -157,7 +157,7 @@ struct mplb_planner {
   bool retained = false;
   mplb_result ret_result;
   int ret_cap = 0, ret_ns = 0, ret_slot = 0;
-  size_t ret_stride = 0, ret_off_state = 0, ret_off_heap = 0, ret_off_poplog = 0;
+  size_t ret_stride = 0, ret_off_state = 0, ret_off_heap = 0, ret_off_poplog = 0, ret_row_bytes = 0;
   std::vector<int> ret_actions;
   std::vector<double> ret_segs;
 };
@@ -167,7 +167,7 @@ namespace {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
-  size_t off_state, off_heap, off_table, off_poplog, stride;
+  size_t off_rows, off_heap, off_table, off_poplog, stride, row_bytes;
   int tsize_max;
 };
 
@@ -177,13 +177,14 @@ Layout make_layout(int cap, int ns, int nU) {
   while ((long long)ts < 2ll * (cap + nU)) ts <<= 1;
   L.tsize_max = ts;
   size_t o = 0;
+  L.row_bytes = sizeof(RowHdr) + (size_t)ns * sizeof(double);
   o += align_up((size_t)cap * sizeof(NodeHot), 256);
-  L.off_state = o;
-  o += align_up((size_t)cap * ns * sizeof(double), 256);
+  L.off_rows = o;
+  o += align_up((size_t)cap * L.row_bytes, 256);
   L.off_heap = o;
   o += align_up((size_t)cap * sizeof(HeapEnt), 256);
   L.off_table = o;
-  o += align_up((size_t)ts * sizeof(unsigned long long), 256);
+  o += align_up((size_t)ts * sizeof(Slot), 256);
   L.off_poplog = o;
   o += align_up((size_t)cap * sizeof(int), 256);
   L.stride = o;
@@ -288,6 +289,7 @@ int build_cfg(mplb_planner *p, int control) {
       bitpos += bits;
     }
   }
+  c.key_wide = (bitpos > 96) ? 1 : 0;
   p->kfields = p->dim * ord;
   p->cfg_control = control;
   p->cfg_map_version = m->version;
@@ -295,10 +297,10 @@ int build_cfg(mplb_planner *p, int control) {
   return MPLB_OK;
 }
 
-template <int DIM, int ORD>
+template <int DIM, int ORD, int MAXU>
 int launch_batch(const DevCfg &c, const BatchArgs &a, int grid, cudaStream_t s) {
-  size_t smem = sizeof(PlanSmem<DIM, ORD>);
-  auto kern = astar_batch_kernel<DIM, ORD>;
+  size_t smem = sizeof(PlanSmem<DIM, ORD, MAXU>);
+  auto kern = astar_batch_kernel<DIM, ORD, MAXU>;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, MPLB_NT, smem, s>>>(c, a);
   g_launches++;
@@ -306,23 +308,24 @@ int launch_batch(const DevCfg &c, const BatchArgs &a, int grid, cudaStream_t s) 
   return MPLB_OK;
 }
 
-template <int DIM, int ORD>
+template <int DIM, int ORD, int MAXU>
 int resident_ctas(int device) {
   int per_sm = 0, sms = 0;
-  size_t smem = sizeof(PlanSmem<DIM, ORD>);
-  auto kern = astar_batch_kernel<DIM, ORD>;
+  size_t smem = sizeof(PlanSmem<DIM, ORD, MAXU>);
+  auto kern = astar_batch_kernel<DIM, ORD, MAXU>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MPLB_NT, smem) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
   return per_sm * sms;
 }
 
-#define DISPATCH(dim, ord, CALL)                                                              \
+#define DISPATCH_U(D, O, nu, CALL) do { if ((nu) <= 32) { CALL(D, O, 32); } else { CALL(D, O, 128); } } while (0)
+#define DISPATCH(dim, ord, nu, CALL)                                                          \
   do {                                                                                        \
-    if (dim == 2 && ord == 1) { CALL(2, 1); } else if (dim == 2 && ord == 2) { CALL(2, 2); }  \
-    else if (dim == 2 && ord == 3) { CALL(2, 3); } else if (dim == 2 && ord == 4) { CALL(2, 4); } \
-    else if (dim == 3 && ord == 1) { CALL(3, 1); } else if (dim == 3 && ord == 2) { CALL(3, 2); } \
-    else if (dim == 3 && ord == 3) { CALL(3, 3); } else { CALL(3, 4); }                       \
+    if (dim == 2 && ord == 1) DISPATCH_U(2, 1, nu, CALL); else if (dim == 2 && ord == 2) DISPATCH_U(2, 2, nu, CALL); \
+    else if (dim == 2 && ord == 3) DISPATCH_U(2, 3, nu, CALL); else if (dim == 2 && ord == 4) DISPATCH_U(2, 4, nu, CALL); \
+    else if (dim == 3 && ord == 1) DISPATCH_U(3, 1, nu, CALL); else if (dim == 3 && ord == 2) DISPATCH_U(3, 2, nu, CALL); \
+    else if (dim == 3 && ord == 3) DISPATCH_U(3, 3, nu, CALL); else DISPATCH_U(3, 4, nu, CALL); \
   } while (0)
 
 /* Core: device-resident batch over arena tiers. */
@@ -339,8 +342,8 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
   if (retain) CUDA_TRY(p->d_slot.reserve((size_t)n));
 
   int resident = 0;
-#define RES_CALL(D, O) resident = resident_ctas<D, O>(p->device)
-  DISPATCH(c.dim, c.ord, RES_CALL);
+#define RES_CALL(D, O, M) resident = resident_ctas<D, O, M>(p->device)
+  DISPATCH(c.dim, c.ord, c.nU, RES_CALL);
   if (resident <= 0) return fail(MPLB_ERR_CUDA, "no resident CTA for the search kernel (is this an sm_100 device?)");
 
   size_t free_b = 0, total_b = 0;
@@ -380,18 +383,18 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
     a.starts = d_starts; a.goals = d_goals; a.results = d_results; a.actions = d_actions; a.seg_states = d_segs;
     a.max_seg = max_seg; a.work = identity ? nullptr : p->d_work.p; a.n_work = n_work;
     a.work_counter = p->d_ctrl.p; a.arena = p->arena.p; a.stride = L.stride; a.cap = cap; a.tsize_max = L.tsize_max;
-    a.off_state = L.off_state; a.off_heap = L.off_heap; a.off_table = L.off_table; a.off_poplog = L.off_poplog;
+    a.off_rows = L.off_rows; a.off_heap = L.off_heap; a.off_table = L.off_table; a.off_poplog = L.off_poplog;
     a.want_poplog = retain ? 1 : 0; a.slot_of_plan = retain ? p->d_slot.p : nullptr;
     a.overflow_count = p->d_ctrl.p + 1; a.overflow_list = p->d_over.p;
-#define LAUNCH_CALL(D, O) rc = launch_batch<D, O>(c, a, slots, s)
-    DISPATCH(c.dim, c.ord, LAUNCH_CALL);
+#define LAUNCH_CALL(D, O, M) rc = launch_batch<D, O, M>(c, a, slots, s)
+    DISPATCH(c.dim, c.ord, c.nU, LAUNCH_CALL);
     if (rc != MPLB_OK) return rc;
     p->last_launches++; p->last_tiers++;
     int n_over = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_over, p->d_ctrl.p + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (retain && n == 1 && n_over == 0) {
-      p->ret_cap = cap; p->ret_ns = c.ns; p->ret_stride = L.stride; p->ret_off_state = L.off_state;
+      p->ret_cap = cap; p->ret_ns = c.ns; p->ret_stride = L.stride; p->ret_off_state = L.off_rows; p->ret_row_bytes = L.row_bytes;
       p->ret_off_heap = L.off_heap; p->ret_off_poplog = L.off_poplog;
     }
     if (n_over == 0) break;
@@ -718,26 +721,28 @@ int mplb_get_nodes(mplb_planner *p, mplb_node *nodes, int cap) {
   if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
   int m = std::min(n, cap);
   std::vector<NodeHot> hot(m);
-  std::vector<double> st((size_t)m * p->ret_ns);
+  std::vector<unsigned char> rw((size_t)m * p->ret_row_bytes);
   unsigned char *base = p->arena.p + (size_t)p->ret_slot * p->ret_stride;
   CUDA_TRY(cudaMemcpy(hot.data(), base, (size_t)m * sizeof(NodeHot), cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(st.data(), base + p->ret_off_state, (size_t)m * p->ret_ns * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(rw.data(), base + p->ret_off_state, (size_t)m * p->ret_row_bytes, cudaMemcpyDeviceToHost));
   const DevCfg &c = p->cfg;
   for (int i = 0; i < m; i++) {
     mplb_node &o = nodes[i];
     std::memset(&o, 0, sizeof(o));
+    const RowHdr *rh = reinterpret_cast<const RowHdr *>(rw.data() + (size_t)i * p->ret_row_bytes);
+    const double *st = reinterpret_cast<const double *>(rw.data() + (size_t)i * p->ret_row_bytes + sizeof(RowHdr));
     for (int d = 0; d < c.ord; d++)
-      for (int ax = 0; ax < c.dim; ax++) o.state[d * 3 + ax] = st[(size_t)i * p->ret_ns + d * c.dim + ax];
+      for (int ax = 0; ax < c.dim; ax++) o.state[d * 3 + ax] = st[d * c.dim + ax];
     o.g = hot[i].g; o.h = hot[i].h;
     for (int f = 0; f < c.ns; f++) {
-      unsigned long long wv = c.kword[f] ? hot[i].k1 : hot[i].k0;
+      unsigned long long wv = c.kword[f] ? rh->k1 : rh->k0;
       unsigned long long v = (wv >> c.kshift[f]) & ((1ull << c.kbits[f]) - 1ull);
       o.key[f] = (int)((long long)v + c.koff[f]);
     }
     o.key[15] = c.ns;
     o.opened = (hot[i].flags & 1) ? 1 : 0;
     o.closed = (hot[i].flags & 2) ? 1 : 0;
-    o.parent = hot[i].parent;
+    o.parent = rh->parent;
     o.action = hot[i].action;
   }
   return n;
@@ -762,7 +767,7 @@ int mplb_get_open(mplb_planner *p, int32_t *node_ids, int cap) {
   std::vector<HeapEnt> h(m);
   unsigned char *base = p->arena.p + (size_t)p->ret_slot * p->ret_stride;
   CUDA_TRY(cudaMemcpy(h.data(), base + p->ret_off_heap, (size_t)m * sizeof(HeapEnt), cudaMemcpyDeviceToHost));
-  for (int i = 0; i < m; i++) node_ids[i] = h[i].node;
+  for (int i = 0; i < m; i++) node_ids[i] = h[i].node & 0x7fffffff;
   return n;
 }
 
@@ -779,14 +784,14 @@ int mplb_expand(mplb_planner *p, const mplb_waypoint *states, int n, mplb_prim_t
   CUDA_TRY(cudaMalloc((void **)&d_r, (size_t)n * c.nU * sizeof(mplb_prim_trace)));
   CUDA_TRY(cudaMemcpy(d_s, states, (size_t)n * sizeof(mplb_waypoint), cudaMemcpyHostToDevice));
   int grid = std::min(n, 148 * 8);
-#define EXPAND_CALL(D, O)                                                                                   \
+#define EXPAND_CALL(D, O, M)                                                                                \
   do {                                                                                                      \
-    size_t smem = sizeof(PlanSmem<D, O>);                                                                   \
-    auto kern = expand_trace_kernel<D, O>;                                                                  \
+    size_t smem = sizeof(PlanSmem<D, O, M>);                                                                \
+    auto kern = expand_trace_kernel<D, O, M>;                                                                \
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     kern<<<grid, MPLB_NT, smem>>>(c, d_s, n, d_r);                                                          \
   } while (0)
-  DISPATCH(c.dim, c.ord, EXPAND_CALL);
+  DISPATCH(c.dim, c.ord, c.nU, EXPAND_CALL);
   g_launches++;
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpy(rows, d_r, (size_t)n * c.nU * sizeof(mplb_prim_trace), cudaMemcpyDeviceToHost);

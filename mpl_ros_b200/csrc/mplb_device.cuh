@@ -53,6 +53,7 @@ struct DevCfg {
   /* lattice-key packing: field f = axis*ord + derivative (wp:92-125 order) */
   int koff[12];
   unsigned char kshift[12], kbits[12], kword[12];
+  int key_wide; /* 1 when word 1 of the key needs more than 32 bits (table slots then also compare the row header) */
 };
 
 /* ------------------------------------------------------------------------------------------------
