@@ -148,6 +148,7 @@ struct mplb_planner {
   DevBuf<mplb_result> d_results;
   DevBuf<int> d_actions;
   DevBuf<double> d_segs;
+  DevBuf<long long> d_phase; /* diagnostics build only */
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
   /* last batch */
@@ -261,6 +262,24 @@ int build_cfg(mplb_planner *p, int control) {
   CUDA_TRY(cudaMemcpy(p->d_toff.p, toff.data(), toff.size() * sizeof(int), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(p->d_tcnt.p, tcnt.data(), tcnt.size() * sizeof(int), cudaMemcpyHostToDevice));
   c.ttab = p->d_ttab.p; c.toff = p->d_toff.p; c.tcnt = p->d_tcnt.p; c.n_hi = n_hi;
+  c.tt_total = (int)ttab.size();
+  c.inv_res = 1.0 / m->res;
+  /* filtered sampling: FP32 displacement error <= ~14 * 2^-24 * (Dsum + 1) cells, Dsum = sum of the largest term
+   * magnitudes of the displacement polynomial in cells; the guard band is 2^-19 * (Dsum + 2) (>= 2x that bound). */
+  {
+    double bnd[5] = {0, p->v_max, p->a_max, p->j_max, 0};
+    bnd[ord] = umax; /* the control itself is the top coefficient */
+    bool known = true;
+    double dsum = 0, tp = 1, fact = 1;
+    for (int d = 1; d <= ord; d++) {
+      tp *= p->dt; fact *= d;
+      if (!(bnd[d] > 0) && d < ord) known = false;
+      dsum += std::fabs(bnd[d]) * tp / fact / m->res;
+    }
+    double delta = std::ldexp(dsum + 2.0, -19);
+    c.use_fast = (known && n_hi < MPLB_NCAP && c.tt_total <= MPLB_TT_CAP && delta <= 0.01) ? 1 : 0;
+    c.fast_delta = (float)delta;
+  }
 
   /* key packing: field f = axis*ord + d; pos fields cover the map plus a margin (end states are not collision
    * tested at t = T, em:99), derivative fields cover their dynamic bound (validated primitives, pr:449-496). */
@@ -319,7 +338,7 @@ int resident_ctas(int device) {
   return per_sm * sms;
 }
 
-#define DISPATCH_U(D, O, nu, CALL) do { if ((nu) <= 32) { CALL(D, O, 32); } else { CALL(D, O, 128); } } while (0)
+#define DISPATCH_U(D, O, nu, CALL) do { if ((nu) <= 32) { CALL(D, O, 1); } else { CALL(D, O, 4); } } while (0)
 #define DISPATCH(dim, ord, nu, CALL)                                                          \
   do {                                                                                        \
     if (dim == 2 && ord == 1) DISPATCH_U(2, 1, nu, CALL); else if (dim == 2 && ord == 2) DISPATCH_U(2, 2, nu, CALL); \
@@ -386,6 +405,10 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
     a.off_rows = L.off_rows; a.off_heap = L.off_heap; a.off_table = L.off_table; a.off_poplog = L.off_poplog;
     a.want_poplog = retain ? 1 : 0; a.slot_of_plan = retain ? p->d_slot.p : nullptr;
     a.overflow_count = p->d_ctrl.p + 1; a.overflow_list = p->d_over.p;
+#ifdef MPLB_PHASE_TIMING
+    CUDA_TRY(p->d_phase.reserve((size_t)n * 8));
+    a.phase_cycles = p->d_phase.p;
+#endif
 #define LAUNCH_CALL(D, O, M) rc = launch_batch<D, O, M>(c, a, slots, s)
     DISPATCH(c.dim, c.ord, c.nU, LAUNCH_CALL);
     if (rc != MPLB_OK) return rc;
@@ -800,6 +823,15 @@ int mplb_expand(mplb_planner *p, const mplb_waypoint *states, int n, mplb_prim_t
   if (e != cudaSuccess) return fail(MPLB_ERR_CUDA, std::string("expand: ") + cudaGetErrorString(e));
   return MPLB_OK;
 }
+
+#ifdef MPLB_PHASE_TIMING
+/* diagnostics build only (not part of the ABI): per-plan phase cycle accumulators of the last batch */
+int mplb_debug_phase_cycles(mplb_planner *p, long long *out, int n) {
+  if (!p || !out) return fail(MPLB_ERR_ARG, "null argument");
+  CUDA_TRY(cudaMemcpy(out, p->d_phase.p, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return MPLB_OK;
+}
+#endif
 
 int mplb_last_batch_stats(mplb_planner *p, double *kernel_ms, int32_t *launches, int32_t *tiers) {
   if (!p) return fail(MPLB_ERR_ARG, "null planner");

@@ -54,6 +54,11 @@ struct DevCfg {
   int koff[12];
   unsigned char kshift[12], kbits[12], kword[12];
   int key_wide; /* 1 when word 1 of the key needs more than 32 bits (table slots then also compare the row header) */
+  /* filtered (FP32) collision sampling: see sample_blocked_fast */
+  double inv_res;   /* 1/res, used only inside filters whose doubtful cases fall back to the exact division */
+  int use_fast;     /* tables fit in shared memory and every dynamic bound is known */
+  int tt_total;     /* number of entries of ttab */
+  float fast_delta; /* guard band around voxel boundaries, in cells (>= proven FP32 error bound) */
 };
 
 /* ------------------------------------------------------------------------------------------------
@@ -195,6 +200,21 @@ __device__ __forceinline__ void lattice_ints(const double *st, int *ints) {
       ints[ax * ORD + d] = round_int(ddiv(x, d == 0 ? 0.01 : 0.1));
     }
   }
+}
+
+/* Pack ints into the 128-bit node key (no parity hash); false when a field leaves its packable range. */
+template <int DIM, int ORD>
+__device__ __forceinline__ bool pack_key_nohash(const DevCfg &c, const int *ints, unsigned long long &k0, unsigned long long &k1) {
+  k0 = 0; k1 = 0;
+  bool ok = true;
+#pragma unroll
+  for (int f = 0; f < DIM * ORD; f++) {
+    long long v = (long long)ints[f] - (long long)c.koff[f];
+    if (v < 0 || v >= (1ll << c.kbits[f])) ok = false;
+    unsigned long long uv = (unsigned long long)v << c.kshift[f];
+    if (c.kword[f]) k1 |= uv; else k0 |= uv;
+  }
+  return ok;
 }
 
 /* Pack ints into the 128-bit node key; returns false when a field leaves its packable range. */

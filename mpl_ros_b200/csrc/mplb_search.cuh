@@ -3,24 +3,35 @@
  *
  * Reference path restated per pop (paths under motion_primitive_library/include/):
  *   GraphSearch::Astar            mpl_planner/common/graph_search.h:39-182   (pop, relax, terminate)
- *   env_map::get_succ             mpl_planner/env/env_map.h:147-172          (phase B1: one thread per control u)
+ *   env_map::get_succ             mpl_planner/env/env_map.h:147-172          (phase B1: one lane per control u)
  *   env_map::traverse_primitive   mpl_planner/env/env_map.h:90-132           (phase B2: one thread per sample)
  *   env_map::is_goal + rayTrace   env_map.h:25-45, mpl_collision/map_util.h:117-134
  *   priorityQueue / compare_pair  mpl_planner/common/state_space.h:15-34     (binary heap, same sift rules as
  *                                 boost::heap::d_ary_heap<arity<2>, mutable_<true>> so pop order is identical)
  *   recoverTraj                   graph_search.h:369-455 (best-predecessor rule kept as a running argmin)
  *
- * Latency structure of one pop (the search of one plan is a serial chain of pops, so the kernel is
- * latency-bound per plan and throughput comes from the batch):
- *   P1  warp 0, one lane per control: end state, dynamic validation, lattice key, sample count     (registers/smem)
- *   P2  all threads: every collision sample of every control in one flat pass (bit-brick loads, L2/L1);
- *       concurrently lanes of warp 0 probe the hash table and prefetch the touched node records    (HBM/L2, overlapped)
- *   P3  warp 0: goal test, relax successors in control order against the SHARED-MEMORY heap using the
- *       prefetched records, pop the next node (its state row was prefetched or is forwarded from smem)
- * Three __syncthreads per pop; no global load sits on the serial chain in the common case.
+ * The search of one plan is a serial chain of pops, so the kernel is latency-bound per plan (measured on B200:
+ * dependent FP64 op 8.3 cycles, __ddiv_rn 125, LDS 34, SHFL 26, HBM round trip ~1000) and throughput comes from
+ * running several hundred plans at once.  One pop is organised so that almost nothing sits on the serial chain:
  *
- * Search state of a plan lives in a private HBM arena (node records, state rows, table, heap spill); the only
- * data shared between CTAs is the read-only map (bit-bricks) and the control / sample-time tables.
+ *   warp 0  (search)  B1: one lane per control — exact FP64 end state, validation, lattice key, sample count;
+ *                     issues the hash-table probe of every candidate successor (ONE HBM round trip: the table slot
+ *                     carries the node's g and best-predecessor g), then helps sampling; after the barrier it
+ *                     relaxes all successors lane-parallel and performs the heap pushes in control order with a
+ *                     warp-cooperative sift-up on the SHARED-MEMORY heap, then takes the next node off the root.
+ *   warps 1-2 (sample) per-pop FP32 sampling coefficients, goal test + parity hash of the current node, then every
+ *                     collision sample of every control (flat list of 8-sample granules) through a FILTERED path:
+ *                     FP32 evaluation with a proven error bound decides the voxel whenever the sample is not within
+ *                     delta of a voxel boundary, otherwise the exact FP64 formula of the reference is evaluated.
+ *   warp 3  (heap)    finishes the previous pop's sift-down and prefetches the new root's state row while the
+ *                     other warps expand the current node.
+ *
+ * Exactness: every value that is stored or compared (states, costs, g, h, f, keys, voxel indices) is identical to the
+ * reference's double arithmetic; filters only skip work when the exact result is provably the same.  Rare hazards
+ * (two successors of one expansion mapping to one node or one table slot) drop to a serial generic routine.
+ *
+ * Search state of a plan lives in a private HBM arena (table, node records, state rows, heap spill); the only data
+ * shared between CTAs is the read-only map (occupancy bit-bricks) and the control / sample-time tables.
  */
 #pragma once
 #include "mplb_device.cuh"
@@ -30,9 +41,19 @@ namespace mplb {
 
 #define MPLB_INTERNAL_OVERFLOW 100 /* arena too small: host retries the plan in a larger tier */
 #define MPLB_INTERNAL_BADCTRL 9
-#define MPLB_OWNER_CAP 2304 /* flat sample list capacity (>= 27*41 and 125*16) */
+#define MPLB_TT_CAP 1024           /* float sample times kept in shared memory */
+#define MPLB_NCAP 64               /* sample divisors n < 64 tabulated in shared memory */
 
-/* Relax-path half of a node: one 32-byte sector. */
+/* Table slot = one 32-byte sector: key, node id and the two values every relaxation compares against. */
+struct __align__(32) Slot {
+  unsigned long long k0;
+  unsigned int k1lo;
+  unsigned int node1; /* node id + 1; 0 = empty */
+  double g;           /* copy of NodeHot::g */
+  double pg;          /* copy of NodeHot::pg */
+};
+static_assert(sizeof(Slot) == 32, "Slot must be 32 bytes");
+
 struct __align__(32) NodeHot {
   double g, h;
   double pg;       /* g of the best predecessor (tie rule of recoverTraj, gs:391-405) */
@@ -43,22 +64,14 @@ struct __align__(32) NodeHot {
 };
 static_assert(sizeof(NodeHot) == 32, "NodeHot must be 32 bytes");
 
-/* Pop-path half of a node: header of the state row, followed by NS doubles of state. */
+/* Header of a state row, followed by NS doubles of state (the stored coord of the node). */
 struct __align__(16) RowHdr {
   unsigned long long k0, k1; /* packed lattice key */
-  unsigned long long kh;     /* 64-bit hash of the lattice ints */
   int parent;                /* best predecessor node */
-  int pad;
+  int slot;                  /* table slot of this node (kept current across table growth) */
+  unsigned long long pad;
 };
 static_assert(sizeof(RowHdr) == 32, "RowHdr must be 32 bytes");
-
-/* Table slot: exact for keys up to 96 bits; wider keys also compare RowHdr::k1. node1 == 0 means empty. */
-struct __align__(16) Slot {
-  unsigned long long k0;
-  unsigned int k1lo;
-  unsigned int node1;
-};
-static_assert(sizeof(Slot) == 16, "Slot must be 16 bytes");
 
 struct HeapEnt {
   double f; /* heap key (gs:54,119) */
@@ -91,12 +104,21 @@ struct BatchArgs {
   int *slot_of_plan;   /* optional: which slot ran plan i (retained single plan) */
   int *overflow_count; /* plans whose arena overflowed in this tier ... */
   int *overflow_list;  /* ... and their ids, for the next (larger) tier */
+  long long *phase_cycles; /* diagnostics build only (MPLB_PHASE_TIMING): 8 accumulators per plan */
 };
 
-template <int DIM, int ORD, int MAXU>
+#ifdef MPLB_PHASE_TIMING
+#define MPLB_TICK(k) do { if (tid == 0) { long long t__ = clock64(); ph[k] += t__ - tlast; tlast = t__; } } while (0)
+#else
+#define MPLB_TICK(k) do { } while (0)
+#endif
+
+template <int DIM, int ORD, int NB>
 struct PlanSmem {
   static constexpr int NS = DIM * ORD;
-  static constexpr int HCAP = (MAXU <= 32) ? 2048 : 1024; /* heap entries kept in shared memory */
+  static constexpr int MAXU = 32 * NB;
+  static constexpr int HCAP = (NB == 1) ? 2048 : 1024; /* heap entries kept in shared memory */
+  static constexpr int GCAP = MAXU * 8;                /* 8-sample granules */
   /* heap top (SoA) */
   double hf[HCAP], hg[HCAP];
   int hn[HCAP];
@@ -104,31 +126,38 @@ struct PlanSmem {
   double cur[NS];
   int cur_ints[NS];
   double cur_g;
-  int cur_node;
+  unsigned long long cur_kh;
+  int cur_node, cur_tag, goal_hit;
   double goal_pos[3], goal_vel[3], goal_acc[3];
   unsigned long long gk0, gk1;
   int goal_key_ok;
+  /* per-plan constants */
   double U[MAXU * 3];
+  double cost[MAXU];   /* J(u) + w*dt, eb:343-345 */
+  float Au[MAXU * 3];  /* top polynomial coefficient of the fast sampling path, in cells */
+  float ttf[MPLB_TT_CAP];
+  int toff_s[MPLB_NCAP], tcnt_s[MPLB_NCAP];
+  /* per-pop sampling base (fast path): cell coordinate of the parent = Y0 + fy0, lower coefficients in cells */
+  int Y0[3];
+  float fy0[3];
+  float Ap[3 * 3];
   /* per-control results of get_succ */
   double es[MAXU * NS]; /* end states, [u][d*DIM+ax] */
-  double cost[MAXU];
-  unsigned long long k0[MAXU], k1[MAXU], kh[MAXU];
+  unsigned long long k0[MAXU], k1[MAXU];
   int verdict[MAXU]; /* 0 self, 1 dyn, 2 blocked, 3 valid, 4 valid-no-motion, 5 needs sampling (transient) */
   int nsamp[MAXU];   /* divisor n */
   int cnt[MAXU];     /* samples to test */
-  int pre[MAXU];     /* exclusive prefix of cnt */
   int first[MAXU];   /* first blocked sample index or INT_MAX */
-  /* prefetched node records for the relax phase */
-  int nid[MAXU];     /* node id or -1 */
-  int slot[MAXU];    /* empty table slot where the probe ended (when nid == -1) */
-  double ng[MAXU], nh[MAXU], npg[MAXU];
-  int npos[MAXU];
-  int nfl[MAXU];
-  int cr_idx[MAXU];  /* successors that created a node in this expansion */
-  int n_created;
+  int nid[MAXU];     /* node id of the successor after relaxation (for state forwarding) */
+  unsigned char gl_u[GCAP], gl_c[GCAP];
+  int n_gran;
   int n_before;      /* n_nodes before this expansion */
-  int m_total;       /* flat sample count */
-  unsigned char owner[MPLB_OWNER_CAP];
+  /* pending sift-down (heap warp) and prefetched root row */
+  int sd_pending, sd_n;
+  double sd_f, sd_g;
+  int pf_node;
+  unsigned long long pf_k0, pf_k1;
+  double pf_st[NS];
   int n_nodes, n_heap, tsize, pops, n_closed, status, plan_idx, key_bad;
   long long n_samples, n_valid;
   unsigned long long pop_hash, closed_hash;
@@ -139,12 +168,12 @@ template <class SM>
 struct HeapView {
   SM &S;
   HeapEnt *spill; /* global array indexed by heap position (entries >= HCAP live here) */
-  int *heap_pos_base; /* &hot[0].heap_pos, stride sizeof(NodeHot) */
+  NodeHot *hot;
   __device__ __forceinline__ void get(int i, double &f, double &g, int &n) const {
     if (i < SM::HCAP) { f = S.hf[i]; g = S.hg[i]; n = S.hn[i]; }
     else { HeapEnt e = spill[i]; f = e.f; g = e.g; n = e.node; }
   }
-  __device__ __forceinline__ void set(int i, double f, double g, int n, NodeHot *hot) const {
+  __device__ __forceinline__ void set(int i, double f, double g, int n) const {
     if (i < SM::HCAP) { S.hf[i] = f; S.hg[i] = g; S.hn[i] = n; }
     else { HeapEnt e; e.f = f; e.g = g; e.node = n; e.pad = 0; spill[i] = e; }
     hot[n & 0x7fffffff].heap_pos = i;
@@ -152,19 +181,34 @@ struct HeapView {
   __device__ __forceinline__ int node_at(int i) const { return (i < SM::HCAP) ? S.hn[i] : spill[i].node; }
   __device__ __forceinline__ void set_g(int i, double g) const { if (i < SM::HCAP) S.hg[i] = g; else spill[i].g = g; }
 
-  /* push/increase: sift up while the parent is strictly worse (boost siftup) */
-  __device__ __forceinline__ void sift_up(int pos, double f, double g, int n, NodeHot *hot) const {
+  /* serial push/increase: sift up while the parent is strictly worse (boost siftup) */
+  __device__ __forceinline__ void sift_up(int pos, double f, double g, int n) const {
     while (pos != 0) {
       int par = (pos - 1) >> 1;
       double pf, pg; int pn;
       get(par, pf, pg, pn);
-      if (heap_worse(pf, pg, f, g)) { set(pos, pf, pg, pn, hot); pos = par; }
+      if (heap_worse(pf, pg, f, g)) { set(pos, pf, pg, pn); pos = par; }
       else break;
     }
-    set(pos, f, g, n, hot);
+    set(pos, f, g, n);
+  }
+  /* warp-cooperative sift up: lane k examines ancestor k+1; identical result to the serial loop */
+  __device__ __forceinline__ void sift_up_warp(int pos, double f, double g, int n, int lane) const {
+    int p1 = pos + 1;
+    int depth = 31 - __clz(p1);            /* number of ancestors */
+    int my = (p1 >> (lane + 1)) - 1;       /* ancestor lane+1 */
+    bool have = lane < depth;
+    double af = 0.0, ag = 0.0; int an = 0;
+    if (have) get(my, af, ag, an);
+    bool moves = have && heap_worse(af, ag, f, g);
+    unsigned stopm = __ballot_sync(0xffffffffu, !moves); /* first non-moving ancestor (or beyond depth) */
+    int stop = __ffs(stopm) - 1;                          /* ancestors 1..stop move down one level */
+    if (lane < stop) set((p1 >> lane) - 1, af, ag, an);   /* ancestor lane+1 -> position of ancestor lane (lane 0: pos) */
+    if (lane == 0) set((p1 >> stop) - 1, f, g, n);
+    __syncwarp();
   }
   /* pop: sift the former last element down from the root; ties still move down (boost siftdown) */
-  __device__ __forceinline__ void sift_down(int n_heap, int pos, double f, double g, int n, NodeHot *hot) const {
+  __device__ __forceinline__ void sift_down(int n_heap, int pos, double f, double g, int n) const {
     while (true) {
       int c = 2 * pos + 1;
       if (c >= n_heap) break;
@@ -175,14 +219,19 @@ struct HeapView {
         get(c + 1, rf, rg, rn);
         if (heap_worse(cf, cg, rf, rg)) { c = c + 1; cf = rf; cg = rg; cn = rn; } /* right child only if strictly better */
       }
-      if (!heap_worse(cf, cg, f, g)) { set(pos, cf, cg, cn, hot); pos = c; }
+      if (!heap_worse(cf, cg, f, g)) { set(pos, cf, cg, cn); pos = c; }
       else break;
     }
-    set(pos, f, g, n, hot);
+    set(pos, f, g, n);
   }
 };
 
 /* ---------------------------------------------------------------- hash table */
+__device__ __forceinline__ unsigned table_hash(unsigned long long k0, unsigned long long k1) {
+  unsigned long long h = (k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
+  return (unsigned)(h >> 32) ^ (unsigned)h;
+}
+
 __device__ __forceinline__ bool slot_matches(const Slot &s, unsigned long long k0, unsigned long long k1, bool wide,
                                              const unsigned char *rows, size_t row_bytes) {
   if (s.k0 != k0 || s.k1lo != (unsigned int)k1) return false;
@@ -191,37 +240,61 @@ __device__ __forceinline__ bool slot_matches(const Slot &s, unsigned long long k
   return h->k1 == k1;
 }
 
-/* returns node id or -1; *end_slot = slot index where the probe stopped (empty slot when -1) */
-__device__ __forceinline__ int table_find(const Slot *table, int tsize, unsigned long long kh, unsigned long long k0,
-                                          unsigned long long k1, bool wide, const unsigned char *rows, size_t row_bytes,
-                                          int *end_slot) {
+/* serial probe from slot i: returns node id or -1; *end_slot = matching slot / first empty slot */
+__device__ __forceinline__ int table_find_from(const Slot *table, int tsize, unsigned i, unsigned long long k0,
+                                               unsigned long long k1, bool wide, const unsigned char *rows, size_t row_bytes,
+                                               int *end_slot, double *g, double *pg) {
   unsigned mask = (unsigned)tsize - 1u;
-  unsigned i = (unsigned)kh & mask;
+  i &= mask;
   while (true) {
     Slot s = table[i];
     if (s.node1 == 0u) { *end_slot = (int)i; return -1; }
-    if (slot_matches(s, k0, k1, wide, rows, row_bytes)) { *end_slot = (int)i; return (int)s.node1 - 1; }
+    if (slot_matches(s, k0, k1, wide, rows, row_bytes)) { *end_slot = (int)i; *g = s.g; *pg = s.pg; return (int)s.node1 - 1; }
     i = (i + 1) & mask;
   }
 }
 
-__device__ __forceinline__ void table_insert_atomic(Slot *table, int tsize, unsigned long long kh, unsigned long long k0,
-                                                    unsigned long long k1, int id) {
+/* rebuild insert (table growth): returns the slot index */
+__device__ __forceinline__ int table_insert_atomic(Slot *table, int tsize, unsigned long long k0, unsigned long long k1, int id,
+                                                   double g, double pg) {
   unsigned mask = (unsigned)tsize - 1u;
-  unsigned i = (unsigned)kh & mask;
+  unsigned i = table_hash(k0, k1) & mask;
   unsigned long long w1 = ((unsigned long long)(unsigned)(id + 1) << 32) | (unsigned long long)(unsigned int)k1;
   unsigned long long *t = reinterpret_cast<unsigned long long *>(table);
-  while (atomicCAS(&t[2 * i + 1], 0ull, w1) != 0ull) i = (i + 1) & mask; /* claim by the (k1lo,node1) word */
-  t[2 * i] = k0;
+  while (atomicCAS(&t[4 * i + 1], 0ull, w1) != 0ull) i = (i + 1) & mask; /* claim by the (k1lo,node1) word */
+  t[4 * i] = k0;
+  table[i].g = g;
+  table[i].pg = pg;
+  return (int)i;
 }
 
-/* ---------------------------------------------------------------- phase B1: one thread per control (em:155-160,163-165) */
+/* ---------------------------------------------------------------- exact reference arithmetic with cheap filters */
+/* lattice int round(x / q) (wp:97-120) with q = 0.01 or 0.1: x*(1/q) decides unless within 1e-6 of a tie. */
+__device__ __forceinline__ int lattice_int(double x, double q, double inv_q) {
+  double y = dmul(x, inv_q);
+  double r = rint(y);
+  if (fabs(dsub(y, r)) < 0.499999) return __double2int_rn(r);
+  return round_int(ddiv(x, q));
+}
+
+/* max(5, (int)ceil(max_v*T/res)) (em:95): the product with 1/res decides unless within 1e-9 of an integer. */
+__device__ __forceinline__ int sample_divisor(double max_v, double T, double res, double inv_res) {
+  double mvT = dmul(max_v, T);
+  double x = dmul(mvT, inv_res);
+  double r = rint(x);
+  int n;
+  if (fabs(dsub(x, r)) > 1e-9) n = __double2int_rn(ceil(x));
+  else n = __double2int_rz(ceil(ddiv(mvT, res)));
+  return n < 5 ? 5 : n;
+}
+
+/* ---------------------------------------------------------------- phase B1: one lane per control (em:155-160,163-165) */
 template <int DIM, int ORD, class SM>
-__device__ __forceinline__ void expand_b1(const DevCfg &c, SM &S, int i) {
+__device__ __forceinline__ void expand_b1(const DevCfg &c, SM &S, int i, unsigned long long &k0, unsigned long long &k1) {
   constexpr int NS = DIM * ORD;
   const double T = c.dt;
   double es[NS];
-  double max_v = 0.0, J = 0.0;
+  double max_v = 0.0;
   bool dyn_ok = true, same_pos = true;
 #pragma unroll
   for (int ax = 0; ax < DIM; ax++) {
@@ -236,40 +309,42 @@ __device__ __forceinline__ void expand_b1(const DevCfg &c, SM &S, int i) {
     if (ORD >= 2 && c.v_max > 0.0 && mv > c.v_max) dyn_ok = false;
     if (ORD >= 3 && c.a_max > 0.0 && A.max_acc(T) > c.a_max) dyn_ok = false;
     if (ORD >= 4 && c.j_max > 0.0 && A.max_jrk(T) > c.j_max) dyn_ok = false;
-    J = dadd(J, A.J(T)); /* pr:403-407 */
     same_pos = same_pos && (S.cur[ax] == es[ax]); /* em:163 */
   }
   int ints[NS];
-  lattice_ints<DIM, ORD>(es, ints);
+#pragma unroll
+  for (int ax = 0; ax < DIM; ax++) {
+#pragma unroll
+    for (int d = 0; d < ORD; d++)
+      ints[ax * ORD + d] = (d == 0) ? lattice_int(es[ax], 0.01, 100.0) : lattice_int(es[d * DIM + ax], 0.1, 10.0);
+  }
   bool self = true;
 #pragma unroll
   for (int f = 0; f < NS; f++) self = self && (ints[f] == S.cur_ints[f]);
 #pragma unroll
   for (int f = 0; f < NS; f++) S.es[i * NS + f] = es[f];
-  unsigned long long k0, k1, kh;
-  bool key_ok = pack_key<DIM, ORD>(c, ints, k0, k1, kh);
-  S.k0[i] = k0; S.k1[i] = k1; S.kh[i] = kh;
+  bool key_ok = pack_key_nohash<DIM, ORD>(c, ints, k0, k1);
+  S.k0[i] = k0; S.k1[i] = k1;
   S.first[i] = 0x7fffffff;
-  S.cost[i] = dadd(J, dmul(c.w, T)); /* eb:343-345; traverse contributes 0 on a plain map */
   int verdict, n = 0, cnt = 0;
   if (self) verdict = 0;
   else if (!dyn_ok) verdict = 1;
   else if (same_pos) verdict = 4;
   else {
     verdict = 5;
-    n = __double2int_rz(ceil(ddiv(dmul(max_v, T), c.res))); /* em:95 */
-    n = n < 5 ? 5 : n;
-    cnt = c.tcnt[n];
+    n = sample_divisor(max_v, T, c.res, c.inv_res);
+    cnt = (n < MPLB_NCAP && c.use_fast) ? S.tcnt_s[n] : c.tcnt[n];
   }
   S.nsamp[i] = n;
   S.cnt[i] = cnt;
   if ((verdict >= 3) && !key_ok) S.key_bad = 1;
   S.verdict[i] = verdict;
+  S.nid[i] = -1;
 }
 
-/* One collision sample (em:100-104,119): true when the sample at time t of control i is outside or occupied. */
+/* One collision sample, exact (em:100-104,119): true when the sample at time t of control i is outside or occupied. */
 template <int DIM, int ORD, class SM>
-__device__ __forceinline__ bool sample_blocked(const DevCfg &c, const SM &S, int i, double t, int *cell_idx) {
+__device__ __noinline__ bool sample_blocked_exact(const DevCfg &c, const SM &S, int i, double t, int *cell_idx) {
   int pn[3] = {0, 0, 0};
   bool outside = false;
 #pragma unroll
@@ -283,8 +358,35 @@ __device__ __forceinline__ bool sample_blocked(const DevCfg &c, const SM &S, int
   return brick_occupied<DIM>(c, pn[0], pn[1], pn[2]);
 }
 
-/* B2, per-control form: warps take controls round-robin, lanes take samples (used by the trace kernel and when
- * the flat sample list would overflow). */
+/* Filtered sample: FP32 displacement in cells relative to the parent's cell coordinate.  The voxel is decided in
+ * FP32 when every axis is farther than c.fast_delta from a voxel boundary (error bound set by the host from the
+ * dynamic limits); otherwise the exact routine decides. */
+template <int DIM, int ORD, class SM>
+__device__ __forceinline__ bool sample_blocked_fast(const DevCfg &c, const SM &S, int i, int n, int k) {
+  const float t = S.ttf[S.toff_s[n] + k];
+  int pn[3] = {0, 0, 0};
+  bool sure = true;
+#pragma unroll
+  for (int ax = 0; ax < DIM; ax++) {
+    float dy = S.Au[i * 3 + ax]; /* Horner over t, coefficients in cells: top one per control, lower ones per pop */
+#pragma unroll
+    for (int d = ORD - 2; d >= 0; d--) dy = fmaf(dy, t, S.Ap[d * 3 + ax]);
+    dy *= t;
+    float w = (S.fy0[ax] + dy) - 0.5f;
+    float r = rintf(w);
+    sure = sure && (fabsf(w - r) < 0.5f - c.fast_delta);
+    pn[ax] = S.Y0[ax] + (int)r;
+  }
+  if (!sure) return sample_blocked_exact<DIM, ORD>(c, S, i, c.ttab[c.toff[n] + k], nullptr);
+  bool outside = false;
+#pragma unroll
+  for (int ax = 0; ax < DIM; ax++) outside = outside || pn[ax] < 0 || pn[ax] >= c.nd[ax];
+  if (outside) return true;
+  return brick_occupied<DIM>(c, pn[0], pn[1], pn[2]);
+}
+
+/* B2, per-control exact form: warps take controls round-robin, lanes take samples (trace kernel, and the search
+ * kernel when the fast tables do not fit). */
 template <int DIM, int ORD, class SM>
 __device__ __forceinline__ void expand_b2_percontrol(const DevCfg &c, SM &S, int warp, int lane, int nwarps) {
   for (int i = warp; i < c.nU; i += nwarps) {
@@ -296,7 +398,7 @@ __device__ __forceinline__ void expand_b2_percontrol(const DevCfg &c, SM &S, int
     for (int base = 0; base < cnt; base += 32) {
       int k = base + lane;
       bool blocked = false;
-      if (k < cnt) blocked = sample_blocked<DIM, ORD>(c, S, i, __ldg(&tt[k]), nullptr);
+      if (k < cnt) blocked = sample_blocked_exact<DIM, ORD>(c, S, i, __ldg(&tt[k]), nullptr);
       unsigned m = __ballot_sync(0xffffffffu, blocked);
       if (m) { first = base + __ffs(m) - 1; break; }
     }
@@ -383,17 +485,86 @@ __device__ __forceinline__ void unpack_ints(const DevCfg &c, unsigned long long 
   }
 }
 
+template <int NS>
+__device__ __forceinline__ unsigned long long khash_of_ints(const int *ints) {
+  unsigned long long h = khash_init();
+#pragma unroll
+  for (int f = 0; f < NS; f++) h = khash_step(h, ints[f]);
+  return khash_final(h);
+}
+
+/* Generic serial relaxation of successors [i0, i1) in control order (lane 0 of warp 0): re-probes the table in
+ * global memory, so it is correct under every hazard (duplicate siblings, slot collisions).  gs:79-143. */
+template <int DIM, int ORD, class SM>
+__device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, const HeapView<SM> &H, Slot *table, NodeHot *hot,
+                                          unsigned char *rows, int i0, int i1, bool wide) {
+  constexpr int NS = DIM * ORD;
+  constexpr size_t ROWB = sizeof(RowHdr) + NS * sizeof(double);
+  const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+  const int cn = S.cur_node;
+  const double cg = S.cur_g;
+  for (int idx = i0; idx < i1; idx++) {
+    int v = S.verdict[idx];
+    if (v == 5) v = (S.first[idx] == 0x7fffffff) ? 3 : 2;
+    if (v < 3) continue;
+    const unsigned long long k0 = S.k0[idx], k1 = S.k1[idx];
+    int slot; double gold = kInf, pgold = 0.0;
+    int nid = table_find_from(table, S.tsize, table_hash(k0, k1), k0, k1, wide, rows, ROWB, &slot, &gold, &pgold);
+    NodeHot hn;
+    if (nid < 0) { /* gs:84-88 */
+      nid = S.n_nodes++;
+      hn.g = kInf; hn.h = heuristic<DIM, ORD>(c, S, &S.es[idx * NS], k0, k1); hn.pg = 0.0; hn.heap_pos = -1; hn.action = -1;
+      hn.flags = 0; hn.pad0 = 0;
+      RowHdr *rh = reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB);
+      rh->k0 = k0; rh->k1 = k1; rh->parent = -1; rh->slot = slot; rh->pad = 0;
+      double *rs = reinterpret_cast<double *>(rows + (size_t)nid * ROWB + sizeof(RowHdr));
+      for (int f = 0; f < NS; f++) rs[f] = S.es[idx * NS + f];
+      Slot sl; sl.k0 = k0; sl.k1lo = (unsigned int)k1; sl.node1 = (unsigned)(nid + 1); sl.g = kInf; sl.pg = 0.0;
+      table[slot] = sl;
+    } else hn = hot[nid];
+    S.nid[idx] = nid;
+    double tentative = dadd(cg, S.cost[idx]); /* gs:107 */
+    if (tentative < hn.g) { /* gs:109-141 */
+      double f = dadd(tentative, dmul(c.eps, hn.h));
+      hn.g = tentative; hn.pg = cg; hn.action = (short)idx;
+      reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB)->parent = cn;
+      table[slot].g = tentative; table[slot].pg = cg;
+      int fl = hn.flags;
+      if ((fl & 1) && !(fl & 2)) { /* increase(): f lowered, sift up only (gs:131-133) */
+        hot[nid] = hn;
+        H.sift_up(hn.heap_pos, f, tentative, nid);
+      } else {
+        int tag = nid;
+        if (fl & 2) { /* closed node re-pushed (gs:135-141): refresh g copies of its stale entries */
+          for (int q = 0; q < S.n_heap; q++) if ((H.node_at(q) & 0x7fffffff) == nid) H.set_g(q, tentative);
+          tag = nid | 0x80000000;
+        }
+        hn.flags = (unsigned char)(fl | 1);
+        hot[nid] = hn;
+        H.sift_up(S.n_heap, f, tentative, tag);
+        S.n_heap++;
+      }
+    } else if (tentative == hn.g && cg > hn.pg) { /* recoverTraj tie: larger predecessor g wins (gs:398-403) */
+      hn.pg = cg; hn.action = (short)idx;
+      hot[nid] = hn;
+      table[slot].pg = cg;
+      reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB)->parent = cn;
+    }
+  }
+}
+
 /* ---------------------------------------------------------------- the kernel */
-template <int DIM, int ORD, int MAXU>
+template <int DIM, int ORD, int NB>
 __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, const BatchArgs a) {
   constexpr int NS = DIM * ORD;
   constexpr int NW = MPLB_NT / 32;
-  using SM = PlanSmem<DIM, ORD, MAXU>;
+  using SM = PlanSmem<DIM, ORD, NB>;
   constexpr size_t ROWB = sizeof(RowHdr) + NS * sizeof(double);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM &S = *reinterpret_cast<SM *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   unsigned char *base = a.arena + (size_t)blockIdx.x * a.stride;
   NodeHot *hot = reinterpret_cast<NodeHot *>(base);
@@ -402,9 +573,22 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
   Slot *table = reinterpret_cast<Slot *>(base + a.off_table);
   int *poplog = reinterpret_cast<int *>(base + a.off_poplog);
   const bool wide = c.key_wide != 0;
-  HeapView<SM> H{S, spill, nullptr};
+  const bool fast = c.use_fast != 0;
+  HeapView<SM> H{S, spill, hot};
 
+  /* ---------------- per-launch constants */
   for (int i = tid; i < c.nU * 3; i += MPLB_NT) S.U[i] = c.U[i];
+  for (int i = tid; i < c.nU; i += MPLB_NT) {
+    double J = 0.0;
+    for (int ax = 0; ax < DIM; ax++) { double u = c.U[i * 3 + ax]; J = dadd(J, dmul(dmul(u, u), c.dt)); } /* pr:92-122,403-407 */
+    S.cost[i] = dadd(J, dmul(c.w, c.dt));                                                                /* eb:343-345 */
+    const double fact = (ORD == 1) ? 1.0 : (ORD == 2) ? 2.0 : (ORD == 3) ? 6.0 : 24.0;
+    for (int ax = 0; ax < 3; ax++) S.Au[i * 3 + ax] = (ax < DIM) ? (float)(c.U[i * 3 + ax] / fact * c.inv_res) : 0.0f;
+  }
+  if (fast) {
+    for (int i = tid; i < MPLB_NCAP; i += MPLB_NT) { S.toff_s[i] = (i <= c.n_hi) ? c.toff[i] : 0; S.tcnt_s[i] = (i <= c.n_hi) ? c.tcnt[i] : 0; }
+    for (int i = tid; i < c.tt_total; i += MPLB_NT) S.ttf[i] = (float)c.ttab[i];
+  }
 
   while (true) {
     __syncthreads();
@@ -418,14 +602,14 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
     /* ---------------- per-plan init (pb:275-306, gs:44-60) */
     {
       unsigned long long *t64 = reinterpret_cast<unsigned long long *>(table);
-      for (int i = tid; i < 2 * 1024; i += MPLB_NT) t64[i] = 0ull;
+      for (int i = tid; i < 4 * 1024; i += MPLB_NT) t64[i] = 0ull;
     }
     if (tid == 0) {
       const mplb_waypoint &st = a.starts[pid];
       const mplb_waypoint &gl = a.goals[pid];
       S.tsize = 1024; S.n_nodes = 0; S.n_heap = 0; S.pops = 0; S.n_closed = 0; S.status = -1;
-      S.key_bad = 0; S.n_samples = 0; S.n_valid = 0; S.n_created = 0; S.n_before = 0;
-      S.pop_hash = 0ull; S.closed_hash = 0ull;
+      S.key_bad = 0; S.n_samples = 0; S.n_valid = 0; S.n_before = 0; S.sd_pending = 0; S.pf_node = -1;
+      S.pop_hash = 0ull; S.closed_hash = 0ull; S.goal_hit = 0;
       for (int ax = 0; ax < 3; ax++) { S.goal_pos[ax] = gl.pos[ax]; S.goal_vel[ax] = gl.vel[ax]; S.goal_acc[ax] = gl.acc[ax]; }
       double s0[NS];
       for (int ax = 0; ax < DIM; ax++) {
@@ -447,8 +631,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
         }
         int gi[NS];
         lattice_ints<DIM, ORD>(gs, gi);
-        unsigned long long gh;
-        S.goal_key_ok = pack_key<DIM, ORD>(c, gi, S.gk0, S.gk1, gh) ? 1 : 0;
+        S.goal_key_ok = pack_key_nohash<DIM, ORD>(c, gi, S.gk0, S.gk1) ? 1 : 0;
       }
       if (st.control != c.control || st.enable_t != 0) S.status = MPLB_INTERNAL_BADCTRL;
       else {
@@ -475,38 +658,40 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
       if (lane == 0 && g0) S.status = MPLB_PLAN_START_IS_GOAL;
     }
     __syncthreads();
-    if (S.status < 0 && tid == 0) { /* gs:47-60: start node, pushed and immediately popped as the first current node */
+    if (S.status < 0 && tid == 0) { /* gs:47-60: the start node is pushed and is necessarily the first pop (gs:64-68) */
       int ints[NS];
       lattice_ints<DIM, ORD>(S.cur, ints);
-      unsigned long long k0, k1, kh;
-      if (!pack_key<DIM, ORD>(c, ints, k0, k1, kh)) S.status = MPLB_PLAN_KEY_RANGE;
+      unsigned long long k0, k1;
+      if (!pack_key_nohash<DIM, ORD>(c, ints, k0, k1)) S.status = MPLB_PLAN_KEY_RANGE;
       else {
         NodeHot n0;
         n0.g = 0.0; n0.h = heuristic<DIM, ORD>(c, S, S.cur, k0, k1); n0.pg = 0.0; n0.heap_pos = 0; n0.action = -1;
-        n0.flags = 3; n0.pad0 = 0; /* opened, and closed by the first pop below */
+        n0.flags = 3; n0.pad0 = 0;
         hot[0] = n0;
+        int slot = table_insert_atomic(table, S.tsize, k0, k1, 0, 0.0, 0.0);
         RowHdr *rh = reinterpret_cast<RowHdr *>(rows);
-        rh->k0 = k0; rh->k1 = k1; rh->kh = kh; rh->parent = -1; rh->pad = 0;
+        rh->k0 = k0; rh->k1 = k1; rh->parent = -1; rh->slot = slot; rh->pad = 0;
         double *rs = reinterpret_cast<double *>(rows + sizeof(RowHdr));
         for (int f = 0; f < NS; f++) rs[f] = S.cur[f];
-        table_insert_atomic(table, S.tsize, kh, k0, k1, 0);
-        S.n_nodes = 1;
-        /* first pop (gs:64-68): the heap holds exactly the start node */
-        S.n_heap = 0;
-        S.cur_node = 0; S.cur_g = 0.0;
+        S.n_nodes = 1; S.n_heap = 0;
+        S.cur_node = 0; S.cur_g = 0.0; S.cur_tag = 0;
         for (int f = 0; f < NS; f++) S.cur_ints[f] = ints[f];
-        S.pop_hash = (0xCBF29CE484222325ull ^ kh) * 0x100000001B3ull;
-        S.n_closed = 1; S.closed_hash = kh;
+        S.pop_hash = 0xCBF29CE484222325ull;
         if (a.want_poplog) poplog[0] = 0;
         S.pops = 1;
       }
     }
     __syncthreads();
 
+#ifdef MPLB_PHASE_TIMING
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#endif
     /* ---------------- main loop (gs:63-162): S.cur* always holds the node popped last */
     while (S.status < 0) {
+      MPLB_TICK(7);
       /* capacity: this expansion can add at most nU nodes / heap entries */
-      if (S.n_nodes + c.nU > a.cap || S.n_heap + c.nU > a.cap) {
+      if (S.n_nodes + c.nU > a.cap || S.n_heap + c.nU + 1 > a.cap) {
         __syncthreads();
         if (tid == 0) S.status = MPLB_INTERNAL_OVERFLOW;
         __syncthreads();
@@ -518,239 +703,289 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
         __syncthreads();
         if (nt > a.tsize_max) { if (tid == 0) S.status = MPLB_INTERNAL_OVERFLOW; __syncthreads(); break; }
         unsigned long long *t64 = reinterpret_cast<unsigned long long *>(table);
-        for (int i = tid; i < 2 * nt; i += MPLB_NT) t64[i] = 0ull;
+        for (int i = tid; i < 4 * nt; i += MPLB_NT) t64[i] = 0ull;
         __syncthreads();
         for (int i = tid; i < S.n_nodes; i += MPLB_NT) {
-          const RowHdr *rh = reinterpret_cast<const RowHdr *>(rows + (size_t)i * ROWB);
-          table_insert_atomic(table, nt, rh->kh, rh->k0, rh->k1, i);
+          RowHdr *rh = reinterpret_cast<RowHdr *>(rows + (size_t)i * ROWB);
+          rh->slot = table_insert_atomic(table, nt, rh->k0, rh->k1, i, hot[i].g, hot[i].pg);
         }
         if (tid == 0) S.tsize = nt;
         __syncthreads();
       }
 
-      /* ---- P1: get_succ, one lane per control (em:147-172) */
-      if (MAXU <= 32) {
-        if (warp == 0) {
-          int cnt = 0;
-          if (lane < c.nU) { expand_b1<DIM, ORD>(c, S, lane); cnt = S.cnt[lane]; }
-          int incl = cnt; /* warp scan of the sample counts */
+      /* ================= P1/P2 ================= */
+      /* per-control registers of warp 0 (probe results), one set per 32-control batch */
+      unsigned long long rk0[NB], rk1[NB];
+      int r_nid[NB], r_slot[NB];
+      double r_g[NB], r_pg[NB], r_h[NB];
+      if (warp == 3) {
+        /* ---- heap warp: finish the previous pop's sift-down, then prefetch the new root's state row */
+        if (lane == 0) {
+          if (S.sd_pending) { H.sift_down(S.n_heap, 0, S.sd_f, S.sd_g, S.sd_n); S.sd_pending = 0; }
+          int pf = -1;
+          if (S.n_heap > 0) {
+            pf = S.hn[0] & 0x7fffffff;
+            const RowHdr *rh = reinterpret_cast<const RowHdr *>(rows + (size_t)pf * ROWB);
+            S.pf_k0 = rh->k0; S.pf_k1 = rh->k1;
+            const double *rs = reinterpret_cast<const double *>(rows + (size_t)pf * ROWB + sizeof(RowHdr));
 #pragma unroll
-          for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-          int excl = incl - cnt;
-          if (lane < c.nU) {
-            S.pre[lane] = excl;
-            if (incl <= MPLB_OWNER_CAP) for (int k = 0; k < cnt; k++) S.owner[excl + k] = (unsigned char)lane;
+            for (int f = 0; f < NS; f++) S.pf_st[f] = rs[f];
           }
-          if (lane == 31) S.m_total = incl;
-        }
-        __syncthreads();
-      } else {
-        for (int i = tid; i < c.nU; i += MPLB_NT) expand_b1<DIM, ORD>(c, S, i);
-        __syncthreads();
-        if (tid < c.nU) {
-          int excl = 0;
-          for (int j = 0; j < tid; j++) excl += S.cnt[j];
-          S.pre[tid] = excl;
-          int cnt = S.cnt[tid];
-          if (excl + cnt <= MPLB_OWNER_CAP) for (int k = 0; k < cnt; k++) S.owner[excl + k] = (unsigned char)tid;
-          if (tid == c.nU - 1) S.m_total = excl + cnt;
-        }
-        __syncthreads();
-      }
-
-      /* ---- P2: table probes + node prefetch (lanes of the first warps), then all collision samples flat */
-      for (int i = tid; i < c.nU; i += MPLB_NT) {
-        int v = S.verdict[i];
-        int nid = -1, slot = -1;
-        if (v >= 4) { /* 4 = valid without sampling, 5 = outcome pending: probe speculatively */
-          nid = table_find(table, S.tsize, S.kh[i], S.k0[i], S.k1[i], wide, rows, ROWB, &slot);
-          if (nid >= 0) {
-            const NodeHot hn = hot[nid];
-            S.ng[i] = hn.g; S.nh[i] = hn.h; S.npg[i] = hn.pg; S.npos[i] = hn.heap_pos; S.nfl[i] = hn.flags;
-          }
-        }
-        S.nid[i] = nid; S.slot[i] = slot;
-      }
-      if (S.m_total <= MPLB_OWNER_CAP) {
-        for (int m = tid; m < S.m_total; m += MPLB_NT) {
-          int u = S.owner[m];
-          int k = m - S.pre[u];
-          double t = __ldg(&c.ttab[c.toff[S.nsamp[u]] + k]);
-          if (sample_blocked<DIM, ORD>(c, S, u, t, nullptr)) atomicMin(&S.first[u], k);
+          S.pf_node = pf;
         }
       } else {
-        expand_b2_percontrol<DIM, ORD>(c, S, warp, lane, NW);
+        if (warp == 0) {
+          /* ---- B1 + probe issue, batch by batch */
+          int gbase = 0;
+#pragma unroll
+          for (int b = 0; b < NB; b++) {
+            const int i = b * 32 + lane;
+            int ng = 0;
+            rk0[b] = 0; rk1[b] = 0; r_nid[b] = -1; r_slot[b] = -1; r_g[b] = kInf; r_pg[b] = 0.0; r_h[b] = 0.0;
+            if (i < c.nU) {
+              expand_b1<DIM, ORD>(c, S, i, rk0[b], rk1[b]);
+              if (fast && S.verdict[i] == 5) ng = (S.cnt[i] + 7) >> 3;
+            }
+            int incl = ng; /* warp scan of the granule counts */
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+            int excl = gbase + incl - ng;
+            for (int q = 0; q < ng; q++) { S.gl_u[excl + q] = (unsigned char)i; S.gl_c[excl + q] = (unsigned char)q; }
+            gbase += __shfl_sync(0xffffffffu, incl, 31);
+          }
+          if (lane == 0) { S.n_gran = gbase; S.n_before = S.n_nodes; }
+        } else if (warp == 1) {
+          /* ---- per-pop sampling base of the fast path (cells): parent cell coordinate and lower coefficients */
+          if (fast && lane < DIM) {
+            const int ax = lane;
+            double y0 = dmul(dsub(S.cur[ax], c.origin[ax]), c.inv_res);
+            double fl = floor(y0);
+            S.Y0[ax] = __double2int_rn(fl);
+            S.fy0[ax] = (float)dsub(y0, fl);
+            if (ORD >= 2) S.Ap[0 * 3 + ax] = (float)dmul(S.cur[DIM + ax], c.inv_res);
+            if (ORD >= 3) S.Ap[1 * 3 + ax] = (float)dmul(dmul(S.cur[2 * DIM + ax], 0.5), c.inv_res);
+            if (ORD >= 4) S.Ap[2 * 3 + ax] = (float)dmul(ddiv(S.cur[3 * DIM + ax], 6.0), c.inv_res);
+          }
+        } else {
+          /* ---- goal test (gs:146) and parity hash of the current node */
+          bool gh = goal_test_warp<DIM, ORD>(c, S, S.cur, lane);
+          if (lane == 0) { S.goal_hit = gh ? 1 : 0; S.cur_kh = khash_of_ints<NS>(S.cur_ints); }
+        }
+        asm volatile("bar.sync 1, 96;" ::: "memory"); /* warps 0-2: B1 outputs, sampling base, goal flag are visible */
+        MPLB_TICK(0);
+        if (warp == 0) {
+          /* issue the table probes (two consecutive slots = 64 bytes) and compute h while they fly */
+          Slot sa[NB], sb[NB];
+          bool probing[NB];
+          unsigned hidx[NB];
+#pragma unroll
+          for (int b = 0; b < NB; b++) {
+            const int i = b * 32 + lane;
+            probing[b] = (i < c.nU) && (S.verdict[i] >= 4);
+            hidx[b] = table_hash(rk0[b], rk1[b]) & ((unsigned)S.tsize - 1u);
+            if (probing[b]) {
+              sa[b] = table[hidx[b]];
+              sb[b] = table[(hidx[b] + 1) & ((unsigned)S.tsize - 1u)];
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < NB; b++) {
+            const int i = b * 32 + lane;
+            if (probing[b]) r_h[b] = heuristic<DIM, ORD>(c, S, &S.es[i * NS], rk0[b], rk1[b]);
+          }
+          MPLB_TICK(1);
+          /* resolve */
+#pragma unroll
+          for (int b = 0; b < NB; b++) {
+            if (!probing[b]) continue;
+            const unsigned mask = (unsigned)S.tsize - 1u;
+            if (sa[b].node1 == 0u) { r_slot[b] = (int)hidx[b]; }
+            else if (slot_matches(sa[b], rk0[b], rk1[b], wide, rows, ROWB)) { r_nid[b] = (int)sa[b].node1 - 1; r_slot[b] = (int)hidx[b]; r_g[b] = sa[b].g; r_pg[b] = sa[b].pg; }
+            else if (sb[b].node1 == 0u) { r_slot[b] = (int)((hidx[b] + 1) & mask); }
+            else if (slot_matches(sb[b], rk0[b], rk1[b], wide, rows, ROWB)) { r_nid[b] = (int)sb[b].node1 - 1; r_slot[b] = (int)((hidx[b] + 1) & mask); r_g[b] = sb[b].g; r_pg[b] = sb[b].pg; }
+            else r_nid[b] = table_find_from(table, S.tsize, hidx[b] + 2, rk0[b], rk1[b], wide, rows, ROWB, &r_slot[b], &r_g[b], &r_pg[b]);
+          }
+        }
+        /* ---- B2: all collision samples of all controls, flat over 8-sample granules (warps 0-2) */
+        if (fast) {
+          const int t96 = tid; /* 0..95 */
+          for (int g = t96 >> 3; g < S.n_gran; g += 12) {
+            const int u = S.gl_u[g];
+            const int k = (int)S.gl_c[g] * 8 + (t96 & 7);
+            if (k < S.cnt[u] && sample_blocked_fast<DIM, ORD>(c, S, u, S.nsamp[u], k)) atomicMin(&S.first[u], k);
+          }
+        } else {
+          expand_b2_percontrol<DIM, ORD>(c, S, warp, lane, 3);
+        }
       }
+      MPLB_TICK(2);
       __syncthreads();
+      MPLB_TICK(3);
 
-      /* ---- P3 (warp 0): goal test of the current node (gs:146), relax (gs:79-143), terminate, pop the next node */
+      /* ================= P3 (warp 0): relax (gs:79-143), terminate (gs:146-161), take the next node (gs:64-68) */
       if (warp == 0) {
         const int cn = S.cur_node;
         const double cg = S.cur_g;
-        const bool goal_hit = goal_test_warp<DIM, ORD>(c, S, S.cur, lane);
-        /* prefetch the state row of the present heap top: it is the next pop unless a successor overtakes it */
-        int pf_node = -1;
-        unsigned long long pf_k0 = 0, pf_k1 = 0, pf_kh = 0;
-        double pf_st[NS];
-        if (lane == 0 && S.n_heap > 0) {
-          pf_node = S.hn[0] & 0x7fffffff;
-          const RowHdr *rh = reinterpret_cast<const RowHdr *>(rows + (size_t)pf_node * ROWB);
-          pf_k0 = rh->k0; pf_k1 = rh->k1; pf_kh = rh->kh;
-          const double *rs = reinterpret_cast<const double *>(rows + (size_t)pf_node * ROWB + sizeof(RowHdr));
-#pragma unroll
-          for (int f = 0; f < NS; f++) pf_st[f] = rs[f];
+        if (lane == 0) { /* bookkeeping of the current pop */
+          unsigned long long kh = S.cur_kh;
+          S.pop_hash = (S.pop_hash ^ kh) * 0x100000001B3ull;
+          if (!S.cur_tag) { S.n_closed++; S.closed_hash += kh; }
         }
-        if (lane == 0) { S.n_before = S.n_nodes; S.n_created = 0; }
-        __syncwarp();
-        long long ns_acc = 0;
-        for (int idx = 0; idx < c.nU; idx++) {
-          int v = S.verdict[idx];
-          if (v == 5) { /* finalize the collision outcome */
-            int first = S.first[idx];
+        int ns_acc = 0, nv_acc = 0;
+        bool created_any = false;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+          const int i = b * 32 + lane;
+          int v = (i < c.nU) ? S.verdict[i] : 0;
+          if (v == 5) {
+            int first = S.first[i];
             v = (first == 0x7fffffff) ? 3 : 2;
-            ns_acc += (v == 3) ? S.cnt[idx] : first + 1;
+            ns_acc += (v == 3) ? S.cnt[i] : first + 1;
           }
-          if (v < 3) continue;
-          /* resolve the node: prefetched id, or one created earlier in this expansion, or a new one */
-          int nid = S.nid[idx];
-          const unsigned long long k0 = S.k0[idx], k1 = S.k1[idx];
-          if (nid < 0 && S.n_created > 0) {
-            int hit = -1;
-            for (int q = lane; q < S.n_created; q += 32) {
-              int j = S.cr_idx[q];
-              if (S.k0[j] == k0 && S.k1[j] == k1) hit = j;
+          const bool valid = v >= 3;
+          const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+          nv_acc += __popc(vmask);
+          if (vmask == 0u) continue;
+          const bool found = valid && r_nid[b] >= 0;
+          const bool isnew = valid && r_nid[b] < 0;
+          /* hazards: two successors -> one node or one table slot; later batches vs nodes created earlier in this pop */
+          bool hazard = false;
+          {
+            unsigned newm = __ballot_sync(0xffffffffu, isnew);
+            unsigned fndm = __ballot_sync(0xffffffffu, found);
+            if (isnew) {
+              unsigned m1 = __match_any_sync(newm, rk0[b] ^ (rk1[b] * 0x9E3779B97F4A7C15ull));
+              unsigned m2 = __match_any_sync(newm, r_slot[b]);
+              hazard = (__popc(m1) > 1) || (__popc(m2) > 1);
             }
-            unsigned bm = __ballot_sync(0xffffffffu, hit >= 0);
-            if (bm) {
-              int j = __shfl_sync(0xffffffffu, hit, __ffs(bm) - 1);
-              nid = S.nid[j];
-              if (lane == 0) { S.nid[idx] = nid; S.ng[idx] = S.ng[j]; S.nh[idx] = S.nh[j]; S.npg[idx] = S.npg[j]; S.npos[idx] = S.npos[j]; S.nfl[idx] = S.nfl[j]; }
+            if (found) { unsigned m3 = __match_any_sync(fndm, r_nid[b]); hazard = hazard || (__popc(m3) > 1); }
+            if (NB > 1 && created_any && isnew) hazard = true; /* probe predates nodes created by earlier batches */
+            if (NB > 1 && found) /* an earlier batch of this pop may already have relaxed the same node */
+              for (int q = 0; q < b * 32; q++) hazard = hazard || (S.nid[q] == r_nid[b]);
+            hazard = __any_sync(0xffffffffu, hazard);
+          }
+          if (hazard) {
+            if (lane == 0) relax_serial<DIM, ORD>(c, S, H, table, hot, rows, b * 32, min(c.nU, b * 32 + 32), wide);
+            __syncwarp();
+            created_any = true;
+            continue;
+          }
+          const double tentative = dadd(cg, valid ? S.cost[i] : 0.0); /* gs:107 */
+          const bool improve = found && tentative < r_g[b];
+          const bool tie = found && tentative == r_g[b] && cg > r_pg[b]; /* recoverTraj tie rule (gs:398-403) */
+          const unsigned newm = __ballot_sync(0xffffffffu, isnew);
+          int nid = r_nid[b];
+          if (isnew) nid = S.n_nodes + __popc(newm & lt_mask);
+          const int n_new = __popc(newm);
+          created_any = created_any || (n_new > 0);
+          if (valid) S.nid[i] = nid;
+          double hval = r_h[b];
+          int fl = 0, hpos = -1;
+          if (improve) { const NodeHot hn = hot[nid]; hval = hn.h; fl = hn.flags; hpos = hn.heap_pos; } /* rare dependent load */
+          const double f = dadd(tentative, dmul(c.eps, hval));
+          /* lane-parallel stores */
+          if (isnew) { /* gs:84-88: the node's coord is this (first) discoverer's state */
+            RowHdr *rh = reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB);
+            rh->k0 = rk0[b]; rh->k1 = rk1[b]; rh->parent = cn; rh->slot = r_slot[b]; rh->pad = 0;
+            double *rs = reinterpret_cast<double *>(rows + (size_t)nid * ROWB + sizeof(RowHdr));
+#pragma unroll
+            for (int q = 0; q < NS; q++) rs[q] = S.es[i * NS + q];
+            Slot sl; sl.k0 = rk0[b]; sl.k1lo = (unsigned int)rk1[b]; sl.node1 = (unsigned)(nid + 1); sl.g = tentative; sl.pg = cg;
+            table[r_slot[b]] = sl;
+            NodeHot hn; hn.g = tentative; hn.h = hval; hn.pg = cg; hn.heap_pos = -1; hn.action = (short)i; hn.flags = 1; hn.pad0 = 0;
+            hot[nid] = hn;
+          } else if (improve) {
+            NodeHot hn; hn.g = tentative; hn.h = hval; hn.pg = cg; hn.heap_pos = hpos; hn.action = (short)i;
+            hn.flags = (unsigned char)(fl | 1); hn.pad0 = 0;
+            hot[nid] = hn;
+            table[r_slot[b]].g = tentative; table[r_slot[b]].pg = cg;
+            reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB)->parent = cn;
+          } else if (tie) {
+            hot[nid].pg = cg; hot[nid].action = (short)i;
+            table[r_slot[b]].pg = cg;
+            reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB)->parent = cn;
+          }
+          if (lane == 0) S.n_nodes += n_new;
+          /* heap operations in control order (gs:129-141) */
+          unsigned hm = __ballot_sync(0xffffffffu, isnew || improve);
+          while (hm) {
+            const int j = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const double jf = __shfl_sync(0xffffffffu, f, j), jg = __shfl_sync(0xffffffffu, tentative, j);
+            const int jn = __shfl_sync(0xffffffffu, nid, j), jfl = __shfl_sync(0xffffffffu, fl, j);
+            int jpos = __shfl_sync(0xffffffffu, hpos, j);
+            const bool jnew = (newm >> j) & 1u;
+            if (!jnew && (jfl & 1) && !(jfl & 2)) { /* increase(): f lowered, sift up only (gs:131-133) */
+              if (jpos < 0 || jpos >= S.n_heap || (H.node_at(jpos) & 0x7fffffff) != jn) jpos = hot[jn].heap_pos; /* moved by an earlier sift of this pop */
+              H.sift_up_warp(jpos, jf, jg, jn, lane);
+            } else {
+              int tag = jn;
+              if (!jnew && (jfl & 2)) { /* closed node re-pushed (gs:135-141): refresh g copies of its stale entries */
+                for (int q = lane; q < S.n_heap; q += 32) if ((H.node_at(q) & 0x7fffffff) == jn) H.set_g(q, jg);
+                tag = jn | 0x80000000;
+                __syncwarp();
+              }
+              const int np = S.n_heap;
+              __syncwarp();
+              H.sift_up_warp(np, jf, jg, tag, lane);
+              if (lane == 0) S.n_heap = np + 1;
               __syncwarp();
             }
           }
-          if (nid < 0) { /* gs:84-88: create the node; its coord is this (first) discoverer's state */
-            int slot = S.slot[idx];
-            /* the probe's end slot may have been taken by a node created earlier in this expansion */
-            bool taken = false;
-            for (int q = lane; q < S.n_created; q += 32) taken = taken || (S.slot[S.cr_idx[q]] == slot);
-            taken = __any_sync(0xffffffffu, taken);
-            if (lane == 0) {
-              if (taken) {
-                unsigned mask = (unsigned)S.tsize - 1u;
-                unsigned i = (unsigned)slot;
-                while (table[i].node1 != 0u) i = (i + 1) & mask;
-                slot = (int)i;
-                S.slot[idx] = slot;
-              }
-              nid = S.n_nodes++;
-              double hval = heuristic<DIM, ORD>(c, S, &S.es[idx * NS], k0, k1);
-              RowHdr *rh = reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB);
-              rh->k0 = k0; rh->k1 = k1; rh->kh = S.kh[idx]; rh->parent = -1; rh->pad = 0;
-              double *rs = reinterpret_cast<double *>(rows + (size_t)nid * ROWB + sizeof(RowHdr));
-#pragma unroll
-              for (int f = 0; f < NS; f++) rs[f] = S.es[idx * NS + f];
-              Slot sl; sl.k0 = k0; sl.k1lo = (unsigned int)k1; sl.node1 = (unsigned)(nid + 1);
-              table[slot] = sl;
-              S.nid[idx] = nid; S.ng[idx] = kInf; S.nh[idx] = hval; S.npg[idx] = 0.0; S.npos[idx] = -1; S.nfl[idx] = 0;
-              S.cr_idx[S.n_created] = idx;
-              S.n_created = S.n_created + 1;
-            }
-            __syncwarp();
-            nid = S.nid[idx];
-          }
-          /* relax (lane 0) */
-          double new_g = 0.0, new_pg = 0.0; int new_fl = 0, new_pos = 0; bool changed = false;
-          if (lane == 0) {
-            S.n_valid++;
-            double tentative = dadd(cg, S.cost[idx]); /* gs:107 */
-            double gold = S.ng[idx];
-            int fl = S.nfl[idx];
-            if (tentative < gold) { /* gs:109-141 */
-              double f = dadd(tentative, dmul(c.eps, S.nh[idx]));
-              NodeHot hn; hn.g = tentative; hn.h = S.nh[idx]; hn.pg = cg; hn.action = (short)idx; hn.pad0 = 0;
-              reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB)->parent = cn;
-              if ((fl & 1) && !(fl & 2)) { /* increase(): f lowered, sift up only (gs:131-133) */
-                int pos = S.npos[idx];
-                if (pos < 0 || pos >= S.n_heap || (H.node_at(pos) & 0x7fffffff) != nid) pos = hot[nid].heap_pos; /* stale cache */
-                hn.flags = (unsigned char)fl; hn.heap_pos = pos;
-                hot[nid] = hn;
-                H.sift_up(pos, f, tentative, nid, hot);
-              } else {
-                int tag = nid;
-                if (fl & 2) { /* closed node re-pushed (gs:135-141): refresh g copies of its stale entries */
-                  for (int q = 0; q < S.n_heap; q++) if ((H.node_at(q) & 0x7fffffff) == nid) H.set_g(q, tentative);
-                  tag = nid | 0x80000000;
-                }
-                fl |= 1;
-                hn.flags = (unsigned char)fl; hn.heap_pos = S.n_heap;
-                hot[nid] = hn;
-                H.sift_up(S.n_heap, f, tentative, tag, hot);
-                S.n_heap++;
-              }
-              changed = true; new_g = tentative; new_pg = cg; new_fl = fl; new_pos = -2; /* position unknown: re-read on use */
-            } else if (tentative == gold && cg > S.npg[idx]) { /* recoverTraj tie: larger predecessor g wins (gs:398-403) */
-              hot[nid].pg = cg; hot[nid].action = (short)idx;
-              reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB)->parent = cn;
-              changed = true; new_g = gold; new_pg = cg; new_fl = fl; new_pos = S.npos[idx];
-            }
-          }
-          /* keep the cached copies of this node coherent for later successors that map to it */
-          changed = __shfl_sync(0xffffffffu, changed, 0);
-          if (changed) {
-            new_g = __shfl_sync(0xffffffffu, new_g, 0); new_pg = __shfl_sync(0xffffffffu, new_pg, 0);
-            new_fl = __shfl_sync(0xffffffffu, new_fl, 0); new_pos = __shfl_sync(0xffffffffu, new_pos, 0);
-            for (int j = lane; j < c.nU; j += 32)
-              if (S.nid[j] == nid) { S.ng[j] = new_g; S.npg[j] = new_pg; S.nfl[j] = new_fl; S.npos[j] = new_pos; }
-          }
-          __syncwarp();
         }
-        /* ---- termination (gs:146-161) and the next pop (gs:64-68) */
+        MPLB_TICK(5);
+        /* ---- termination and the next pop */
+        ns_acc = __reduce_add_sync(0xffffffffu, ns_acc);
         if (lane == 0) {
           S.n_samples += ns_acc;
+          S.n_valid += nv_acc;
           int status = -1;
           if (S.key_bad) status = MPLB_PLAN_KEY_RANGE;
-          else if (goal_hit) status = MPLB_PLAN_OK;
+          else if (S.goal_hit) status = MPLB_PLAN_OK;
           else if (c.max_num > 0 && S.pops >= c.max_num) status = MPLB_PLAN_MAX_EXPAND;
           else if (S.n_heap == 0) status = MPLB_PLAN_QUEUE_EMPTY;
           if (status >= 0) S.status = status;
           else {
-            int tagged = S.hn[0];
-            double topg = S.hg[0];
-            int n = S.n_heap - 1;
-            if (n > 0) { double lf, lg; int ln; H.get(n, lf, lg, ln); H.sift_down(n, 0, lf, lg, ln, hot); }
+            const int tagged = S.hn[0];
+            const double topg = S.hg[0];
+            const int n = S.n_heap - 1;
+            if (n > 0) { H.get(n, S.sd_f, S.sd_g, S.sd_n); S.sd_pending = 1; } /* sift-down deferred to the heap warp */
             S.n_heap = n;
-            int nx = tagged & 0x7fffffff;
-            unsigned long long k0, k1, kh;
+            const int nx = tagged & 0x7fffffff;
+            unsigned long long k0, k1;
             if (nx >= S.n_before) { /* created in this expansion: forward its state from shared memory */
-              int j = -1;
-              for (int q = 0; q < S.n_created; q++) if (S.nid[S.cr_idx[q]] == nx) { j = S.cr_idx[q]; break; }
-              k0 = S.k0[j]; k1 = S.k1[j]; kh = S.kh[j];
+              int j = 0;
+              for (int q = 0; q < c.nU; q++) if (S.nid[q] == nx) { j = q; break; }
+              k0 = S.k0[j]; k1 = S.k1[j];
 #pragma unroll
-              for (int f = 0; f < NS; f++) pf_st[f] = S.es[j * NS + f];
-            } else if (nx == pf_node) {
-              k0 = pf_k0; k1 = pf_k1; kh = pf_kh;
+              for (int f = 0; f < NS; f++) S.cur[f] = S.es[j * NS + f];
+            } else if (nx == S.pf_node) {
+              k0 = S.pf_k0; k1 = S.pf_k1;
+#pragma unroll
+              for (int f = 0; f < NS; f++) S.cur[f] = S.pf_st[f];
             } else {
               const RowHdr *rh = reinterpret_cast<const RowHdr *>(rows + (size_t)nx * ROWB);
-              k0 = rh->k0; k1 = rh->k1; kh = rh->kh;
+              k0 = rh->k0; k1 = rh->k1;
               const double *rs = reinterpret_cast<const double *>(rows + (size_t)nx * ROWB + sizeof(RowHdr));
 #pragma unroll
-              for (int f = 0; f < NS; f++) pf_st[f] = rs[f];
+              for (int f = 0; f < NS; f++) S.cur[f] = rs[f];
             }
-#pragma unroll
-            for (int f = 0; f < NS; f++) S.cur[f] = pf_st[f];
             unpack_ints<NS>(c, k0, k1, S.cur_ints);
             S.cur_node = nx;
             S.cur_g = topg;
-            S.pop_hash = (S.pop_hash ^ kh) * 0x100000001B3ull;
-            if (!(tagged & 0x80000000)) { S.n_closed++; S.closed_hash += kh; }
+            S.cur_tag = (tagged & 0x80000000) ? 1 : 0;
             hot[nx].flags = 3; /* iterationclosed = true (gs:68); a popped node is always opened */
             if (a.want_poplog && S.pops < a.cap) poplog[S.pops] = nx;
             S.pops++;
           }
         }
+        MPLB_TICK(6);
       }
       __syncthreads();
     }
+#ifdef MPLB_PHASE_TIMING
+    if (tid == 0 && a.phase_cycles) for (int k = 0; k < 8; k++) a.phase_cycles[(size_t)pid * 8 + k] = ph[k];
+#endif
 
     /* ---------------- results + recoverTraj (gs:369-455) */
     if (tid == 0) {
@@ -796,6 +1031,8 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
     }
     if (a.want_poplog) { /* retained plan: expose the shared-memory part of the heap to the host getters */
       __syncthreads();
+      if (tid == 0 && S.sd_pending) { H.sift_down(S.n_heap, 0, S.sd_f, S.sd_g, S.sd_n); S.sd_pending = 0; }
+      __syncthreads();
       for (int i = tid; i < S.n_heap && i < SM::HCAP; i += MPLB_NT) {
         HeapEnt e; e.f = S.hf[i]; e.g = S.hg[i]; e.node = S.hn[i]; e.pad = 0;
         spill[i] = e;
@@ -805,16 +1042,22 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
 }
 
 /* ---------------------------------------------------------------- get_succ for arbitrary states (parity artefact) */
-template <int DIM, int ORD, int MAXU>
+template <int DIM, int ORD, int NB>
 __global__ void __launch_bounds__(MPLB_NT) expand_trace_kernel(const DevCfg c, const mplb_waypoint *states, int n_states,
                                                                mplb_prim_trace *rows) {
   constexpr int NS = DIM * ORD;
   constexpr int NW = MPLB_NT / 32;
-  using SM = PlanSmem<DIM, ORD, MAXU>;
+  using SM = PlanSmem<DIM, ORD, NB>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM &S = *reinterpret_cast<SM *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < c.nU * 3; i += MPLB_NT) S.U[i] = c.U[i];
+  for (int i = tid; i < c.nU; i += MPLB_NT) {
+    double J = 0.0;
+    for (int ax = 0; ax < DIM; ax++) { double u = c.U[i * 3 + ax]; J = dadd(J, dmul(dmul(u, u), c.dt)); }
+    S.cost[i] = dadd(J, dmul(c.w, c.dt));
+  }
+  if (c.use_fast) for (int i = tid; i < MPLB_NCAP; i += MPLB_NT) S.tcnt_s[i] = (i <= c.n_hi) ? c.tcnt[i] : 0;
   for (int s = blockIdx.x; s < n_states; s += gridDim.x) {
     __syncthreads();
     if (tid == 0) {
@@ -829,7 +1072,7 @@ __global__ void __launch_bounds__(MPLB_NT) expand_trace_kernel(const DevCfg c, c
       S.key_bad = 0;
     }
     __syncthreads();
-    for (int i = tid; i < c.nU; i += MPLB_NT) expand_b1<DIM, ORD>(c, S, i);
+    for (int i = tid; i < c.nU; i += MPLB_NT) { unsigned long long k0, k1; expand_b1<DIM, ORD>(c, S, i, k0, k1); }
     __syncthreads();
     expand_b2_percontrol<DIM, ORD>(c, S, warp, lane, NW);
     __syncthreads();
@@ -843,7 +1086,7 @@ __global__ void __launch_bounds__(MPLB_NT) expand_trace_kernel(const DevCfg c, c
       r.block_idx = -1;
       if (v == 2) {
         int cell = -1;
-        sample_blocked<DIM, ORD>(c, S, i, c.ttab[c.toff[S.nsamp[i]] + S.first[i]], &cell);
+        sample_blocked_exact<DIM, ORD>(c, S, i, c.ttab[c.toff[S.nsamp[i]] + S.first[i]], &cell);
         r.block_idx = cell;
       }
       r.cost = (v >= 3) ? S.cost[i] : (v == 2 ? __longlong_as_double(0x7ff0000000000000ll) : 0.0);

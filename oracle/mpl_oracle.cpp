@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -404,6 +405,7 @@ struct Planner {
   std::vector<int> pop_order;
   std::vector<int> traj_actions;
   std::vector<int> traj_nodes;  // parent node of each segment
+  long long dbg_increase = 0;  // decrease-key events (diagnostics, printed when ORC_DEBUG is set)
   orc_result last;
 
   /* em:25-45 */
@@ -563,7 +565,7 @@ struct Planner {
         if (tentative < sn.g) {  // gs:107-141
           sn.g = tentative;
           double fval = sn.g + eps * sn.h;
-          if (sn.opened && !sn.closed) heap.increase(sn.heap_entry, fval);
+          if (sn.opened && !sn.closed) { heap.increase(sn.heap_entry, fval); dbg_increase++; }
           else { sn.heap_entry = heap.push(fval, sid); nodes[sid].opened = true; }
         }
       }
@@ -572,6 +574,7 @@ struct Planner {
       if (heap.empty()) { status = 3; break; }                                           // gs:157-161
     }
     last.pops = expand_iteration;
+    if (std::getenv("ORC_DEBUG")) std::fprintf(stderr, "orc: pops %d nodes %zu increase %lld valid %lld\n", expand_iteration, nodes.size(), dbg_increase, (long long)last.n_valid);
     last.n_nodes = (int)nodes.size();
     last.n_open = (int)heap.q.size();
     last.n_closed = n_closed;

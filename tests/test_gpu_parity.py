@@ -178,3 +178,49 @@ def test_map_ops():
     out[:, :-1, :][occ[:, 1:, :]] = 100
     assert np.array_equal(mu.getMap(), out.reshape(-1))
     assert mu.getRes() == m.res and np.array_equal(mu.getDim(), m.dim) and np.array_equal(mu.getOrigin(), m.origin)
+
+
+def test_duplicate_sibling_hazard():
+    """Controls so small that several successors of one expansion share one lattice key (and one table slot):
+    exercises the serial hazard path; the reference keeps the FIRST discoverer's state (graph_search.h:84-88)."""
+    m, dim, params, U, start, goal = load_config("corridor")
+    U = maps.make_U(0.008, 1, 2)
+    params = dict(v_max=1.0, a_max=1.0, dt=1.0, max_num=300)
+    pl, op = make_pair(m, dim, params, U)
+    sg, so = waypoint_pair(start, mp.ACC, vel=[0.5, 0.1])
+    gg, go = waypoint_pair(goal, mp.ACC)
+    pl.plan(sg, gg)
+    ro = op.plan(so, go)
+    assert_results_equal(pl.result(), ro)
+    on = _nodes_by_key(op.nodes(ro["n_nodes"]))
+    gnk = _nodes_by_key(pl.getNodes())
+    assert set(on) == set(gnk)
+    for k, a in gnk.items():
+        assert np.array_equal(a["state"][:6], on[k]["state"][:6]) and a["g"] == on[k]["g"], k
+
+
+def test_jrk_125_controls_3d():
+    """BASELINE configs[4] shape at test size: 3D, jerk control, |U| = 125 (u in {-2..2}^3), dt = 0.5 — the
+    four-batch (|U| > 32) kernel instantiation."""
+    m = maps.load_fixture("skir")
+    U = maps.make_U(2.0, 2, 3)
+    assert U.shape[0] == 125
+    params = dict(v_max=3.0, a_max=2.0, dt=0.5, max_num=400, tol_pos=0.5)
+    pl, op = make_pair(m, 3, params, U)
+    sg, so = waypoint_pair([5.5, 5.5, 0.5], mp.JRK)
+    gg, go = waypoint_pair([1.5, 1.5, 5.5], mp.JRK)
+    pl.plan(sg, gg)
+    ro = op.plan(so, go)
+    assert_results_equal(pl.result(), ro)
+    assert np.array_equal(pl.getActions(), op.actions(ro["n_seg"]))
+    gn = pl.getNodes()
+    assert np.array_equal(gn["key"][pl.getPopLog()], op.pop_keys(ro["pops"]))
+    # batch of a few more queries through the same instantiation
+    S, G = maps.sample_queries(m, 12, seed=5)
+    sg, so = waypoint_pair(S, mp.JRK)
+    gg, go = waypoint_pair(G, mp.JRK)
+    rg, ag, _ = pl.plan_batch(sg, gg, max_seg=48)
+    ro2, ao = op.plan_batch(so, go, nthreads=8, max_seg=48)
+    for i in range(len(S)):
+        assert_results_equal(rg[i], ro2[i], i)
+    assert np.array_equal(ag, ao)

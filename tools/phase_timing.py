@@ -1,0 +1,47 @@
+#!/usr/bin/env python3
+"""Diagnostics: build libmplb with -DMPLB_PHASE_TIMING into a separate .so, run the bench batch once and print
+the per-phase clock64() cycle shares of thread 0 (the serial chain of a plan).  Not part of the product."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+from mpl_ros_b200 import build as B  # noqa: E402
+
+out = os.path.join(ROOT, "mpl_ros_b200", "libmplb_prof.so")
+if "--build-only" in sys.argv or not os.path.exists(out):
+    subprocess.check_call([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")] + B.NVCC_FLAGS + ["-DMPLB_PHASE_TIMING", "-o", out, B.SRC])
+    if "--build-only" in sys.argv:
+        sys.exit(0)
+from mpl_ros_b200 import _lib  # noqa: E402
+_lib.LIB_PATH = out
+import mpl_ros_b200 as mp  # noqa: E402
+from mpl_ros_b200 import maps  # noqa: E402
+import bench  # noqa: E402
+
+m = maps.levine256()
+mu = mp.VoxelMapUtil(); mu.setMap(m.origin, m.dim, m.data, m.res); mu.freeUnknown()
+pl = mp.VoxelMapPlanner(False); pl.setMapUtil(mu)
+pl.setVmax(2.0); pl.setAmax(1.0); pl.setDt(1.0); pl.setU(maps.make_U(1.0, 1, 3)); pl.setTol(0.5)
+s, g = bench.make_queries(m, 0)
+for _ in range(2):
+    res, _, _ = pl.plan_batch(s, g, max_seg=64)
+print("kernel_ms", pl.last_batch_stats())
+ph = np.zeros((len(s), 8), dtype=np.int64)
+L = _lib.lib()
+L.mplb_debug_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+assert L.mplb_debug_phase_cycles(pl._h, ph.ctypes.data_as(C.c_void_p), len(s)) == 0
+names = ["P1 get_succ(B1)+scan+sync", "P2 probe+prefetch", "P2 samples", "P2 barrier wait", "P3 goal+prefetch issue",
+         "P3 relax loop", "P3 terminate+pop", "loop top (sync+checks)"]
+pops = res["pops"].astype(np.float64)
+tot = ph.sum()
+print("total pops", int(pops.sum()), "cycles/pop (all plans)", tot / pops.sum())
+for k, nm in enumerate(names):
+    print("%-28s %6.1f%%  %8.0f cyc/pop" % (nm, 100.0 * ph[:, k].sum() / tot, ph[:, k].sum() / pops.sum()))
+big = np.argsort(-pops)[:5]
+for i in big:
+    print("plan", i, "pops", int(pops[i]), "cycles/pop", ph[i].sum() / pops[i], (ph[i] / pops[i]).astype(int).tolist())
