@@ -178,7 +178,7 @@ Layout make_layout(int cap, int ns, int nU) {
   while ((long long)ts < 2ll * (cap + nU)) ts <<= 1;
   L.tsize_max = ts;
   size_t o = 0;
-  L.row_bytes = sizeof(RowHdr) + (size_t)ns * sizeof(double);
+  L.row_bytes = (sizeof(RowHdr) + (size_t)ns * sizeof(double) + 15) & ~(size_t)15;
   o += align_up((size_t)cap * sizeof(NodeHot), 256);
   L.off_rows = o;
   o += align_up((size_t)cap * L.row_bytes, 256);
@@ -201,6 +201,8 @@ int control_order(int control) {
     default: return 0;
   }
 }
+
+double margin_cells(double vmax_eff, double dt, double res) { return std::max(2.0, 2.0 * vmax_eff * dt) / res; }
 
 int bits_for(long long range) {
   int b = 1;
@@ -264,8 +266,8 @@ int build_cfg(mplb_planner *p, int control) {
   c.ttab = p->d_ttab.p; c.toff = p->d_toff.p; c.tcnt = p->d_tcnt.p; c.n_hi = n_hi;
   c.tt_total = (int)ttab.size();
   c.inv_res = 1.0 / m->res;
-  /* filtered sampling: FP32 displacement error <= ~14 * 2^-24 * (Dsum + 1) cells, Dsum = sum of the largest term
-   * magnitudes of the displacement polynomial in cells; the guard band is 2^-19 * (Dsum + 2) (>= 2x that bound). */
+  /* filtered sampling (sample_blocked_filtered): FP64 Horner in cells; magnitude bound M = largest cell coordinate
+   * + sum of the largest displacement terms; evaluation error < 2^-45 * M, guard band 2^-40 * M. */
   {
     double bnd[5] = {0, p->v_max, p->a_max, p->j_max, 0};
     bnd[ord] = umax; /* the control itself is the top coefficient */
@@ -276,11 +278,12 @@ int build_cfg(mplb_planner *p, int control) {
       if (!(bnd[d] > 0) && d < ord) known = false;
       dsum += std::fabs(bnd[d]) * tp / fact / m->res;
     }
-    double delta = std::ldexp(dsum + 2.0, -19);
-    c.use_fast = (known && n_hi < MPLB_NCAP && c.tt_total <= MPLB_TT_CAP && delta <= 0.01) ? 1 : 0;
-    c.fast_delta = (float)delta;
+    double maxc = 0;
+    for (int i = 0; i < p->dim; i++) maxc = std::max(maxc, (double)m->nd[i]);
+    double delta = std::ldexp(maxc + margin_cells(vmax_eff, p->dt, m->res) + dsum + 2.0, -40);
+    c.use_fast = (known && n_hi < MPLB_NCAP && delta <= 1e-6) ? 1 : 0;
+    c.fast_delta = delta;
   }
-
   /* key packing: field f = axis*ord + d; pos fields cover the map plus a margin (end states are not collision
    * tested at t = T, em:99), derivative fields cover their dynamic bound (validated primitives, pr:449-496). */
   double margin = std::max(2.0, 2.0 * vmax_eff * p->dt);
@@ -406,7 +409,7 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
     a.want_poplog = retain ? 1 : 0; a.slot_of_plan = retain ? p->d_slot.p : nullptr;
     a.overflow_count = p->d_ctrl.p + 1; a.overflow_list = p->d_over.p;
 #ifdef MPLB_PHASE_TIMING
-    CUDA_TRY(p->d_phase.reserve((size_t)n * 8));
+    CUDA_TRY(p->d_phase.reserve((size_t)n * 16));
     a.phase_cycles = p->d_phase.p;
 #endif
 #define LAUNCH_CALL(D, O, M) rc = launch_batch<D, O, M>(c, a, slots, s)
@@ -828,7 +831,7 @@ int mplb_expand(mplb_planner *p, const mplb_waypoint *states, int n, mplb_prim_t
 /* diagnostics build only (not part of the ABI): per-plan phase cycle accumulators of the last batch */
 int mplb_debug_phase_cycles(mplb_planner *p, long long *out, int n) {
   if (!p || !out) return fail(MPLB_ERR_ARG, "null argument");
-  CUDA_TRY(cudaMemcpy(out, p->d_phase.p, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(out, p->d_phase.p, (size_t)n * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return MPLB_OK;
 }
 #endif

@@ -58,7 +58,7 @@ struct DevCfg {
   double inv_res;   /* 1/res, used only inside filters whose doubtful cases fall back to the exact division */
   int use_fast;     /* tables fit in shared memory and every dynamic bound is known */
   int tt_total;     /* number of entries of ttab */
-  float fast_delta; /* guard band around voxel boundaries, in cells (>= proven FP32 error bound) */
+  double fast_delta; /* guard band around rounding ties of the filtered sampler, in cells */
 };
 
 /* ------------------------------------------------------------------------------------------------

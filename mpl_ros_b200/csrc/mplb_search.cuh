@@ -109,7 +109,9 @@ struct BatchArgs {
 
 #ifdef MPLB_PHASE_TIMING
 #define MPLB_TICK(k) do { if (tid == 0) { long long t__ = clock64(); ph[k] += t__ - tlast; tlast = t__; } } while (0)
+#define MPLB_COUNT(k, v) atomicAdd(&S.dbg[k], (unsigned long long)(v))
 #else
+#define MPLB_COUNT(k, v) do { } while (0)
 #define MPLB_TICK(k) do { } while (0)
 #endif
 
@@ -134,13 +136,11 @@ struct PlanSmem {
   /* per-plan constants */
   double U[MAXU * 3];
   double cost[MAXU];   /* J(u) + w*dt, eb:343-345 */
-  float Au[MAXU * 3];  /* top polynomial coefficient of the fast sampling path, in cells */
-  float ttf[MPLB_TT_CAP];
+  double Au[MAXU * 3]; /* top polynomial coefficient of the filtered sampling path, in cells */
   int toff_s[MPLB_NCAP], tcnt_s[MPLB_NCAP];
   /* per-pop sampling base (fast path): cell coordinate of the parent = Y0 + fy0, lower coefficients in cells */
-  int Y0[3];
-  float fy0[3];
-  float Ap[3 * 3];
+  double y0[3];
+  double Ap[3 * 3];
   /* per-control results of get_succ */
   double es[MAXU * NS]; /* end states, [u][d*DIM+ax] */
   unsigned long long k0[MAXU], k1[MAXU];
@@ -161,6 +161,9 @@ struct PlanSmem {
   int n_nodes, n_heap, tsize, pops, n_closed, status, plan_idx, key_bad;
   long long n_samples, n_valid;
   unsigned long long pop_hash, closed_hash;
+#ifdef MPLB_PHASE_TIMING
+  unsigned long long dbg[8];
+#endif
 };
 
 /* ---------------------------------------------------------------- heap in shared memory with global spill */
@@ -345,6 +348,9 @@ __device__ __forceinline__ void expand_b1(const DevCfg &c, SM &S, int i, unsigne
 /* One collision sample, exact (em:100-104,119): true when the sample at time t of control i is outside or occupied. */
 template <int DIM, int ORD, class SM>
 __device__ __noinline__ bool sample_blocked_exact(const DevCfg &c, const SM &S, int i, double t, int *cell_idx) {
+#ifdef MPLB_PHASE_TIMING
+  atomicAdd(const_cast<unsigned long long *>(&S.dbg[4]), 1ull);
+#endif
   int pn[3] = {0, 0, 0};
   bool outside = false;
 #pragma unroll
@@ -358,30 +364,29 @@ __device__ __noinline__ bool sample_blocked_exact(const DevCfg &c, const SM &S, 
   return brick_occupied<DIM>(c, pn[0], pn[1], pn[2]);
 }
 
-/* Filtered sample: FP32 displacement in cells relative to the parent's cell coordinate.  The voxel is decided in
- * FP32 when every axis is farther than c.fast_delta from a voxel boundary (error bound set by the host from the
- * dynamic limits); otherwise the exact routine decides. */
+/* Filtered sample.  The cell coordinate y = (p(t) - origin)/res is evaluated as one FP64 Horner chain in cells
+ * (parent coordinate y0 and lower coefficients per pop, top coefficient per control; FMA allowed because the
+ * value is only used to decide a rounding).  Its error is < 2^-45 * (|y| + displacement terms); when y - 0.5 is
+ * farther than c.fast_delta (>= 2^-40 * the same magnitude, set by the host) from a rounding tie, round(y - 0.5)
+ * equals the reference's round((p - origin)/res - 0.5) (mu:103-108).  Otherwise *sure is cleared and the caller
+ * evaluates the exact formula. */
 template <int DIM, int ORD, class SM>
-__device__ __forceinline__ bool sample_blocked_fast(const DevCfg &c, const SM &S, int i, int n, int k) {
-  const float t = S.ttf[S.toff_s[n] + k];
+__device__ __forceinline__ bool sample_blocked_filtered(const DevCfg &c, const SM &S, int i, double t, bool *sure) {
   int pn[3] = {0, 0, 0};
-  bool sure = true;
+  bool ok = true, outside = false;
 #pragma unroll
   for (int ax = 0; ax < DIM; ax++) {
-    float dy = S.Au[i * 3 + ax]; /* Horner over t, coefficients in cells: top one per control, lower ones per pop */
+    double dy = S.Au[i * 3 + ax];
 #pragma unroll
-    for (int d = ORD - 2; d >= 0; d--) dy = fmaf(dy, t, S.Ap[d * 3 + ax]);
-    dy *= t;
-    float w = (S.fy0[ax] + dy) - 0.5f;
-    float r = rintf(w);
-    sure = sure && (fabsf(w - r) < 0.5f - c.fast_delta);
-    pn[ax] = S.Y0[ax] + (int)r;
+    for (int d = ORD - 2; d >= 0; d--) dy = __fma_rn(dy, t, S.Ap[d * 3 + ax]);
+    double w = __fma_rn(dy, t, S.y0[ax]) - 0.5;
+    double r = rint(w);
+    ok = ok && (fabs(w - r) < 0.5 - c.fast_delta);
+    pn[ax] = __double2int_rn(r);
+    outside = outside || pn[ax] < 0 || pn[ax] >= c.nd[ax];
   }
-  if (!sure) return sample_blocked_exact<DIM, ORD>(c, S, i, c.ttab[c.toff[n] + k], nullptr);
-  bool outside = false;
-#pragma unroll
-  for (int ax = 0; ax < DIM; ax++) outside = outside || pn[ax] < 0 || pn[ax] >= c.nd[ax];
-  if (outside) return true;
+  *sure = ok;
+  if (outside || !ok) return outside;
   return brick_occupied<DIM>(c, pn[0], pn[1], pn[2]);
 }
 
@@ -499,7 +504,7 @@ template <int DIM, int ORD, class SM>
 __device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, const HeapView<SM> &H, Slot *table, NodeHot *hot,
                                           unsigned char *rows, int i0, int i1, bool wide) {
   constexpr int NS = DIM * ORD;
-  constexpr size_t ROWB = sizeof(RowHdr) + NS * sizeof(double);
+  constexpr size_t ROWB = (sizeof(RowHdr) + NS * sizeof(double) + 15) & ~(size_t)15; /* 16-byte aligned rows */
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
   const int cn = S.cur_node;
   const double cg = S.cur_g;
@@ -559,7 +564,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
   constexpr int NS = DIM * ORD;
   constexpr int NW = MPLB_NT / 32;
   using SM = PlanSmem<DIM, ORD, NB>;
-  constexpr size_t ROWB = sizeof(RowHdr) + NS * sizeof(double);
+  constexpr size_t ROWB = (sizeof(RowHdr) + NS * sizeof(double) + 15) & ~(size_t)15; /* 16-byte aligned rows */
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM &S = *reinterpret_cast<SM *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -583,11 +588,10 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
     for (int ax = 0; ax < DIM; ax++) { double u = c.U[i * 3 + ax]; J = dadd(J, dmul(dmul(u, u), c.dt)); } /* pr:92-122,403-407 */
     S.cost[i] = dadd(J, dmul(c.w, c.dt));                                                                /* eb:343-345 */
     const double fact = (ORD == 1) ? 1.0 : (ORD == 2) ? 2.0 : (ORD == 3) ? 6.0 : 24.0;
-    for (int ax = 0; ax < 3; ax++) S.Au[i * 3 + ax] = (ax < DIM) ? (float)(c.U[i * 3 + ax] / fact * c.inv_res) : 0.0f;
+    for (int ax = 0; ax < 3; ax++) S.Au[i * 3 + ax] = (ax < DIM) ? c.U[i * 3 + ax] / fact * c.inv_res : 0.0;
   }
   if (fast) {
     for (int i = tid; i < MPLB_NCAP; i += MPLB_NT) { S.toff_s[i] = (i <= c.n_hi) ? c.toff[i] : 0; S.tcnt_s[i] = (i <= c.n_hi) ? c.tcnt[i] : 0; }
-    for (int i = tid; i < c.tt_total; i += MPLB_NT) S.ttf[i] = (float)c.ttab[i];
   }
 
   while (true) {
@@ -686,6 +690,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
 #ifdef MPLB_PHASE_TIMING
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
+    if (tid < 8) S.dbg[tid] = 0;
 #endif
     /* ---------------- main loop (gs:63-162): S.cur* always holds the node popped last */
     while (S.status < 0) {
@@ -753,18 +758,15 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
             for (int q = 0; q < ng; q++) { S.gl_u[excl + q] = (unsigned char)i; S.gl_c[excl + q] = (unsigned char)q; }
             gbase += __shfl_sync(0xffffffffu, incl, 31);
           }
-          if (lane == 0) { S.n_gran = gbase; S.n_before = S.n_nodes; }
+          if (lane == 0) { S.n_gran = gbase; S.n_before = S.n_nodes; MPLB_COUNT(2, gbase); MPLB_COUNT(0, fast ? 1 : 0); }
         } else if (warp == 1) {
           /* ---- per-pop sampling base of the fast path (cells): parent cell coordinate and lower coefficients */
           if (fast && lane < DIM) {
             const int ax = lane;
-            double y0 = dmul(dsub(S.cur[ax], c.origin[ax]), c.inv_res);
-            double fl = floor(y0);
-            S.Y0[ax] = __double2int_rn(fl);
-            S.fy0[ax] = (float)dsub(y0, fl);
-            if (ORD >= 2) S.Ap[0 * 3 + ax] = (float)dmul(S.cur[DIM + ax], c.inv_res);
-            if (ORD >= 3) S.Ap[1 * 3 + ax] = (float)dmul(dmul(S.cur[2 * DIM + ax], 0.5), c.inv_res);
-            if (ORD >= 4) S.Ap[2 * 3 + ax] = (float)dmul(ddiv(S.cur[3 * DIM + ax], 6.0), c.inv_res);
+            S.y0[ax] = dmul(dsub(S.cur[ax], c.origin[ax]), c.inv_res);
+            if (ORD >= 2) S.Ap[0 * 3 + ax] = dmul(S.cur[DIM + ax], c.inv_res);
+            if (ORD >= 3) S.Ap[1 * 3 + ax] = dmul(dmul(S.cur[2 * DIM + ax], 0.5), c.inv_res);
+            if (ORD >= 4) S.Ap[2 * 3 + ax] = dmul(ddiv(S.cur[3 * DIM + ax], 6.0), c.inv_res);
           }
         } else {
           /* ---- goal test (gs:146) and parity hash of the current node */
@@ -808,11 +810,29 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
         }
         /* ---- B2: all collision samples of all controls, flat over 8-sample granules (warps 0-2) */
         if (fast) {
-          const int t96 = tid; /* 0..95 */
-          for (int g = t96 >> 3; g < S.n_gran; g += 12) {
-            const int u = S.gl_u[g];
-            const int k = (int)S.gl_c[g] * 8 + (t96 & 7);
-            if (k < S.cnt[u] && sample_blocked_fast<DIM, ORD>(c, S, u, S.nsamp[u], k)) atomicMin(&S.first[u], k);
+          const int t96 = tid; /* 0..95: 12 granules of 8 samples per pass, 4 independent passes in flight */
+          for (int g0 = t96 >> 3; g0 < S.n_gran; g0 += 48) {
+            int su[4], sk[4], sn[4];
+            bool act[4], blk[4], sure[4];
+            double st[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+              const int g = g0 + 12 * r;
+              act[r] = g < S.n_gran;
+              su[r] = act[r] ? S.gl_u[g] : 0;
+              sk[r] = act[r] ? (int)S.gl_c[g] * 8 + (t96 & 7) : 0;
+              sn[r] = S.nsamp[su[r]];
+              act[r] = act[r] && sk[r] < S.cnt[su[r]];
+              st[r] = act[r] ? __ldg(&c.ttab[S.toff_s[sn[r]] + sk[r]]) : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) { sure[r] = true; blk[r] = act[r] && sample_blocked_filtered<DIM, ORD>(c, S, su[r], st[r], &sure[r]); }
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+              if (act[r] && !sure[r]) blk[r] = sample_blocked_exact<DIM, ORD>(c, S, su[r], st[r], nullptr);
+              if (act[r]) MPLB_COUNT(1, 1);
+              if (blk[r]) atomicMin(&S.first[su[r]], sk[r]);
+            }
           }
         } else {
           expand_b2_percontrol<DIM, ORD>(c, S, warp, lane, 3);
@@ -865,7 +885,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
             hazard = __any_sync(0xffffffffu, hazard);
           }
           if (hazard) {
-            if (lane == 0) relax_serial<DIM, ORD>(c, S, H, table, hot, rows, b * 32, min(c.nU, b * 32 + 32), wide);
+            if (lane == 0) { MPLB_COUNT(3, 1); relax_serial<DIM, ORD>(c, S, H, table, hot, rows, b * 32, min(c.nU, b * 32 + 32), wide); }
             __syncwarp();
             created_any = true;
             continue;
@@ -984,7 +1004,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
       __syncthreads();
     }
 #ifdef MPLB_PHASE_TIMING
-    if (tid == 0 && a.phase_cycles) for (int k = 0; k < 8; k++) a.phase_cycles[(size_t)pid * 8 + k] = ph[k];
+    if (tid == 0 && a.phase_cycles) for (int k = 0; k < 8; k++) { a.phase_cycles[(size_t)pid * 16 + k] = ph[k]; a.phase_cycles[(size_t)pid * 16 + 8 + k] = (long long)S.dbg[k]; }
 #endif
 
     /* ---------------- results + recoverTraj (gs:369-455) */

@@ -31,10 +31,13 @@ s, g = bench.make_queries(m, 0)
 for _ in range(2):
     res, _, _ = pl.plan_batch(s, g, max_seg=64)
 print("kernel_ms", pl.last_batch_stats())
-ph = np.zeros((len(s), 8), dtype=np.int64)
+ph16 = np.zeros((len(s), 16), dtype=np.int64)
 L = _lib.lib()
 L.mplb_debug_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-assert L.mplb_debug_phase_cycles(pl._h, ph.ctypes.data_as(C.c_void_p), len(s)) == 0
+assert L.mplb_debug_phase_cycles(pl._h, ph16.ctypes.data_as(C.c_void_p), len(s)) == 0
+ph = ph16[:, :8]
+dbg = ph16[:, 8:]
+print('counters per pop: fast_on %.3f samples %.1f granules %.1f hazards %.4f exact_samples %.3f' % tuple(dbg[:, k].sum() / res['pops'].sum() for k in (0, 1, 2, 3, 4)))
 names = ["P1 get_succ(B1)+scan+sync", "P2 probe+prefetch", "P2 samples", "P2 barrier wait", "P3 goal+prefetch issue",
          "P3 relax loop", "P3 terminate+pop", "loop top (sync+checks)"]
 pops = res["pops"].astype(np.float64)
