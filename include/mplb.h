@@ -131,7 +131,8 @@ enum mplb_param {
   MPLB_TOL_VEL = 9,
   MPLB_TOL_ACC = 10,
   MPLB_T_MAX = 11,  /* setTmax   :203 (accepted, ignored exactly like env_map::is_goal does, env_map.h:25-45) */
-  MPLB_MEM_FRACTION = 100 /* fraction of free device memory the search arenas may take (default 0.6) */
+  MPLB_MEM_FRACTION = 100, /* fraction of free device memory the search arenas may take (default 0.6) */
+  MPLB_MAX_SLOTS = 101     /* tuning: cap on concurrently resident plans (CTAs); 0 = all resident CTAs */
 };
 int mplb_planner_set_param(mplb_planner *p, int key, double value);
 /* setU (planner_base.h:246): n rows of udim (= Dim) doubles; the row index is the action id. */

@@ -53,7 +53,7 @@ SYMBOLS = {
 }
 
 PARAM = dict(v_max=0, a_max=1, j_max=2, yaw_max=3, dt=4, w=5, epsilon=6, max_num=7, tol_pos=8, tol_vel=9,
-             tol_acc=10, t_max=11, mem_fraction=100)
+             tol_acc=10, t_max=11, mem_fraction=100, max_slots=101)
 
 _LIB = None
 

@@ -128,6 +128,7 @@ struct mplb_planner {
   double tol_pos = 0.5, tol_vel = -1, tol_acc = -1, t_max = INFINITY;
   int max_num = -1;
   double mem_fraction = 0.6;
+  int max_slots = 0; /* 0 = as many CTAs as are resident */
   std::vector<double> U; /* nU x 3 */
   int nU = 0;
 
@@ -175,7 +176,7 @@ struct Layout {
 Layout make_layout(int cap, int ns, int nU) {
   Layout L;
   int ts = 1024;
-  while ((long long)ts < 2ll * (cap + nU)) ts <<= 1;
+  while ((long long)ts < 4ll * (cap + nU)) ts <<= 1;
   L.tsize_max = ts;
   size_t o = 0;
   L.row_bytes = (sizeof(RowHdr) + (size_t)ns * sizeof(double) + 15) & ~(size_t)15;
@@ -281,8 +282,13 @@ int build_cfg(mplb_planner *p, int control) {
     double maxc = 0;
     for (int i = 0; i < p->dim; i++) maxc = std::max(maxc, (double)m->nd[i]);
     double delta = std::ldexp(maxc + margin_cells(vmax_eff, p->dt, m->res) + dsum + 2.0, -40);
-    c.use_fast = (known && n_hi < MPLB_NCAP && delta <= 1e-6) ? 1 : 0;
+    c.use_fast = (known && n_hi < MPLB_NCAP && c.tt_total <= MPLB_TT_CAP && delta <= 1e-6) ? 1 : 0;
     c.fast_delta = delta;
+  }
+  {
+    int e = 0;
+    double mant = std::frexp(p->v_max, &e);
+    c.vmax_rcp_exact = (p->v_max > 0 && mant == 0.5 && e > -500 && e < 500) ? 1.0 / p->v_max : 0.0;
   }
   /* key packing: field f = axis*ord + d; pos fields cover the map plus a margin (end states are not collision
    * tested at t = T, em:99), derivative fields cover their dynamic bound (validated primitives, pr:449-496). */
@@ -380,6 +386,7 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
   while (n_work > 0) {
     Layout L = make_layout(cap, c.ns, c.nU);
     int slots = std::min(n_work, resident);
+    if (p->max_slots > 0) slots = std::min(slots, p->max_slots);
     if ((size_t)slots * L.stride > budget) slots = (int)(budget / L.stride);
     if (slots <= 0) { /* nothing larger fits: the remaining plans report NOMEM (their overflow status is rewritten) */
       std::vector<int> ids(n_work);
@@ -635,6 +642,7 @@ int mplb_planner_set_param(mplb_planner *p, int key, double v) {
       if (!(v > 0 && v <= 0.95)) return fail(MPLB_ERR_ARG, "mem fraction must be in (0, 0.95]");
       p->mem_fraction = v;
       break;
+    case MPLB_MAX_SLOTS: p->max_slots = (int)v; break;
     default: return fail(MPLB_ERR_ARG, "unknown parameter key");
   }
   p->dirty = true;

@@ -24,6 +24,15 @@ __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a,
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 
+/* Rounding without the XU pipe.  On B200 every FP64 conversion / rounding instruction (F2I, I2F, FRND, MUFU.RCP64H)
+ * issues to the XU pipe, which the first profile of this kernel showed 65 % busy; adding and subtracting
+ * 1.5 * 2^52 rounds to nearest-even on the FP64 pipe instead and leaves the integer in the low mantissa word.
+ * Valid for |x| < 2^31; used only inside filters that defer to the exact formula near ties. */
+#define MPLB_MAGIC 6755399441055744.0
+__device__ __forceinline__ double magic_add(double x) { return __dadd_rn(x, MPLB_MAGIC); }
+__device__ __forceinline__ double magic_rint(double xm) { return __dsub_rn(xm, MPLB_MAGIC); }
+__device__ __forceinline__ int magic_int(double xm) { return __double2loint(xm); }
+
 /* std::round (half away from zero), exact: x - trunc(x) is exactly representable. */
 __device__ __forceinline__ double round_haz(double x) {
   double r = trunc(x);
@@ -59,6 +68,7 @@ struct DevCfg {
   int use_fast;     /* tables fit in shared memory and every dynamic bound is known */
   int tt_total;     /* number of entries of ttab */
   double fast_delta; /* guard band around rounding ties of the filtered sampler, in cells */
+  double vmax_rcp_exact; /* 1/v_max when v_max is a power of two (x / v_max == x * this, bit for bit), else 0 */
 };
 
 /* ------------------------------------------------------------------------------------------------
@@ -70,20 +80,27 @@ struct DevCfg {
 template <int ORD>
 struct Axis {
   double c1, c2, c3, c4, c5;
-  __device__ __forceinline__ Axis(const double *st, int stride, double u) {
+  double top; /* leading coefficient divided by its factorial exactly as pr:128-131 does (u/2, u/6, u/24): per-control
+                 constant, computed once per launch with a true division (x/2 is the exact scaling x*0.5) */
+  __device__ __forceinline__ static double top_of(double u) {
+    return (ORD == 1) ? u : (ORD == 2) ? __dmul_rn(u, 0.5) : (ORD == 3) ? __ddiv_rn(u, 6.0) : __ddiv_rn(u, 24.0);
+  }
+  __device__ __forceinline__ Axis(const double *st, int stride, double u, double top_) {
     c1 = c2 = c3 = c4 = 0.0;
     c5 = st[0];
+    top = top_;
     if (ORD == 1) { c4 = u; }
     if (ORD == 2) { c3 = u; c4 = st[stride]; }
     if (ORD == 3) { c2 = u; c3 = st[2 * stride]; c4 = st[stride]; }
     if (ORD == 4) { c1 = u; c2 = st[3 * stride]; c3 = st[2 * stride]; c4 = st[stride]; }
   }
+  __device__ __forceinline__ Axis(const double *st, int stride, double u) : Axis(st, stride, u, top_of(u)) {}
   /* pr:128-131   c0/120 t^5 + c1/24 t^4 + c2/6 t^3 + c3/2 t t + c4 t + c5 */
   __device__ __forceinline__ double p(double t) const {
     double s = 0.0;
-    if (ORD >= 4) s = dmul(ddiv(c1, 24.0), dmul(dmul(dmul(t, t), t), t));
-    if (ORD >= 3) { double x = dmul(ddiv(c2, 6.0), dmul(dmul(t, t), t)); s = (ORD >= 4) ? dadd(s, x) : x; }
-    if (ORD >= 2) { double x = dmul(dmul(ddiv(c3, 2.0), t), t); s = (ORD >= 3) ? dadd(s, x) : x; }
+    if (ORD >= 4) s = dmul(top, dmul(dmul(dmul(t, t), t), t));
+    if (ORD >= 3) { double x = dmul((ORD == 3) ? top : ddiv(c2, 6.0), dmul(dmul(t, t), t)); s = (ORD >= 4) ? dadd(s, x) : x; }
+    if (ORD >= 2) { double x = dmul(dmul((ORD == 2) ? top : dmul(c3, 0.5), t), t); s = (ORD >= 3) ? dadd(s, x) : x; }
     { double x = dmul(c4, t); s = (ORD >= 2) ? dadd(s, x) : x; }
     return dadd(s, c5);
   }
@@ -92,7 +109,7 @@ struct Axis {
     if (ORD == 1) return c4;
     double s = 0.0;
     if (ORD >= 4) s = dmul(ddiv(c1, 6.0), dmul(dmul(t, t), t));
-    if (ORD >= 3) { double x = dmul(dmul(ddiv(c2, 2.0), t), t); s = (ORD >= 4) ? dadd(s, x) : x; }
+    if (ORD >= 3) { double x = dmul(dmul(dmul(c2, 0.5), t), t); s = (ORD >= 4) ? dadd(s, x) : x; }
     { double x = dmul(c3, t); s = (ORD >= 3) ? dadd(s, x) : x; }
     return dadd(s, c4);
   }
@@ -100,7 +117,7 @@ struct Axis {
   __device__ __forceinline__ double a(double t) const {
     if (ORD <= 2) return c3;
     double s = 0.0;
-    if (ORD >= 4) s = dmul(dmul(ddiv(c1, 2.0), t), t);
+    if (ORD >= 4) s = dmul(dmul(dmul(c1, 0.5), t), t);
     { double x = dmul(c2, t); s = (ORD >= 4) ? dadd(s, x) : x; }
     return dadd(s, c3);
   }
@@ -119,7 +136,7 @@ struct Axis {
       }
     }
     if (ORD == 4) {
-      double qc = ddiv(c1, 2.0);
+      double qc = dmul(c1, 0.5);
       if (qc != 0.0) { /* quad(b=qc, c=c2, d=c3), mt:22-33 */
         double disc = dsub(dmul(c2, c2), dmul(dmul(4.0, qc), c3));
         if (!(disc < 0.0)) {

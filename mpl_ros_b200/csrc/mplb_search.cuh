@@ -110,7 +110,13 @@ struct BatchArgs {
 #ifdef MPLB_PHASE_TIMING
 #define MPLB_TICK(k) do { if (tid == 0) { long long t__ = clock64(); ph[k] += t__ - tlast; tlast = t__; } } while (0)
 #define MPLB_COUNT(k, v) atomicAdd(&S.dbg[k], (unsigned long long)(v))
+#if MPLB_PHASE_TIMING == 2
+#define MPLB_TICK2(k) do { if (tid == 0) { long long t__ = clock64(); S.dbg[k] += (unsigned long long)(t__ - tlast2); tlast2 = t__; } } while (0)
 #else
+#define MPLB_TICK2(k) do { } while (0)
+#endif
+#else
+#define MPLB_TICK2(k) do { } while (0)
 #define MPLB_COUNT(k, v) do { } while (0)
 #define MPLB_TICK(k) do { } while (0)
 #endif
@@ -119,7 +125,7 @@ template <int DIM, int ORD, int NB>
 struct PlanSmem {
   static constexpr int NS = DIM * ORD;
   static constexpr int MAXU = 32 * NB;
-  static constexpr int HCAP = (NB == 1) ? 2048 : 1024; /* heap entries kept in shared memory */
+  static constexpr int HCAP = (NB == 1) ? 1536 : 1024; /* heap entries kept in shared memory */
   static constexpr int GCAP = MAXU * 8;                /* 8-sample granules */
   /* heap top (SoA) */
   double hf[HCAP], hg[HCAP];
@@ -136,6 +142,7 @@ struct PlanSmem {
   /* per-plan constants */
   double U[MAXU * 3];
   double cost[MAXU];   /* J(u) + w*dt, eb:343-345 */
+  double Ut[MAXU * 3]; /* u / ORD! exactly as pr:128-131 divides the leading coefficient */
   double Au[MAXU * 3]; /* top polynomial coefficient of the filtered sampling path, in cells */
   int toff_s[MPLB_NCAP], tcnt_s[MPLB_NCAP];
   /* per-pop sampling base (fast path): cell coordinate of the parent = Y0 + fy0, lower coefficients in cells */
@@ -149,7 +156,12 @@ struct PlanSmem {
   int cnt[MAXU];     /* samples to test */
   int first[MAXU];   /* first blocked sample index or INT_MAX */
   int nid[MAXU];     /* node id of the successor after relaxation (for state forwarding) */
-  unsigned char gl_u[GCAP], gl_c[GCAP];
+  /* probe results of warp 0 (staged in shared memory so nothing lives in registers across the barrier) */
+  int p_nid[MAXU], p_slot[MAXU];
+  double p_g[MAXU], p_pg[MAXU], p_h[MAXU];
+  unsigned int gl[GCAP]; /* granule: control | first sample k0 << 8 | sample count << 16 ... */
+  unsigned short gl_t[GCAP]; /* ... and index of its first sample time in tts */
+  double tts[MPLB_TT_CAP]; /* accumulated sample times (em:98-99), all divisors */
   int n_gran;
   int n_before;      /* n_nodes before this expansion */
   /* pending sift-down (heap warp) and prefetched root row */
@@ -272,22 +284,30 @@ __device__ __forceinline__ int table_insert_atomic(Slot *table, int tsize, unsig
 }
 
 /* ---------------------------------------------------------------- exact reference arithmetic with cheap filters */
+/* Cold exact paths are kept out of line on purpose: the per-pop instruction footprint has to stay well inside the
+ * 32 KB L1.5 instruction cache (a first version with everything inlined touched 36 KB per pop and ran several
+ * times slower, every line missing). */
+__device__ __noinline__ int lattice_int_exact(double x, double q) { return round_int(ddiv(x, q)); }
+__device__ __noinline__ int sample_divisor_exact(double mvT, double res) { return __double2int_rz(ceil(ddiv(mvT, res))); }
+__device__ __noinline__ double div_exact(double a, double b) { return ddiv(a, b); }
+
 /* lattice int round(x / q) (wp:97-120) with q = 0.01 or 0.1: x*(1/q) decides unless within 1e-6 of a tie. */
 __device__ __forceinline__ int lattice_int(double x, double q, double inv_q) {
   double y = dmul(x, inv_q);
-  double r = rint(y);
-  if (fabs(dsub(y, r)) < 0.499999) return __double2int_rn(r);
-  return round_int(ddiv(x, q));
+  double ym = magic_add(y);
+  if (fabs(dsub(y, magic_rint(ym))) < 0.499999 && fabs(y) < 1073741824.0) return magic_int(ym);
+  return lattice_int_exact(x, q);
 }
 
 /* max(5, (int)ceil(max_v*T/res)) (em:95): the product with 1/res decides unless within 1e-9 of an integer. */
 __device__ __forceinline__ int sample_divisor(double max_v, double T, double res, double inv_res) {
   double mvT = dmul(max_v, T);
   double x = dmul(mvT, inv_res);
-  double r = rint(x);
+  double xm = magic_add(x);
+  double r = magic_rint(xm);
   int n;
-  if (fabs(dsub(x, r)) > 1e-9) n = __double2int_rn(ceil(x));
-  else n = __double2int_rz(ceil(ddiv(mvT, res)));
+  if (fabs(dsub(x, r)) > 1e-9 && x < 1073741824.0) n = magic_int(xm) + ((x > r) ? 1 : 0); /* ceil(x) */
+  else n = sample_divisor_exact(mvT, res);
   return n < 5 ? 5 : n;
 }
 
@@ -301,7 +321,7 @@ __device__ __forceinline__ void expand_b1(const DevCfg &c, SM &S, int i, unsigne
   bool dyn_ok = true, same_pos = true;
 #pragma unroll
   for (int ax = 0; ax < DIM; ax++) {
-    Axis<ORD> A(&S.cur[ax], DIM, S.U[i * 3 + ax]);
+    Axis<ORD> A(&S.cur[ax], DIM, S.U[i * 3 + ax], S.Ut[i * 3 + ax]);
     es[0 * DIM + ax] = A.p(T);
     if (ORD >= 2) es[1 * DIM + ax] = A.v(T);
     if (ORD >= 3) es[2 * DIM + ax] = A.a(T);
@@ -355,7 +375,7 @@ __device__ __noinline__ bool sample_blocked_exact(const DevCfg &c, const SM &S, 
   bool outside = false;
 #pragma unroll
   for (int ax = 0; ax < DIM; ax++) {
-    Axis<ORD> A(&S.cur[ax], DIM, S.U[i * 3 + ax]);
+    Axis<ORD> A(&S.cur[ax], DIM, S.U[i * 3 + ax], S.Ut[i * 3 + ax]);
     pn[ax] = float_to_cell(A.p(t), c.origin[ax], c.res);
     outside = outside || pn[ax] < 0 || pn[ax] >= c.nd[ax];
   }
@@ -379,10 +399,10 @@ __device__ __forceinline__ bool sample_blocked_filtered(const DevCfg &c, const S
     double dy = S.Au[i * 3 + ax];
 #pragma unroll
     for (int d = ORD - 2; d >= 0; d--) dy = __fma_rn(dy, t, S.Ap[d * 3 + ax]);
-    double w = __fma_rn(dy, t, S.y0[ax]) - 0.5;
-    double r = rint(w);
-    ok = ok && (fabs(w - r) < 0.5 - c.fast_delta);
-    pn[ax] = __double2int_rn(r);
+    double w = __dsub_rn(__fma_rn(dy, t, S.y0[ax]), 0.5);
+    double wm = magic_add(w);
+    ok = ok && (fabs(__dsub_rn(w, magic_rint(wm))) < 0.5 - c.fast_delta);
+    pn[ax] = magic_int(wm);
     outside = outside || pn[ax] < 0 || pn[ax] >= c.nd[ax];
   }
   *sure = ok;
@@ -413,7 +433,7 @@ __device__ __forceinline__ void expand_b2_percontrol(const DevCfg &c, SM &S, int
 
 /* em:25-45 for a state (tolerances, then ray trace mu:117-134); executed by one full warp. */
 template <int DIM, int ORD, class SM>
-__device__ __forceinline__ bool goal_test_warp(const DevCfg &c, const SM &S, const double *st, int lane) {
+__device__ __noinline__ bool goal_test_warp(const DevCfg &c, const SM &S, const double *st, int lane) {
   double m = 0.0;
 #pragma unroll
   for (int ax = 0; ax < DIM; ax++) m = fmax(m, fabs(dsub(st[ax], S.goal_pos[ax])));
@@ -475,7 +495,7 @@ __device__ __forceinline__ double heuristic(const DevCfg &c, const SM &S, const 
   double m = 0.0;
 #pragma unroll
   for (int ax = 0; ax < DIM; ax++) m = fmax(m, fabs(dsub(st[ax], S.goal_pos[ax])));
-  if (c.v_max > 0.0) return ddiv(dmul(c.w, m), c.v_max);
+  if (c.v_max > 0.0) return (c.vmax_rcp_exact != 0.0) ? dmul(dmul(c.w, m), c.vmax_rcp_exact) : div_exact(dmul(c.w, m), c.v_max);
   return dmul(c.w, m);
 }
 
@@ -501,8 +521,9 @@ __device__ __forceinline__ unsigned long long khash_of_ints(const int *ints) {
 /* Generic serial relaxation of successors [i0, i1) in control order (lane 0 of warp 0): re-probes the table in
  * global memory, so it is correct under every hazard (duplicate siblings, slot collisions).  gs:79-143. */
 template <int DIM, int ORD, class SM>
-__device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, const HeapView<SM> &H, Slot *table, NodeHot *hot,
+__device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, HeapEnt *spill, Slot *table, NodeHot *hot,
                                           unsigned char *rows, int i0, int i1, bool wide) {
+  const HeapView<SM> H{S, spill, hot}; /* built here: a view whose address escapes would turn heap accesses generic */
   constexpr int NS = DIM * ORD;
   constexpr size_t ROWB = (sizeof(RowHdr) + NS * sizeof(double) + 15) & ~(size_t)15; /* 16-byte aligned rows */
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
@@ -558,9 +579,43 @@ __device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, const HeapView
   }
 }
 
+/* B2, flat form: thread `t` of `nthreads` sampling threads takes sample (t & 7) of granule (t >> 3) + k*(nthreads/8);
+ * R granules are processed per pass with their loads issued together (independent dependency chains). */
+template <int DIM, int ORD, class SM>
+__device__ __forceinline__ void sample_granules(const DevCfg &c, SM &S, int t, int nthreads) {
+  const int gstep = nthreads >> 3;
+  const int sub = t & 7;
+  constexpr int R = 2; /* granules in flight per thread */
+  for (int g0 = t >> 3; g0 < S.n_gran; g0 += R * gstep) {
+    unsigned info[R];
+    double st[R];
+    bool act[R], blk[R], sure[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int g = g0 + gstep * r;
+      const bool in = g < S.n_gran;
+      info[r] = in ? S.gl[g] : 0u;
+      const int k = (int)((info[r] >> 8) & 0xffu) + sub;
+      act[r] = in && k < (int)(info[r] >> 16);
+      st[r] = act[r] ? S.tts[(int)S.gl_t[in ? g : 0] + sub] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      sure[r] = true;
+      blk[r] = act[r] && sample_blocked_filtered<DIM, ORD>(c, S, (int)(info[r] & 0xffu), st[r], &sure[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int u = (int)(info[r] & 0xffu);
+      if (act[r] && !sure[r]) blk[r] = sample_blocked_exact<DIM, ORD>(c, S, u, st[r], nullptr);
+      if (blk[r]) atomicMin(&S.first[u], (int)((info[r] >> 8) & 0xffu) + sub);
+    }
+  }
+}
+
 /* ---------------------------------------------------------------- the kernel */
 template <int DIM, int ORD, int NB>
-__global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, const BatchArgs a) {
+__global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ BatchArgs a) {
   constexpr int NS = DIM * ORD;
   constexpr int NW = MPLB_NT / 32;
   using SM = PlanSmem<DIM, ORD, NB>;
@@ -582,7 +637,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
   HeapView<SM> H{S, spill, hot};
 
   /* ---------------- per-launch constants */
-  for (int i = tid; i < c.nU * 3; i += MPLB_NT) S.U[i] = c.U[i];
+  for (int i = tid; i < c.nU * 3; i += MPLB_NT) { S.U[i] = c.U[i]; S.Ut[i] = Axis<ORD>::top_of(c.U[i]); }
   for (int i = tid; i < c.nU; i += MPLB_NT) {
     double J = 0.0;
     for (int ax = 0; ax < DIM; ax++) { double u = c.U[i * 3 + ax]; J = dadd(J, dmul(dmul(u, u), c.dt)); } /* pr:92-122,403-407 */
@@ -592,6 +647,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
   }
   if (fast) {
     for (int i = tid; i < MPLB_NCAP; i += MPLB_NT) { S.toff_s[i] = (i <= c.n_hi) ? c.toff[i] : 0; S.tcnt_s[i] = (i <= c.n_hi) ? c.tcnt[i] : 0; }
+    for (int i = tid; i < c.tt_total; i += MPLB_NT) S.tts[i] = c.ttab[i];
   }
 
   while (true) {
@@ -690,6 +746,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
 #ifdef MPLB_PHASE_TIMING
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
+    long long tlast2 = tlast;
     if (tid < 8) S.dbg[tid] = 0;
 #endif
     /* ---------------- main loop (gs:63-162): S.cur* always holds the node popped last */
@@ -702,9 +759,9 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
         __syncthreads();
         break;
       }
-      if ((S.n_nodes + c.nU) * 2 > S.tsize) { /* grow the table in place and re-insert every node */
+      if ((S.n_nodes + c.nU) * 4 > S.tsize) { /* keep the load factor <= 1/4: grow in place and re-insert every node */
         int nt = S.tsize;
-        while ((S.n_nodes + c.nU) * 2 > nt) nt <<= 1;
+        while ((S.n_nodes + c.nU) * 4 > nt) nt <<= 1;
         __syncthreads();
         if (nt > a.tsize_max) { if (tid == 0) S.status = MPLB_INTERNAL_OVERFLOW; __syncthreads(); break; }
         unsigned long long *t64 = reinterpret_cast<unsigned long long *>(table);
@@ -721,8 +778,6 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
       /* ================= P1/P2 ================= */
       /* per-control registers of warp 0 (probe results), one set per 32-control batch */
       unsigned long long rk0[NB], rk1[NB];
-      int r_nid[NB], r_slot[NB];
-      double r_g[NB], r_pg[NB], r_h[NB];
       if (warp == 3) {
         /* ---- heap warp: finish the previous pop's sift-down, then prefetch the new root's state row */
         if (lane == 0) {
@@ -746,7 +801,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
           for (int b = 0; b < NB; b++) {
             const int i = b * 32 + lane;
             int ng = 0;
-            rk0[b] = 0; rk1[b] = 0; r_nid[b] = -1; r_slot[b] = -1; r_g[b] = kInf; r_pg[b] = 0.0; r_h[b] = 0.0;
+            rk0[b] = 0; rk1[b] = 0;
             if (i < c.nU) {
               expand_b1<DIM, ORD>(c, S, i, rk0[b], rk1[b]);
               if (fast && S.verdict[i] == 5) ng = (S.cnt[i] + 7) >> 3;
@@ -755,7 +810,10 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
             int excl = gbase + incl - ng;
-            for (int q = 0; q < ng; q++) { S.gl_u[excl + q] = (unsigned char)i; S.gl_c[excl + q] = (unsigned char)q; }
+            for (int q = 0; q < ng; q++) {
+              S.gl[excl + q] = (unsigned)i | ((unsigned)(q * 8) << 8) | ((unsigned)S.cnt[i] << 16);
+              S.gl_t[excl + q] = (unsigned short)(S.toff_s[S.nsamp[i]] + q * 8);
+            }
             gbase += __shfl_sync(0xffffffffu, incl, 31);
           }
           if (lane == 0) { S.n_gran = gbase; S.n_before = S.n_nodes; MPLB_COUNT(2, gbase); MPLB_COUNT(0, fast ? 1 : 0); }
@@ -776,66 +834,50 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
         asm volatile("bar.sync 1, 96;" ::: "memory"); /* warps 0-2: B1 outputs, sampling base, goal flag are visible */
         MPLB_TICK(0);
         if (warp == 0) {
-          /* issue the table probes (two consecutive slots = 64 bytes) and compute h while they fly */
-          Slot sa[NB], sb[NB];
-          bool probing[NB];
-          unsigned hidx[NB];
+          /* issue the table probes — WIN consecutive 32-byte slots per candidate, one HBM round trip in all but a
+           * few per cent of the cases at load factor <= 1/4 — and compute h while they fly */
+          constexpr int WIN = (NB == 1) ? 4 : 2;
 #pragma unroll
           for (int b = 0; b < NB; b++) {
             const int i = b * 32 + lane;
-            probing[b] = (i < c.nU) && (S.verdict[i] >= 4);
-            hidx[b] = table_hash(rk0[b], rk1[b]) & ((unsigned)S.tsize - 1u);
-            if (probing[b]) {
-              sa[b] = table[hidx[b]];
-              sb[b] = table[(hidx[b] + 1) & ((unsigned)S.tsize - 1u)];
+            const bool probing = (i < c.nU) && (S.verdict[i] >= 4);
+            const unsigned mask = (unsigned)S.tsize - 1u;
+            const unsigned h0 = table_hash(rk0[b], rk1[b]) & mask;
+            Slot sw[WIN];
+            if (probing) {
+#pragma unroll
+              for (int q = 0; q < WIN; q++) sw[q] = table[(h0 + q) & mask];
             }
-          }
+            double hv = 0.0;
+            if (probing) hv = heuristic<DIM, ORD>(c, S, &S.es[i * NS], rk0[b], rk1[b]);
+            int nid = -1, slot = -1;
+            double g = kInf, pg = 0.0;
+            if (probing) {
+              bool done = false;
 #pragma unroll
-          for (int b = 0; b < NB; b++) {
-            const int i = b * 32 + lane;
-            if (probing[b]) r_h[b] = heuristic<DIM, ORD>(c, S, &S.es[i * NS], rk0[b], rk1[b]);
+              for (int q = 0; q < WIN; q++) {
+                if (!done) {
+                  if (sw[q].node1 == 0u) { slot = (int)((h0 + q) & mask); done = true; }
+                  else if (slot_matches(sw[q], rk0[b], rk1[b], wide, rows, ROWB)) {
+                    nid = (int)sw[q].node1 - 1; slot = (int)((h0 + q) & mask); g = sw[q].g; pg = sw[q].pg; done = true;
+                  }
+                }
+              }
+              if (!done) nid = table_find_from(table, S.tsize, h0 + WIN, rk0[b], rk1[b], wide, rows, ROWB, &slot, &g, &pg);
+            }
+            if (i < c.nU) { S.p_nid[i] = nid; S.p_slot[i] = slot; S.p_g[i] = g; S.p_pg[i] = pg; S.p_h[i] = hv; }
           }
           MPLB_TICK(1);
-          /* resolve */
-#pragma unroll
-          for (int b = 0; b < NB; b++) {
-            if (!probing[b]) continue;
-            const unsigned mask = (unsigned)S.tsize - 1u;
-            if (sa[b].node1 == 0u) { r_slot[b] = (int)hidx[b]; }
-            else if (slot_matches(sa[b], rk0[b], rk1[b], wide, rows, ROWB)) { r_nid[b] = (int)sa[b].node1 - 1; r_slot[b] = (int)hidx[b]; r_g[b] = sa[b].g; r_pg[b] = sa[b].pg; }
-            else if (sb[b].node1 == 0u) { r_slot[b] = (int)((hidx[b] + 1) & mask); }
-            else if (slot_matches(sb[b], rk0[b], rk1[b], wide, rows, ROWB)) { r_nid[b] = (int)sb[b].node1 - 1; r_slot[b] = (int)((hidx[b] + 1) & mask); r_g[b] = sb[b].g; r_pg[b] = sb[b].pg; }
-            else r_nid[b] = table_find_from(table, S.tsize, hidx[b] + 2, rk0[b], rk1[b], wide, rows, ROWB, &r_slot[b], &r_g[b], &r_pg[b]);
-          }
         }
-        /* ---- B2: all collision samples of all controls, flat over 8-sample granules (warps 0-2) */
-        if (fast) {
-          const int t96 = tid; /* 0..95: 12 granules of 8 samples per pass, 4 independent passes in flight */
-          for (int g0 = t96 >> 3; g0 < S.n_gran; g0 += 48) {
-            int su[4], sk[4], sn[4];
-            bool act[4], blk[4], sure[4];
-            double st[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-              const int g = g0 + 12 * r;
-              act[r] = g < S.n_gran;
-              su[r] = act[r] ? S.gl_u[g] : 0;
-              sk[r] = act[r] ? (int)S.gl_c[g] * 8 + (t96 & 7) : 0;
-              sn[r] = S.nsamp[su[r]];
-              act[r] = act[r] && sk[r] < S.cnt[su[r]];
-              st[r] = act[r] ? __ldg(&c.ttab[S.toff_s[sn[r]] + sk[r]]) : 0.0;
-            }
-#pragma unroll
-            for (int r = 0; r < 4; r++) { sure[r] = true; blk[r] = act[r] && sample_blocked_filtered<DIM, ORD>(c, S, su[r], st[r], &sure[r]); }
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-              if (act[r] && !sure[r]) blk[r] = sample_blocked_exact<DIM, ORD>(c, S, su[r], st[r], nullptr);
-              if (act[r]) MPLB_COUNT(1, 1);
-              if (blk[r]) atomicMin(&S.first[su[r]], sk[r]);
-            }
-          }
-        } else {
-          expand_b2_percontrol<DIM, ORD>(c, S, warp, lane, 3);
+        /* ---- B2: all collision samples of all controls, flat over 8-sample granules (warps 1-2; warp 3 joins below) */
+        if (warp != 0) {
+#ifndef MPLB_EXPERIMENT_NOSAMPLE
+          if (fast) sample_granules<DIM, ORD>(c, S, tid - 32, 64);
+          else
+#else
+          if (!fast)
+#endif
+          expand_b2_percontrol<DIM, ORD>(c, S, warp - 1, lane, 2);
         }
       }
       MPLB_TICK(2);
@@ -844,6 +886,9 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
 
       /* ================= P3 (warp 0): relax (gs:79-143), terminate (gs:146-161), take the next node (gs:64-68) */
       if (warp == 0) {
+#if defined(MPLB_PHASE_TIMING) && MPLB_PHASE_TIMING == 2
+        tlast2 = clock64();
+#endif
         const int cn = S.cur_node;
         const double cg = S.cur_g;
         if (lane == 0) { /* bookkeeping of the current pop */
@@ -863,69 +908,80 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
             ns_acc += (v == 3) ? S.cnt[i] : first + 1;
           }
           const bool valid = v >= 3;
+          const int r_nid_b = (i < c.nU) ? S.p_nid[i] : -1;
+          const int r_slot_b = (i < c.nU) ? S.p_slot[i] : -1;
+          const double r_g_b = (i < c.nU) ? S.p_g[i] : kInf;
+          const double r_pg_b = (i < c.nU) ? S.p_pg[i] : 0.0;
+          const double r_h_b = (i < c.nU) ? S.p_h[i] : 0.0;
+          const unsigned long long rk0_b = (i < c.nU) ? S.k0[i] : 0ull, rk1_b = (i < c.nU) ? S.k1[i] : 0ull;
+          MPLB_TICK2(0);
           const unsigned vmask = __ballot_sync(0xffffffffu, valid);
           nv_acc += __popc(vmask);
           if (vmask == 0u) continue;
-          const bool found = valid && r_nid[b] >= 0;
-          const bool isnew = valid && r_nid[b] < 0;
+          const bool found = valid && r_nid_b >= 0;
+          const bool isnew = valid && r_nid_b < 0;
           /* hazards: two successors -> one node or one table slot; later batches vs nodes created earlier in this pop */
           bool hazard = false;
           {
             unsigned newm = __ballot_sync(0xffffffffu, isnew);
             unsigned fndm = __ballot_sync(0xffffffffu, found);
             if (isnew) {
-              unsigned m1 = __match_any_sync(newm, rk0[b] ^ (rk1[b] * 0x9E3779B97F4A7C15ull));
-              unsigned m2 = __match_any_sync(newm, r_slot[b]);
+              unsigned m1 = __match_any_sync(newm, rk0_b ^ (rk1_b * 0x9E3779B97F4A7C15ull));
+              unsigned m2 = __match_any_sync(newm, r_slot_b);
               hazard = (__popc(m1) > 1) || (__popc(m2) > 1);
             }
-            if (found) { unsigned m3 = __match_any_sync(fndm, r_nid[b]); hazard = hazard || (__popc(m3) > 1); }
+            if (found) { unsigned m3 = __match_any_sync(fndm, r_nid_b); hazard = hazard || (__popc(m3) > 1); }
             if (NB > 1 && created_any && isnew) hazard = true; /* probe predates nodes created by earlier batches */
             if (NB > 1 && found) /* an earlier batch of this pop may already have relaxed the same node */
-              for (int q = 0; q < b * 32; q++) hazard = hazard || (S.nid[q] == r_nid[b]);
+              for (int q = 0; q < b * 32; q++) hazard = hazard || (S.nid[q] == r_nid_b);
             hazard = __any_sync(0xffffffffu, hazard);
           }
+          MPLB_TICK2(1);
           if (hazard) {
-            if (lane == 0) { MPLB_COUNT(3, 1); relax_serial<DIM, ORD>(c, S, H, table, hot, rows, b * 32, min(c.nU, b * 32 + 32), wide); }
+            if (lane == 0) { MPLB_COUNT(3, 1); relax_serial<DIM, ORD>(c, S, spill, table, hot, rows, b * 32, min(c.nU, b * 32 + 32), wide); }
             __syncwarp();
             created_any = true;
             continue;
           }
           const double tentative = dadd(cg, valid ? S.cost[i] : 0.0); /* gs:107 */
-          const bool improve = found && tentative < r_g[b];
-          const bool tie = found && tentative == r_g[b] && cg > r_pg[b]; /* recoverTraj tie rule (gs:398-403) */
+          const bool improve = found && tentative < r_g_b;
+          const bool tie = found && tentative == r_g_b && cg > r_pg_b; /* recoverTraj tie rule (gs:398-403) */
           const unsigned newm = __ballot_sync(0xffffffffu, isnew);
-          int nid = r_nid[b];
+          int nid = r_nid_b;
           if (isnew) nid = S.n_nodes + __popc(newm & lt_mask);
           const int n_new = __popc(newm);
           created_any = created_any || (n_new > 0);
           if (valid) S.nid[i] = nid;
-          double hval = r_h[b];
+          double hval = r_h_b;
           int fl = 0, hpos = -1;
           if (improve) { const NodeHot hn = hot[nid]; hval = hn.h; fl = hn.flags; hpos = hn.heap_pos; } /* rare dependent load */
           const double f = dadd(tentative, dmul(c.eps, hval));
+          MPLB_TICK2(2);
           /* lane-parallel stores */
           if (isnew) { /* gs:84-88: the node's coord is this (first) discoverer's state */
             RowHdr *rh = reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB);
-            rh->k0 = rk0[b]; rh->k1 = rk1[b]; rh->parent = cn; rh->slot = r_slot[b]; rh->pad = 0;
+            rh->k0 = rk0_b; rh->k1 = rk1_b; rh->parent = cn; rh->slot = r_slot_b; rh->pad = 0;
             double *rs = reinterpret_cast<double *>(rows + (size_t)nid * ROWB + sizeof(RowHdr));
 #pragma unroll
             for (int q = 0; q < NS; q++) rs[q] = S.es[i * NS + q];
-            Slot sl; sl.k0 = rk0[b]; sl.k1lo = (unsigned int)rk1[b]; sl.node1 = (unsigned)(nid + 1); sl.g = tentative; sl.pg = cg;
-            table[r_slot[b]] = sl;
+            Slot sl; sl.k0 = rk0_b; sl.k1lo = (unsigned int)rk1_b; sl.node1 = (unsigned)(nid + 1); sl.g = tentative; sl.pg = cg;
+            table[r_slot_b] = sl;
             NodeHot hn; hn.g = tentative; hn.h = hval; hn.pg = cg; hn.heap_pos = -1; hn.action = (short)i; hn.flags = 1; hn.pad0 = 0;
             hot[nid] = hn;
           } else if (improve) {
             NodeHot hn; hn.g = tentative; hn.h = hval; hn.pg = cg; hn.heap_pos = hpos; hn.action = (short)i;
             hn.flags = (unsigned char)(fl | 1); hn.pad0 = 0;
             hot[nid] = hn;
-            table[r_slot[b]].g = tentative; table[r_slot[b]].pg = cg;
+            table[r_slot_b].g = tentative; table[r_slot_b].pg = cg;
             reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB)->parent = cn;
           } else if (tie) {
             hot[nid].pg = cg; hot[nid].action = (short)i;
-            table[r_slot[b]].pg = cg;
+            table[r_slot_b].pg = cg;
             reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB)->parent = cn;
           }
           if (lane == 0) S.n_nodes += n_new;
+          MPLB_TICK2(3);
+          MPLB_TICK(4);
           /* heap operations in control order (gs:129-141) */
           unsigned hm = __ballot_sync(0xffffffffu, isnew || improve);
           while (hm) {
@@ -1063,7 +1119,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const DevCfg c, co
 
 /* ---------------------------------------------------------------- get_succ for arbitrary states (parity artefact) */
 template <int DIM, int ORD, int NB>
-__global__ void __launch_bounds__(MPLB_NT) expand_trace_kernel(const DevCfg c, const mplb_waypoint *states, int n_states,
+__global__ void __launch_bounds__(MPLB_NT) expand_trace_kernel(const __grid_constant__ DevCfg c, const mplb_waypoint *states, int n_states,
                                                                mplb_prim_trace *rows) {
   constexpr int NS = DIM * ORD;
   constexpr int NW = MPLB_NT / 32;
@@ -1071,7 +1127,7 @@ __global__ void __launch_bounds__(MPLB_NT) expand_trace_kernel(const DevCfg c, c
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM &S = *reinterpret_cast<SM *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < c.nU * 3; i += MPLB_NT) S.U[i] = c.U[i];
+  for (int i = tid; i < c.nU * 3; i += MPLB_NT) { S.U[i] = c.U[i]; S.Ut[i] = Axis<ORD>::top_of(c.U[i]); }
   for (int i = tid; i < c.nU; i += MPLB_NT) {
     double J = 0.0;
     for (int ax = 0; ax < DIM; ax++) { double u = c.U[i * 3 + ax]; J = dadd(J, dmul(dmul(u, u), c.dt)); }

@@ -234,6 +234,7 @@ class MapPlanner:
     def setEpsilon(self, e): self._set("epsilon", e)
     def setMaxNum(self, n): self._set("max_num", n)
     def setMemFraction(self, f): self._set("mem_fraction", f)
+    def setMaxSlots(self, n): self._set("max_slots", n)
 
     def setDt(self, dt):
         self._set("dt", dt)

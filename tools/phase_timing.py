@@ -14,7 +14,7 @@ from mpl_ros_b200 import build as B  # noqa: E402
 
 out = os.path.join(ROOT, "mpl_ros_b200", "libmplb_prof.so")
 if "--build-only" in sys.argv or not os.path.exists(out):
-    subprocess.check_call([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")] + B.NVCC_FLAGS + ["-DMPLB_PHASE_TIMING", "-o", out, B.SRC])
+    subprocess.check_call([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")] + B.NVCC_FLAGS + ["-DMPLB_PHASE_TIMING=" + os.environ.get("MPLB_PT", "1"), "-o", out, B.SRC])
     if "--build-only" in sys.argv:
         sys.exit(0)
 from mpl_ros_b200 import _lib  # noqa: E402
@@ -28,6 +28,9 @@ mu = mp.VoxelMapUtil(); mu.setMap(m.origin, m.dim, m.data, m.res); mu.freeUnknow
 pl = mp.VoxelMapPlanner(False); pl.setMapUtil(mu)
 pl.setVmax(2.0); pl.setAmax(1.0); pl.setDt(1.0); pl.setU(maps.make_U(1.0, 1, 3)); pl.setTol(0.5)
 s, g = bench.make_queries(m, 0)
+if len(sys.argv) > 1 and sys.argv[1].isdigit():
+    pl.setMaxSlots(int(sys.argv[1]))
+    print('max_slots', sys.argv[1])
 for _ in range(2):
     res, _, _ = pl.plan_batch(s, g, max_seg=64)
 print("kernel_ms", pl.last_batch_stats())
@@ -37,9 +40,10 @@ L.mplb_debug_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 assert L.mplb_debug_phase_cycles(pl._h, ph16.ctypes.data_as(C.c_void_p), len(s)) == 0
 ph = ph16[:, :8]
 dbg = ph16[:, 8:]
+print('dbg per pop', (dbg.sum(axis=0) / res['pops'].sum()).astype(int).tolist())
 print('counters per pop: fast_on %.3f samples %.1f granules %.1f hazards %.4f exact_samples %.3f' % tuple(dbg[:, k].sum() / res['pops'].sum() for k in (0, 1, 2, 3, 4)))
-names = ["P1 get_succ(B1)+scan+sync", "P2 probe+prefetch", "P2 samples", "P2 barrier wait", "P3 goal+prefetch issue",
-         "P3 relax loop", "P3 terminate+pop", "loop top (sync+checks)"]
+names = ["P1 B1+scan+bar1", "P2 probe issue + h", "P2 probe resolve", "P2 barrier wait", "P3 relax: decide+stores",
+         "P3 relax: heap ops", "P3 terminate+pop", "loop top (sync+checks)"]
 pops = res["pops"].astype(np.float64)
 tot = ph.sum()
 print("total pops", int(pops.sum()), "cycles/pop (all plans)", tot / pops.sum())
