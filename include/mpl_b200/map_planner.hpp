@@ -1,0 +1,387 @@
+/*
+ * map_planner.hpp — header-only C++ host layer that puts the reference's class surface back on top of the C ABI
+ * (include/mplb.h): MPL::MapUtil<Dim>, Waypoint<Dim>, Primitive<Dim>, Trajectory<Dim>, MPL::MapPlanner<Dim>
+ * (OccMapPlanner / VoxelMapPlanner), with the member names and argument meaning of
+ *   motion_primitive_library/include/mpl_collision/map_util.h        (MapUtil)
+ *   motion_primitive_library/include/mpl_basis/waypoint.h            (Waypoint, control flags)
+ *   motion_primitive_library/include/mpl_basis/primitive.h:205-431   (Primitive: coefficient rows, evaluate)
+ *   motion_primitive_library/include/mpl_basis/trajectory.h:42-57,277-292
+ *   motion_primitive_library/include/mpl_planner/common/planner_base.h:18-345 and planner/map_planner.h:20-125
+ * so that callers written against the reference (MPL/test/test_planner_2d.cpp, mpl_test_node/src/
+ * map_planner_node.cpp) compile against this header with their planner calls unchanged.
+ *
+ * Vector types: when Eigen is available (a ROS site) define MPL_B200_USE_EIGEN before including this header and
+ * Vecf<N>/Veci<N>/VecDf are the reference's Eigen aliases (data_type.h:49-75); otherwise a minimal fixed-size
+ * array type with operator() and operator[] is used (this image has no Eigen).
+ *
+ * Everything numerical runs in libmplb.so on the GPU; there is no CPU fallback — failures surface as `false`
+ * from plan() with the message of mplb_last_error() printed when the planner is verbose.
+ */
+#ifndef MPL_B200_MAP_PLANNER_HPP
+#define MPL_B200_MAP_PLANNER_HPP
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <limits>
+#include <memory>
+#include <vector>
+
+#include "../mplb.h"
+
+typedef double decimal_t; /* data_type.h:49 */
+
+#ifdef MPL_B200_USE_EIGEN
+#include <Eigen/Geometry>
+#include <Eigen/StdVector>
+template <typename T>
+using vec_E = std::vector<T, Eigen::aligned_allocator<T>>;
+template <int N>
+using Vecf = Eigen::Matrix<decimal_t, N, 1>;
+template <int N>
+using Veci = Eigen::Matrix<int, N, 1>;
+typedef Eigen::Matrix<decimal_t, Eigen::Dynamic, 1> VecDf;
+#else
+template <typename T>
+using vec_E = std::vector<T>;
+template <typename T, int N>
+struct mplb_small_vec {
+  T v[N];
+  mplb_small_vec() { for (int i = 0; i < N; i++) v[i] = T(0); }
+  mplb_small_vec(T a, T b) { static_assert(N == 2, "2 components"); v[0] = a; v[1] = b; }
+  mplb_small_vec(T a, T b, T c) { static_assert(N == 3, "3 components"); v[0] = a; v[1] = b; v[2] = c; }
+  T &operator()(int i) { return v[i]; }
+  const T &operator()(int i) const { return v[i]; }
+  T &operator[](int i) { return v[i]; }
+  const T &operator[](int i) const { return v[i]; }
+  static mplb_small_vec Zero() { return mplb_small_vec(); }
+  int size() const { return N; }
+};
+template <int N>
+using Vecf = mplb_small_vec<decimal_t, N>;
+template <int N>
+using Veci = mplb_small_vec<int, N>;
+typedef std::vector<decimal_t> VecDf; /* control rows: size() and operator[] like the Eigen dynamic vector */
+#endif
+template <int N>
+using vec_Vecf = vec_E<Vecf<N>>;
+template <int N>
+using vec_Veci = vec_E<Veci<N>>;
+typedef Vecf<2> Vec2f;
+typedef Vecf<3> Vec3f;
+typedef Veci<2> Vec2i;
+typedef Veci<3> Vec3i;
+
+namespace Control { /* control.h:10-20 */
+enum Control { NONE = 0, VEL = 0b00001, ACC = 0b00011, JRK = 0b00111, SNP = 0b01111,
+               VELxYAW = 0b10001, ACCxYAW = 0b10011, JRKxYAW = 0b10111, SNPxYAW = 0b11111 };
+}
+
+/* waypoint.h:22-58 */
+template <int Dim>
+struct Waypoint {
+  Waypoint() : control(Control::NONE) {}
+  Waypoint(Control::Control c) : control(c) {}
+  Vecf<Dim> pos, vel, acc, jrk;
+  decimal_t yaw{0};
+  decimal_t t{0};
+  union {
+    struct {
+      bool use_pos : 1;
+      bool use_vel : 1;
+      bool use_acc : 1;
+      bool use_jrk : 1;
+      bool use_yaw : 1;
+    };
+    Control::Control control : 5;
+  };
+  bool enable_t{false};
+};
+typedef Waypoint<2> Waypoint2D;
+typedef Waypoint<3> Waypoint3D;
+
+/* primitive.h:205-431 — per-axis coefficient rows (highest order first), rebuilt exactly like
+ * env_base::forward_action (env_base.h:228-231) from (parent state, U[action], dt). */
+template <int Dim>
+class Primitive {
+ public:
+  Primitive() {}
+  Primitive(const Waypoint<Dim> &p, const VecDf &u, decimal_t t) : t_(t), control_(p.control) {
+    for (int i = 0; i < Dim; i++) {
+      double *c = c_[i];
+      for (int k = 0; k < 6; k++) c[k] = 0;
+      switch (control_) { /* primitive.h:35-52 */
+        case Control::VEL: c[4] = u[i]; c[5] = p.pos(i); break;
+        case Control::ACC: c[3] = u[i]; c[4] = p.vel(i); c[5] = p.pos(i); break;
+        case Control::JRK: c[2] = u[i]; c[3] = p.acc(i); c[4] = p.vel(i); c[5] = p.pos(i); break;
+        case Control::SNP: c[1] = u[i]; c[2] = p.jrk(i); c[3] = p.acc(i); c[4] = p.vel(i); c[5] = p.pos(i); break;
+        default: break;
+      }
+    }
+  }
+  decimal_t t() const { return t_; }
+  Control::Control control() const { return control_; }
+  const double *coeff(int k) const { return c_[k]; } /* float64[6] row of planning_ros_msgs/Primitive (cx, cy, cz) */
+  Waypoint<Dim> evaluate(decimal_t t) const { /* primitive.h:128-145,321-331 */
+    Waypoint<Dim> p(control_);
+    for (int k = 0; k < Dim; k++) {
+      const double *c = c_[k];
+      const double t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
+      p.pos(k) = c[0] / 120 * t5 + c[1] / 24 * t4 + c[2] / 6 * t3 + c[3] / 2 * t * t + c[4] * t + c[5];
+      p.vel(k) = c[0] / 24 * t4 + c[1] / 6 * t3 + c[2] / 2 * t * t + c[3] * t + c[4];
+      p.acc(k) = c[0] / 6 * t3 + c[1] / 2 * t * t + c[2] * t + c[3];
+      p.jrk(k) = c[0] / 2 * t * t + c[1] * t + c[2];
+    }
+    return p;
+  }
+  decimal_t J(const Control::Control &control) const { /* primitive.h:92-122,403-407 for c0 = 0 rows */
+    decimal_t j = 0;
+    for (int k = 0; k < Dim; k++) {
+      const double *c = c_[k];
+      const double t = t_;
+      if (control == Control::VEL)
+        j += (c[1] * c[1] / 252) * std::pow(t, 7) + (c[1] * c[2] / 36) * std::pow(t, 6) + (c[2] * c[2] / 20 + c[1] * c[3] / 15) * std::pow(t, 5) +
+             (c[2] * c[3] / 4 + c[1] * c[4] / 12) * std::pow(t, 4) + (c[3] * c[3] / 3 + c[2] * c[4] / 3) * t * t * t + c[3] * c[4] * t * t + c[4] * c[4] * t;
+      else if (control == Control::ACC)
+        j += (c[1] * c[1] / 20) * std::pow(t, 5) + (c[1] * c[2] / 4) * std::pow(t, 4) + (c[2] * c[2] / 3 + c[1] * c[3] / 3) * t * t * t + c[2] * c[3] * t * t + c[3] * c[3] * t;
+      else if (control == Control::JRK)
+        j += (c[1] * c[1]) / 3 * t * t * t + c[1] * c[2] * t * t + c[2] * c[2] * t;
+      else if (control == Control::SNP)
+        j += c[1] * c[1] * t;
+    }
+    return j;
+  }
+
+ private:
+  decimal_t t_{0};
+  Control::Control control_{Control::NONE};
+  double c_[Dim][6];
+};
+typedef Primitive<2> Primitive2D;
+typedef Primitive<3> Primitive3D;
+
+/* trajectory.h:42-57,250-254,277-292 */
+template <int Dim>
+class Trajectory {
+ public:
+  Trajectory() : total_t_(0) {}
+  Trajectory(const vec_E<Primitive<Dim>> &prs) : segs(prs) {
+    taus.push_back(0);
+    for (const auto &pr : prs) taus.push_back(pr.t() + taus.back());
+    total_t_ = taus.back();
+  }
+  decimal_t getTotalTime() const { return total_t_; }
+  vec_E<Primitive<Dim>> getPrimitives() const { return segs; }
+  decimal_t J(const Control::Control &control) const {
+    decimal_t j = 0;
+    for (const auto &seg : segs) j += seg.J(control);
+    return j;
+  }
+  vec_E<Waypoint<Dim>> getWaypoints() const {
+    vec_E<Waypoint<Dim>> ws;
+    if (segs.empty()) return ws;
+    decimal_t t = 0;
+    for (const auto &seg : segs) {
+      ws.push_back(seg.evaluate(0));
+      ws.back().t = t;
+      t += seg.t();
+    }
+    ws.push_back(segs.back().evaluate(segs.back().t()));
+    ws.back().t = t;
+    return ws;
+  }
+  vec_E<Primitive<Dim>> segs;
+  std::vector<decimal_t> taus;
+
+ private:
+  decimal_t total_t_;
+};
+typedef Trajectory<2> Trajectory2D;
+typedef Trajectory<3> Trajectory3D;
+
+namespace MPL {
+
+typedef std::vector<signed char> Tmap; /* map_util.h:14 */
+
+/* map_util.h:20-314 — the grid lives on the GPU; getters read it back. */
+template <int Dim>
+class MapUtil {
+ public:
+  MapUtil() {}
+  ~MapUtil() { if (h_) mplb_map_destroy(h_); }
+  MapUtil(const MapUtil &) = delete;
+  MapUtil &operator=(const MapUtil &) = delete;
+
+  void setMap(const Vecf<Dim> &ori, const Veci<Dim> &dim, const Tmap &map, decimal_t res) { /* map_util.h:84-90 */
+    if (h_) { mplb_map_destroy(h_); h_ = nullptr; }
+    int32_t nd[3] = {1, 1, 1};
+    double o[3] = {0, 0, 0};
+    for (int i = 0; i < Dim; i++) { nd[i] = dim(i); o[i] = ori(i); }
+    dim_ = dim; origin_d_ = ori; res_ = res;
+    if (mplb_map_create(Dim, nd, o, res, reinterpret_cast<const int8_t *>(map.data()), &h_) != MPLB_OK)
+      std::printf("[MapUtil] setMap failed: %s\n", mplb_last_error());
+  }
+  void freeUnknown() { if (h_) mplb_map_free_unknown(h_); }                               /* map_util.h:259-276 */
+  void dilate(const vec_Veci<Dim> &dilate_neighbor) {                                      /* map_util.h:221-257 */
+    std::vector<int32_t> ns;
+    for (const auto &it : dilate_neighbor) for (int i = 0; i < Dim; i++) ns.push_back(it(i));
+    if (h_) mplb_map_dilate(h_, ns.data(), (int)dilate_neighbor.size());
+  }
+  Tmap getMap() {                                                                          /* map_util.h:25 */
+    size_t n = 1;
+    for (int i = 0; i < Dim; i++) n *= (size_t)dim_(i);
+    Tmap m(n);
+    if (h_) mplb_map_get_data(h_, reinterpret_cast<int8_t *>(m.data()), n);
+    return m;
+  }
+  decimal_t getRes() { return res_; }
+  Veci<Dim> getDim() { return dim_; }
+  Vecf<Dim> getOrigin() { return origin_d_; }
+  Veci<Dim> floatToInt(const Vecf<Dim> &pt) { /* map_util.h:103-108 */
+    Veci<Dim> pn;
+    for (int i = 0; i < Dim; i++) pn(i) = (int)std::round((pt(i) - origin_d_(i)) / res_ - 0.5);
+    return pn;
+  }
+  Vecf<Dim> intToFloat(const Veci<Dim> &pn) { /* map_util.h:110-114 */
+    Vecf<Dim> p;
+    for (int i = 0; i < Dim; i++) p(i) = (pn(i) + 0.5) * res_ + origin_d_(i);
+    return p;
+  }
+  mplb_map *handle() const { return h_; }
+
+ private:
+  mplb_map *h_ = nullptr;
+  decimal_t res_ = 0;
+  Vecf<Dim> origin_d_;
+  Veci<Dim> dim_;
+};
+typedef MapUtil<2> OccMapUtil;
+typedef MapUtil<3> VoxelMapUtil;
+
+/* planner_base.h:18-345 + map_planner.h:20-125 */
+template <int Dim>
+class MapPlanner {
+ public:
+  typedef Waypoint<Dim> Coord;
+  MapPlanner(bool verbose = false) : planner_verbose_(verbose) {
+    if (mplb_planner_create(Dim, verbose ? 1 : 0, &h_) != MPLB_OK) std::printf("[MapPlanner] %s\n", mplb_last_error());
+  }
+  ~MapPlanner() { if (h_) mplb_planner_destroy(h_); }
+  MapPlanner(const MapPlanner &) = delete;
+  MapPlanner &operator=(const MapPlanner &) = delete;
+
+  void setMapUtil(const std::shared_ptr<MapUtil<Dim>> &map_util) { /* map_planner.cpp:14-18 */
+    map_util_ = map_util;
+    if (h_ && map_util && mplb_planner_set_map(h_, map_util->handle()) != MPLB_OK) report();
+  }
+  bool initialized() { return initialized_; }
+  void setVmax(decimal_t v) { set(MPLB_V_MAX, v); }
+  void setAmax(decimal_t a) { set(MPLB_A_MAX, a); }
+  void setJmax(decimal_t j) { set(MPLB_J_MAX, j); }
+  void setYawmax(decimal_t yaw) { set(MPLB_YAW_MAX, yaw); }
+  void setTmax(decimal_t t) { set(MPLB_T_MAX, t); }
+  void setDt(decimal_t dt) { dt_ = dt; set(MPLB_DT, dt); }
+  void setW(decimal_t w) { set(MPLB_W, w); }
+  void setEpsilon(decimal_t eps) { set(MPLB_EPSILON, eps); }
+  void setMaxNum(int num) { set(MPLB_MAX_NUM, num); }
+  void setTol(decimal_t tol_pos, decimal_t tol_vel = -1, decimal_t tol_acc = -1) { /* planner_base.h:255-265 */
+    set(MPLB_TOL_POS, tol_pos); set(MPLB_TOL_VEL, tol_vel); set(MPLB_TOL_ACC, tol_acc);
+  }
+  void setU(const vec_E<VecDf> &U) { /* planner_base.h:246 */
+    U_ = U;
+    std::vector<double> flat;
+    for (const auto &u : U) for (int k = 0; k < Dim; k++) flat.push_back(u[k]);
+    if (h_ && mplb_planner_set_controls(h_, flat.data(), (int)U.size(), Dim) != MPLB_OK) report();
+  }
+
+  /* planner_base.h:275-325 */
+  bool plan(const Coord &start, const Coord &goal) {
+    mplb_waypoint s = to_c(start), g = to_c(goal);
+    control_ = start.control;
+    traj_ = Trajectory<Dim>();
+    if (!h_ || mplb_plan(h_, &s, &g, &last_) != MPLB_OK) { report(); traj_cost_ = std::numeric_limits<decimal_t>::infinity(); return false; }
+    initialized_ = true;
+    traj_cost_ = last_.cost;
+    if (last_.status == MPLB_PLAN_OK) {
+      std::vector<int32_t> acts(last_.n_seg > 0 ? last_.n_seg : 1);
+      std::vector<double> st((size_t)(last_.n_seg > 0 ? last_.n_seg : 1) * 13);
+      mplb_get_actions(h_, acts.data(), (int)acts.size());
+      mplb_get_seg_states(h_, st.data(), (int)acts.size());
+      vec_E<Primitive<Dim>> prs;
+      for (int i = 0; i < last_.n_seg; i++) {
+        Waypoint<Dim> w(control_);
+        for (int k = 0; k < Dim; k++) { w.pos(k) = st[i * 13 + k]; w.vel(k) = st[i * 13 + 3 + k]; w.acc(k) = st[i * 13 + 6 + k]; w.jrk(k) = st[i * 13 + 9 + k]; }
+        prs.push_back(Primitive<Dim>(w, U_[acts[i]], dt_));
+      }
+      traj_ = Trajectory<Dim>(prs);
+    }
+    return last_.status == MPLB_PLAN_OK || last_.status == MPLB_PLAN_START_IS_GOAL;
+  }
+
+  Trajectory<Dim> getTraj() const { return traj_; }          /* planner_base.h:28 */
+  decimal_t getTrajCost() const { return traj_cost_; }       /* planner_base.h:155 */
+  int getExpandedNum() const { return last_.pops; }          /* planner_base.h:148 */
+  vec_Vecf<Dim> getCloseSet() const { return node_points(2, false); }     /* planner_base.h:84-91 */
+  vec_Vecf<Dim> getOpenSet() const {                                       /* planner_base.h:77-81 */
+    std::vector<mplb_node> nodes = fetch_nodes();
+    std::vector<int32_t> ids(last_.n_open > 0 ? last_.n_open : 1);
+    mplb_get_open(h_, ids.data(), (int)ids.size());
+    vec_Vecf<Dim> ps;
+    for (int i = 0; i < last_.n_open; i++) ps.push_back(pos_of(nodes[ids[i]]));
+    return ps;
+  }
+  vec_Vecf<Dim> getExpandedNodes() const {                                 /* planner_base.h:140, env_map.h:154 */
+    std::vector<mplb_node> nodes = fetch_nodes();
+    std::vector<int32_t> ids(last_.pops > 0 ? last_.pops : 1);
+    int n = mplb_get_pop_log(h_, ids.data(), (int)ids.size());
+    vec_Vecf<Dim> ps;
+    for (int i = 0; i < n; i++) ps.push_back(pos_of(nodes[ids[i]]));
+    return ps;
+  }
+  const mplb_result &result() const { return last_; }
+  mplb_planner *handle() const { return h_; }
+
+ protected:
+  void set(int key, double v) { if (h_ && mplb_planner_set_param(h_, key, v) != MPLB_OK) report(); }
+  void report() const { if (planner_verbose_) std::printf("[MapPlanner] %s\n", mplb_last_error()); }
+  static mplb_waypoint to_c(const Coord &w) {
+    mplb_waypoint c;
+    for (int k = 0; k < 3; k++) { c.pos[k] = c.vel[k] = c.acc[k] = c.jrk[k] = 0; }
+    for (int k = 0; k < Dim; k++) { c.pos[k] = w.pos(k); c.vel[k] = w.vel(k); c.acc[k] = w.acc(k); c.jrk[k] = w.jrk(k); }
+    c.yaw = w.yaw; c.t = w.t; c.control = (int)w.control; c.enable_t = w.enable_t ? 1 : 0;
+    return c;
+  }
+  std::vector<mplb_node> fetch_nodes() const {
+    std::vector<mplb_node> nodes(last_.n_nodes > 0 ? last_.n_nodes : 1);
+    mplb_get_nodes(h_, nodes.data(), (int)nodes.size());
+    return nodes;
+  }
+  static Vecf<Dim> pos_of(const mplb_node &n) {
+    Vecf<Dim> p;
+    for (int k = 0; k < Dim; k++) p(k) = n.state[k];
+    return p;
+  }
+  vec_Vecf<Dim> node_points(int flag, bool) const {
+    std::vector<mplb_node> nodes = fetch_nodes();
+    vec_Vecf<Dim> ps;
+    for (int i = 0; i < last_.n_nodes; i++)
+      if ((flag == 2 && nodes[i].closed) || (flag == 1 && nodes[i].opened)) ps.push_back(pos_of(nodes[i]));
+    return ps;
+  }
+
+  mplb_planner *h_ = nullptr;
+  std::shared_ptr<MapUtil<Dim>> map_util_;
+  vec_E<VecDf> U_;
+  decimal_t dt_ = 1.0;
+  Control::Control control_ = Control::NONE;
+  Trajectory<Dim> traj_;
+  decimal_t traj_cost_ = std::numeric_limits<decimal_t>::infinity();
+  mplb_result last_{};
+  bool initialized_ = false;
+  bool planner_verbose_;
+};
+typedef MapPlanner<2> OccMapPlanner;   /* map_planner.h:122 */
+typedef MapPlanner<3> VoxelMapPlanner; /* map_planner.h:125 */
+
+}  // namespace MPL
+#endif

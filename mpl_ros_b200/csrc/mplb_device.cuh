@@ -16,7 +16,7 @@
 
 namespace mplb {
 
-#define MPLB_NT 128   /* threads per CTA: one CTA owns one plan */
+#define MPLB_NT 256   /* threads per CTA: one CTA owns one plan (warp 0 search, warps 1-6 sampling, warp 7 heap) */
 #define MPLB_MAXU 128 /* max |U| */
 
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }

@@ -585,7 +585,7 @@ template <int DIM, int ORD, class SM>
 __device__ __forceinline__ void sample_granules(const DevCfg &c, SM &S, int t, int nthreads) {
   const int gstep = nthreads >> 3;
   const int sub = t & 7;
-  constexpr int R = 2; /* granules in flight per thread */
+  constexpr int R = 4; /* granules in flight per thread */
   for (int g0 = t >> 3; g0 < S.n_gran; g0 += R * gstep) {
     unsigned info[R];
     double st[R];
@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
       /* ================= P1/P2 ================= */
       /* per-control registers of warp 0 (probe results), one set per 32-control batch */
       unsigned long long rk0[NB], rk1[NB];
-      if (warp == 3) {
+      if (warp == NW - 1) {
         /* ---- heap warp: finish the previous pop's sift-down, then prefetch the new root's state row */
         if (lane == 0) {
           if (S.sd_pending) { H.sift_down(S.n_heap, 0, S.sd_f, S.sd_g, S.sd_n); S.sd_pending = 0; }
@@ -826,12 +826,12 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
             if (ORD >= 3) S.Ap[1 * 3 + ax] = dmul(dmul(S.cur[2 * DIM + ax], 0.5), c.inv_res);
             if (ORD >= 4) S.Ap[2 * 3 + ax] = dmul(ddiv(S.cur[3 * DIM + ax], 6.0), c.inv_res);
           }
-        } else {
+        } else if (warp == 2) {
           /* ---- goal test (gs:146) and parity hash of the current node */
           bool gh = goal_test_warp<DIM, ORD>(c, S, S.cur, lane);
           if (lane == 0) { S.goal_hit = gh ? 1 : 0; S.cur_kh = khash_of_ints<NS>(S.cur_ints); }
         }
-        asm volatile("bar.sync 1, 96;" ::: "memory"); /* warps 0-2: B1 outputs, sampling base, goal flag are visible */
+        asm volatile("bar.sync 1, %0;" ::"n"(MPLB_NT - 32) : "memory"); /* all but the heap warp: B1 outputs, sampling base, goal flag visible */
         MPLB_TICK(0);
         if (warp == 0) {
           /* issue the table probes — WIN consecutive 32-byte slots per candidate, one HBM round trip in all but a
@@ -869,15 +869,15 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
           }
           MPLB_TICK(1);
         }
-        /* ---- B2: all collision samples of all controls, flat over 8-sample granules (warps 1-2; warp 3 joins below) */
+        /* ---- B2: all collision samples of all controls, flat over 8-sample granules (warps 1..NW-2) */
         if (warp != 0) {
 #ifndef MPLB_EXPERIMENT_NOSAMPLE
-          if (fast) sample_granules<DIM, ORD>(c, S, tid - 32, 64);
+          if (fast) sample_granules<DIM, ORD>(c, S, tid - 32, MPLB_NT - 64);
           else
 #else
           if (!fast)
 #endif
-          expand_b2_percontrol<DIM, ORD>(c, S, warp - 1, lane, 2);
+          expand_b2_percontrol<DIM, ORD>(c, S, warp - 1, lane, NW - 2);
         }
       }
       MPLB_TICK(2);
