@@ -395,8 +395,35 @@ int launch_batch(const DevCfg &c, const BatchArgs &a, int grid, cudaStream_t s) 
   size_t smem = sizeof(PlanSmem<DIM, ORD, MAXU>);
   auto kern = astar_batch_kernel<DIM, ORD, MAXU>;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, MPLB_NT, smem, s>>>(c, a);
+  /* the occupancy bricks are the only data with reuse across pops and plans: keep them resident in L2 */
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(MPLB_NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  int nattr = 0;
+  size_t brick_bytes = (size_t)c.bd[0] * c.bd[1] * c.bd[2] * sizeof(unsigned long long);
+  static thread_local int persist_max = -1, window_max = 0;
+  if (persist_max < 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&window_max, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_max / 2);
+    cudaGetLastError();
+  }
+  if (persist_max > 0 && window_max > 0) {
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = const_cast<unsigned long long *>(c.bricks);
+    attr[0].val.accessPolicyWindow.num_bytes = std::min(brick_bytes, (size_t)window_max);
+    attr[0].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)(persist_max / 2) / (double)std::max<size_t>(brick_bytes, 1));
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    nattr = 1;
+  }
+  cfg.attrs = attr; cfg.numAttrs = nattr;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, c, a);
   g_launches++;
+  if (e != cudaSuccess) return fail(MPLB_ERR_CUDA, std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(e));
   CUDA_TRY(cudaGetLastError());
   return MPLB_OK;
 }

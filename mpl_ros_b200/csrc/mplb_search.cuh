@@ -241,6 +241,26 @@ struct HeapView {
   }
 };
 
+/* Arena data (table slots, node records, state rows) is touched once or twice per pop: load it with .cg so that it
+ * does not evict the occupancy bricks, which are the only global data with reuse, from L1. */
+__device__ __forceinline__ Slot load_slot_cg(const Slot *p) {
+  const int4 *q = reinterpret_cast<const int4 *>(p);
+  int4 a = __ldcg(q), b = __ldcg(q + 1);
+  Slot s;
+  s.k0 = ((unsigned long long)(unsigned)a.y << 32) | (unsigned)a.x;
+  s.k1lo = (unsigned)a.z; s.node1 = (unsigned)a.w;
+  s.g = __hiloint2double(b.y, b.x); s.pg = __hiloint2double(b.w, b.z);
+  return s;
+}
+__device__ __forceinline__ NodeHot load_hot_cg(const NodeHot *p) {
+  const int4 *q = reinterpret_cast<const int4 *>(p);
+  int4 a = __ldcg(q), b = __ldcg(q + 1);
+  NodeHot h;
+  h.g = __hiloint2double(a.y, a.x); h.h = __hiloint2double(a.w, a.z); h.pg = __hiloint2double(b.y, b.x);
+  h.heap_pos = b.z; h.action = (short)(b.w & 0xffff); h.flags = (unsigned char)((b.w >> 16) & 0xff); h.pad0 = 0;
+  return h;
+}
+
 /* ---------------------------------------------------------------- hash table */
 __device__ __forceinline__ unsigned table_hash(unsigned long long k0, unsigned long long k1) {
   unsigned long long h = (k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
@@ -786,10 +806,10 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
           if (S.n_heap > 0) {
             pf = S.hn[0] & 0x7fffffff;
             const RowHdr *rh = reinterpret_cast<const RowHdr *>(rows + (size_t)pf * ROWB);
-            S.pf_k0 = rh->k0; S.pf_k1 = rh->k1;
+            S.pf_k0 = __ldcg(&rh->k0); S.pf_k1 = __ldcg(&rh->k1);
             const double *rs = reinterpret_cast<const double *>(rows + (size_t)pf * ROWB + sizeof(RowHdr));
 #pragma unroll
-            for (int f = 0; f < NS; f++) S.pf_st[f] = rs[f];
+            for (int f = 0; f < NS; f++) S.pf_st[f] = __ldcg(&rs[f]);
           }
           S.pf_node = pf;
         }
@@ -846,7 +866,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
             Slot sw[WIN];
             if (probing) {
 #pragma unroll
-              for (int q = 0; q < WIN; q++) sw[q] = table[(h0 + q) & mask];
+              for (int q = 0; q < WIN; q++) sw[q] = load_slot_cg(&table[(h0 + q) & mask]);
             }
             double hv = 0.0;
             if (probing) hv = heuristic<DIM, ORD>(c, S, &S.es[i * NS], rk0[b], rk1[b]);
@@ -954,7 +974,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
           if (valid) S.nid[i] = nid;
           double hval = r_h_b;
           int fl = 0, hpos = -1;
-          if (improve) { const NodeHot hn = hot[nid]; hval = hn.h; fl = hn.flags; hpos = hn.heap_pos; } /* rare dependent load */
+          if (improve) { const NodeHot hn = load_hot_cg(&hot[nid]); hval = hn.h; fl = hn.flags; hpos = hn.heap_pos; } /* rare dependent load */
           const double f = dadd(tentative, dmul(c.eps, hval));
           MPLB_TICK2(2);
           /* lane-parallel stores */

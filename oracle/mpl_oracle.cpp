@@ -405,7 +405,8 @@ struct Planner {
   std::vector<int> pop_order;
   std::vector<int> traj_actions;
   std::vector<int> traj_nodes;  // parent node of each segment
-  long long dbg_increase = 0;  // decrease-key events (diagnostics, printed when ORC_DEBUG is set)
+  long long dbg_increase = 0, dbg_pred_total = 0, dbg_pred_hit = 0, dbg_pred_new = 0;
+  int dbg_pred = -1, dbg_nodes_before = 0;  // decrease-key events (diagnostics, printed when ORC_DEBUG is set)
   orc_result last;
 
   /* em:25-45 */
@@ -533,7 +534,10 @@ struct Planner {
     while (true) {
       expand_iteration++;
       curr = heap.top_node();
+      if (dbg_pred >= 0) { dbg_pred_total++; if (dbg_pred == curr) dbg_pred_hit++; else if (curr >= dbg_nodes_before) dbg_pred_new++; }
       heap.pop();
+      dbg_pred = heap.empty() ? -1 : heap.top_node();
+      dbg_nodes_before = (int)nodes.size();
       uint64_t kh = key_hash(nodes[curr].key);
       pop_hash = (pop_hash ^ kh) * 0x100000001B3ull;
       if (!nodes[curr].closed) { n_closed++; closed_hash += kh; }
@@ -574,7 +578,7 @@ struct Planner {
       if (heap.empty()) { status = 3; break; }                                           // gs:157-161
     }
     last.pops = expand_iteration;
-    if (std::getenv("ORC_DEBUG")) std::fprintf(stderr, "orc: pops %d nodes %zu increase %lld valid %lld\n", expand_iteration, nodes.size(), dbg_increase, (long long)last.n_valid);
+    if (std::getenv("ORC_DEBUG")) std::fprintf(stderr, "orc: pops %d nodes %zu increase %lld valid %lld pred_hit %.3f pred_new %.3f\n", expand_iteration, nodes.size(), dbg_increase, (long long)last.n_valid, dbg_pred_total ? (double)dbg_pred_hit / dbg_pred_total : 0.0, dbg_pred_total ? (double)dbg_pred_new / dbg_pred_total : 0.0);
     last.n_nodes = (int)nodes.size();
     last.n_open = (int)heap.q.size();
     last.n_closed = n_closed;
