@@ -63,7 +63,7 @@ def b_alg(res, nU):
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, gpu):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -73,7 +73,9 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """t0/t1: wall-clock window (time.time()) of the timed region; samples outside it are dropped when at least
+        three fall inside (the sampler is started before the warm-up because nvidia-smi takes ~0.5 s to start)."""
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -82,6 +84,22 @@ class ClockSampler:
         self.f.flush()
         rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
+        rows = [r for r in rows if len(r) >= 10]
+        window = "timed region"
+        if t0 is not None:
+            import datetime
+            inside = []
+            for r in rows:
+                try:
+                    ts = datetime.datetime.strptime(r[9].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    continue
+                if t0 - 0.05 <= ts <= t1 + 0.05:
+                    inside.append(r)
+            if len(inside) >= 3:
+                rows = inside
+            else:
+                window = "warm-up + timed region (fewer than 3 samples fell inside the timed region)"
         sm = [float(r[1]) for r in rows if len(r) >= 9]
         reasons = set()
         for r in rows:
@@ -91,7 +109,7 @@ class ClockSampler:
                 if v.strip().lower() == "active":
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(rows[0][2]) if rows else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def run_reference(args):
@@ -163,6 +181,7 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MPLB_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -209,12 +228,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
     for _ in range(args.warmup):
         flush.zero_()
         step_device()
     barrier()
     launches0 = _lib.lib().mplb_launch_count()
-    clocks = ClockSampler(local)
+    t_wall0 = time.time()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms = []
     for k in range(args.steps):
@@ -224,7 +244,8 @@ def main():
         ev[k][1].record(stream)
         kernel_ms.append(pl.last_batch_stats()["kernel_ms"])
     barrier()
-    clk = clocks.stop()
+    t_wall1 = time.time()
+    clk = clocks.stop(t_wall0, t_wall1)
     launches = int(_lib.lib().mplb_launch_count() - launches0)
     ms_steps = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(ms_steps))
