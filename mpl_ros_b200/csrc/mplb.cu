@@ -121,8 +121,14 @@ __global__ void k_label_step(int *lab, int nx, int ny, int nz, int *changed) {
   }
   if (any) *changed = 1;
 }
-__global__ void k_plan_keys(const mplb_waypoint *starts, const mplb_waypoint *goals, int n, const int *lab, int dim, int nx, int ny,
-                            int nz, double ox, double oy, double oz, double res, unsigned *keys) {
+__global__ void k_label_count(const int *lab, int *cnt, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int l = lab[i];
+    if (l >= 0) atomicAdd(&cnt[l], 1);
+  }
+}
+__global__ void k_plan_keys(const mplb_waypoint *starts, const mplb_waypoint *goals, int n, const int *lab, const int *comp_size,
+                            int dim, int nx, int ny, int nz, double ox, double oy, double oz, double res, unsigned *keys) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double o[3] = {ox, oy, oz};
@@ -142,7 +148,10 @@ __global__ void k_plan_keys(const mplb_waypoint *starts, const mplb_waypoint *go
   if (lab && in_s && in_g) {
     int ls = lab[(size_t)cs[0] + (size_t)nx * cs[1] + (size_t)nx * ny * cs[2]];
     int lg = lab[(size_t)cg[0] + (size_t)nx * cg[1] + (size_t)nx * ny * cg[2]];
-    if (ls >= 0 && ls != lg) key |= 1u << 30; /* goal not in the start's free-space component: exhaustive search expected */
+    if (ls >= 0 && ls != lg) { /* goal not in the start's free-space component: the search exhausts that component */
+      unsigned sz = comp_size ? (unsigned)comp_size[ls] >> 3 : 0u;
+      key = (1u << 30) | (sz > 0xffffffu ? 0xffffffu : sz);
+    }
   }
   keys[i] = key;
 }
@@ -169,6 +178,7 @@ struct mplb_map {
   int8_t *d_grid = nullptr;
   unsigned long long *d_bricks = nullptr;
   int *d_labels = nullptr; /* free-space component label per cell (scheduling hint), built lazily */
+  int *d_comp_size = nullptr; /* number of cells carrying each label */
   unsigned long long labels_version = ~0ull;
   unsigned long long version = 0;
 
@@ -492,6 +502,12 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
           CUDA_TRY(cudaStreamSynchronize(s));
           if (!changed) break;
         }
+        if (!m->d_comp_size && cudaMalloc((void **)&m->d_comp_size, m->ncell * sizeof(int)) != cudaSuccess) { cudaGetLastError(); m->d_comp_size = nullptr; }
+        if (m->d_comp_size) {
+          CUDA_TRY(cudaMemsetAsync(m->d_comp_size, 0, m->ncell * sizeof(int), s));
+          k_label_count<<<blocks, 256, 0, s>>>(m->d_labels, m->d_comp_size, m->ncell);
+          g_launches++;
+        }
         m->labels_version = m->version;
       }
     }
@@ -499,8 +515,9 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
     CUDA_TRY(cudaEventRecord(p->ev0, s)); /* the per-batch ordering kernels are inside the timed region */
     ev0_done = true;
     int nb = (n + 127) / 128;
-    k_plan_keys<<<nb, 128, 0, s>>>(d_starts, d_goals, n, (m->labels_version == m->version) ? m->d_labels : nullptr, m->dim, m->nd[0],
-                                 m->nd[1], m->nd[2], m->origin[0], m->origin[1], m->origin[2], m->res, p->d_keys.p);
+    const bool have_labels = (m->labels_version == m->version) && m->d_labels;
+    k_plan_keys<<<nb, 128, 0, s>>>(d_starts, d_goals, n, have_labels ? m->d_labels : nullptr, have_labels ? m->d_comp_size : nullptr,
+                                 m->dim, m->nd[0], m->nd[1], m->nd[2], m->origin[0], m->origin[1], m->origin[2], m->res, p->d_keys.p);
     k_plan_order<<<nb, 128, 0, s>>>(p->d_keys.p, n, p->d_work.p);
     g_launches += 2;
     p->last_launches += 2;
@@ -714,6 +731,7 @@ void mplb_map_destroy(mplb_map *m) {
   if (m->d_grid) cudaFree(m->d_grid);
   if (m->d_bricks) cudaFree(m->d_bricks);
   if (m->d_labels) cudaFree(m->d_labels);
+  if (m->d_comp_size) cudaFree(m->d_comp_size);
   delete m;
 }
 

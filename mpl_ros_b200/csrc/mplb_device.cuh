@@ -18,6 +18,9 @@ namespace mplb {
 
 #define MPLB_NT 256   /* threads per CTA: one CTA owns one plan (warp 0 search, warps 1-6 sampling, warp 7 heap) */
 #define MPLB_MAXU 128 /* max |U| */
+#ifndef MPLB_MIN_CTAS
+#define MPLB_MIN_CTAS 3 /* resident CTAs per SM the search kernel is compiled for (4 caps registers at 64 and spills: measured no faster) */
+#endif
 
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }

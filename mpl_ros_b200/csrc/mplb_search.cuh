@@ -121,12 +121,39 @@ struct BatchArgs {
 #define MPLB_TICK(k) do { } while (0)
 #endif
 
+/* Everything get_succ produces for one node (B1 outputs, sampling base, sample list, collision outcomes).  With
+ * |U| <= 32 there are two of them: while the search warp commits the current node, the heap warp already runs B1 for
+ * the node that will be popped next (the heap root after the previous pop's sift-down is the next pop unless a
+ * successor overtakes it, which measured < 0.1 % of the pops). */
+template <int DIM, int ORD, int MAXU>
+struct ExpBuf {
+  static constexpr int NS = DIM * ORD;
+  static constexpr int GCAP = MAXU * 8; /* 8-sample granules */
+  double st[NS];     /* state of the expanded node */
+  int ints[NS];      /* its lattice ints */
+  int node, ready, key_bad, n_gran;
+  double y0[3];      /* filtered sampling: cell coordinate of the parent and lower coefficients, in cells */
+  double Ap[3 * 3];
+  double es[MAXU * NS]; /* end states, [u][d*DIM+ax] */
+  unsigned long long k0[MAXU], k1[MAXU];
+  int verdict[MAXU]; /* 0 self, 1 dyn, 2 blocked, 3 valid, 4 valid-no-motion, 5 needs sampling (transient) */
+  int nsamp[MAXU];   /* divisor n */
+  int cnt[MAXU];     /* samples to test */
+  int first[MAXU];   /* first blocked sample index or INT_MAX */
+  int nid[MAXU];     /* node id of the successor after relaxation (for state forwarding) */
+  unsigned int gl[GCAP];     /* granule: control | first sample k0 << 8 | sample count << 16 ... */
+  unsigned short gl_t[GCAP]; /* ... and index of its first sample time in tts */
+};
+
 template <int DIM, int ORD, int NB>
 struct PlanSmem {
   static constexpr int NS = DIM * ORD;
   static constexpr int MAXU = 32 * NB;
+  static constexpr int NBUF = (NB == 1) ? 2 : 1; /* expansion records: 2 = B1 of the next pop is pipelined */
+  typedef ExpBuf<DIM, ORD, MAXU> EB;
+  EB eb[NBUF];
+  int cur_buf;
   static constexpr int HCAP = (NB == 1) ? 1536 : 1024; /* heap entries kept in shared memory */
-  static constexpr int GCAP = MAXU * 8;                /* 8-sample granules */
   /* heap top (SoA) */
   double hf[HCAP], hg[HCAP];
   int hn[HCAP];
@@ -145,24 +172,10 @@ struct PlanSmem {
   double Ut[MAXU * 3]; /* u / ORD! exactly as pr:128-131 divides the leading coefficient */
   double Au[MAXU * 3]; /* top polynomial coefficient of the filtered sampling path, in cells */
   int toff_s[MPLB_NCAP], tcnt_s[MPLB_NCAP];
-  /* per-pop sampling base (fast path): cell coordinate of the parent = Y0 + fy0, lower coefficients in cells */
-  double y0[3];
-  double Ap[3 * 3];
-  /* per-control results of get_succ */
-  double es[MAXU * NS]; /* end states, [u][d*DIM+ax] */
-  unsigned long long k0[MAXU], k1[MAXU];
-  int verdict[MAXU]; /* 0 self, 1 dyn, 2 blocked, 3 valid, 4 valid-no-motion, 5 needs sampling (transient) */
-  int nsamp[MAXU];   /* divisor n */
-  int cnt[MAXU];     /* samples to test */
-  int first[MAXU];   /* first blocked sample index or INT_MAX */
-  int nid[MAXU];     /* node id of the successor after relaxation (for state forwarding) */
   /* probe results of warp 0 (staged in shared memory so nothing lives in registers across the barrier) */
   int p_nid[MAXU], p_slot[MAXU];
   double p_g[MAXU], p_pg[MAXU], p_h[MAXU];
-  unsigned int gl[GCAP]; /* granule: control | first sample k0 << 8 | sample count << 16 ... */
-  unsigned short gl_t[GCAP]; /* ... and index of its first sample time in tts */
   double tts[MPLB_TT_CAP]; /* accumulated sample times (em:98-99), all divisors */
-  int n_gran;
   int n_before;      /* n_nodes before this expansion */
   /* pending sift-down (heap warp) and prefetched root row */
   int sd_pending, sd_n;
@@ -170,7 +183,7 @@ struct PlanSmem {
   int pf_node;
   unsigned long long pf_k0, pf_k1;
   double pf_st[NS];
-  int n_nodes, n_heap, tsize, pops, n_closed, status, plan_idx, key_bad;
+  int n_nodes, n_heap, tsize, pops, n_closed, status, plan_idx;
   long long n_samples, n_valid;
   unsigned long long pop_hash, closed_hash;
 #ifdef MPLB_PHASE_TIMING
@@ -332,8 +345,8 @@ __device__ __forceinline__ int sample_divisor(double max_v, double T, double res
 }
 
 /* ---------------------------------------------------------------- phase B1: one lane per control (em:155-160,163-165) */
-template <int DIM, int ORD, class SM>
-__device__ __forceinline__ void expand_b1(const DevCfg &c, SM &S, int i, unsigned long long &k0, unsigned long long &k1) {
+template <int DIM, int ORD, class SM, class EBT>
+__device__ __forceinline__ void expand_b1(const DevCfg &c, const SM &S, EBT &E, int i) {
   constexpr int NS = DIM * ORD;
   const double T = c.dt;
   double es[NS];
@@ -341,7 +354,7 @@ __device__ __forceinline__ void expand_b1(const DevCfg &c, SM &S, int i, unsigne
   bool dyn_ok = true, same_pos = true;
 #pragma unroll
   for (int ax = 0; ax < DIM; ax++) {
-    Axis<ORD> A(&S.cur[ax], DIM, S.U[i * 3 + ax], S.Ut[i * 3 + ax]);
+    Axis<ORD> A(&E.st[ax], DIM, S.U[i * 3 + ax], S.Ut[i * 3 + ax]);
     es[0 * DIM + ax] = A.p(T);
     if (ORD >= 2) es[1 * DIM + ax] = A.v(T);
     if (ORD >= 3) es[2 * DIM + ax] = A.a(T);
@@ -352,7 +365,7 @@ __device__ __forceinline__ void expand_b1(const DevCfg &c, SM &S, int i, unsigne
     if (ORD >= 2 && c.v_max > 0.0 && mv > c.v_max) dyn_ok = false;
     if (ORD >= 3 && c.a_max > 0.0 && A.max_acc(T) > c.a_max) dyn_ok = false;
     if (ORD >= 4 && c.j_max > 0.0 && A.max_jrk(T) > c.j_max) dyn_ok = false;
-    same_pos = same_pos && (S.cur[ax] == es[ax]); /* em:163 */
+    same_pos = same_pos && (E.st[ax] == es[ax]); /* em:163 */
   }
   int ints[NS];
 #pragma unroll
@@ -363,12 +376,13 @@ __device__ __forceinline__ void expand_b1(const DevCfg &c, SM &S, int i, unsigne
   }
   bool self = true;
 #pragma unroll
-  for (int f = 0; f < NS; f++) self = self && (ints[f] == S.cur_ints[f]);
+  for (int f = 0; f < NS; f++) self = self && (ints[f] == E.ints[f]);
 #pragma unroll
-  for (int f = 0; f < NS; f++) S.es[i * NS + f] = es[f];
+  for (int f = 0; f < NS; f++) E.es[i * NS + f] = es[f];
+  unsigned long long k0, k1;
   bool key_ok = pack_key_nohash<DIM, ORD>(c, ints, k0, k1);
-  S.k0[i] = k0; S.k1[i] = k1;
-  S.first[i] = 0x7fffffff;
+  E.k0[i] = k0; E.k1[i] = k1;
+  E.first[i] = 0x7fffffff;
   int verdict, n = 0, cnt = 0;
   if (self) verdict = 0;
   else if (!dyn_ok) verdict = 1;
@@ -378,16 +392,52 @@ __device__ __forceinline__ void expand_b1(const DevCfg &c, SM &S, int i, unsigne
     n = sample_divisor(max_v, T, c.res, c.inv_res);
     cnt = (n < MPLB_NCAP && c.use_fast) ? S.tcnt_s[n] : c.tcnt[n];
   }
-  S.nsamp[i] = n;
-  S.cnt[i] = cnt;
-  if ((verdict >= 3) && !key_ok) S.key_bad = 1;
-  S.verdict[i] = verdict;
-  S.nid[i] = -1;
+  E.nsamp[i] = n;
+  E.cnt[i] = cnt;
+  if ((verdict >= 3) && !key_ok) E.key_bad = 1;
+  E.verdict[i] = verdict;
+  E.nid[i] = -1;
+}
+
+/* B1 for all controls of one node by ONE warp, plus the flat sample list (granules) and the sampling base.
+ * E.st / E.ints must hold the node's state and lattice ints. */
+template <int DIM, int ORD, int NB, class SM, class EBT>
+__device__ __forceinline__ void b1_warp(const DevCfg &c, const SM &S, EBT &E, int lane, bool fast) {
+  if (lane == 0) E.key_bad = 0;
+  if (fast && lane < DIM) { /* sampling base (cells): parent cell coordinate and lower polynomial coefficients */
+    const int ax = lane;
+    E.y0[ax] = dmul(dsub(E.st[ax], c.origin[ax]), c.inv_res);
+    if (ORD >= 2) E.Ap[0 * 3 + ax] = dmul(E.st[DIM + ax], c.inv_res);
+    if (ORD >= 3) E.Ap[1 * 3 + ax] = dmul(dmul(E.st[2 * DIM + ax], 0.5), c.inv_res);
+    if (ORD >= 4) E.Ap[2 * 3 + ax] = dmul(div_exact(E.st[3 * DIM + ax], 6.0), c.inv_res);
+  }
+  __syncwarp();
+  int gbase = 0;
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    const int i = b * 32 + lane;
+    int ng = 0;
+    if (i < c.nU) {
+      expand_b1<DIM, ORD>(c, S, E, i);
+      if (fast && E.verdict[i] == 5) ng = (E.cnt[i] + 7) >> 3;
+    }
+    int incl = ng; /* warp scan of the granule counts */
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    int excl = gbase + incl - ng;
+    for (int q = 0; q < ng; q++) {
+      E.gl[excl + q] = (unsigned)i | ((unsigned)(q * 8) << 8) | ((unsigned)E.cnt[i] << 16);
+      E.gl_t[excl + q] = (unsigned short)(S.toff_s[E.nsamp[i]] + q * 8);
+    }
+    gbase += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) E.n_gran = gbase;
+  __syncwarp();
 }
 
 /* One collision sample, exact (em:100-104,119): true when the sample at time t of control i is outside or occupied. */
 template <int DIM, int ORD, class SM>
-__device__ __noinline__ bool sample_blocked_exact(const DevCfg &c, const SM &S, int i, double t, int *cell_idx) {
+__device__ __noinline__ bool sample_blocked_exact(const DevCfg &c, const SM &S, const double *st, int i, double t, int *cell_idx) {
 #ifdef MPLB_PHASE_TIMING
   atomicAdd(const_cast<unsigned long long *>(&S.dbg[4]), 1ull);
 #endif
@@ -395,7 +445,7 @@ __device__ __noinline__ bool sample_blocked_exact(const DevCfg &c, const SM &S, 
   bool outside = false;
 #pragma unroll
   for (int ax = 0; ax < DIM; ax++) {
-    Axis<ORD> A(&S.cur[ax], DIM, S.U[i * 3 + ax], S.Ut[i * 3 + ax]);
+    Axis<ORD> A(&st[ax], DIM, S.U[i * 3 + ax], S.Ut[i * 3 + ax]);
     pn[ax] = float_to_cell(A.p(t), c.origin[ax], c.res);
     outside = outside || pn[ax] < 0 || pn[ax] >= c.nd[ax];
   }
@@ -410,16 +460,16 @@ __device__ __noinline__ bool sample_blocked_exact(const DevCfg &c, const SM &S, 
  * farther than c.fast_delta (>= 2^-40 * the same magnitude, set by the host) from a rounding tie, round(y - 0.5)
  * equals the reference's round((p - origin)/res - 0.5) (mu:103-108).  Otherwise *sure is cleared and the caller
  * evaluates the exact formula. */
-template <int DIM, int ORD, class SM>
-__device__ __forceinline__ bool sample_blocked_filtered(const DevCfg &c, const SM &S, int i, double t, bool *sure) {
+template <int DIM, int ORD, class SM, class EBT>
+__device__ __forceinline__ bool sample_blocked_filtered(const DevCfg &c, const SM &S, const EBT &E, int i, double t, bool *sure) {
   int pn[3] = {0, 0, 0};
   bool ok = true, outside = false;
 #pragma unroll
   for (int ax = 0; ax < DIM; ax++) {
     double dy = S.Au[i * 3 + ax];
 #pragma unroll
-    for (int d = ORD - 2; d >= 0; d--) dy = __fma_rn(dy, t, S.Ap[d * 3 + ax]);
-    double w = __dsub_rn(__fma_rn(dy, t, S.y0[ax]), 0.5);
+    for (int d = ORD - 2; d >= 0; d--) dy = __fma_rn(dy, t, E.Ap[d * 3 + ax]);
+    double w = __dsub_rn(__fma_rn(dy, t, E.y0[ax]), 0.5);
     double wm = magic_add(w);
     ok = ok && (fabs(__dsub_rn(w, magic_rint(wm))) < 0.5 - c.fast_delta);
     pn[ax] = magic_int(wm);
@@ -432,22 +482,22 @@ __device__ __forceinline__ bool sample_blocked_filtered(const DevCfg &c, const S
 
 /* B2, per-control exact form: warps take controls round-robin, lanes take samples (trace kernel, and the search
  * kernel when the fast tables do not fit). */
-template <int DIM, int ORD, class SM>
-__device__ __forceinline__ void expand_b2_percontrol(const DevCfg &c, SM &S, int warp, int lane, int nwarps) {
+template <int DIM, int ORD, class SM, class EBT>
+__device__ __forceinline__ void expand_b2_percontrol(const DevCfg &c, const SM &S, EBT &E, int warp, int lane, int nwarps) {
   for (int i = warp; i < c.nU; i += nwarps) {
-    if (S.verdict[i] != 5) continue;
-    int n = S.nsamp[i];
-    int cnt = S.cnt[i];
+    if (E.verdict[i] != 5) continue;
+    int n = E.nsamp[i];
+    int cnt = E.cnt[i];
     const double *tt = c.ttab + c.toff[n];
     int first = 0x7fffffff;
     for (int base = 0; base < cnt; base += 32) {
       int k = base + lane;
       bool blocked = false;
-      if (k < cnt) blocked = sample_blocked_exact<DIM, ORD>(c, S, i, __ldg(&tt[k]), nullptr);
+      if (k < cnt) blocked = sample_blocked_exact<DIM, ORD>(c, S, E.st, i, __ldg(&tt[k]), nullptr);
       unsigned m = __ballot_sync(0xffffffffu, blocked);
       if (m) { first = base + __ffs(m) - 1; break; }
     }
-    if (lane == 0) S.first[i] = first;
+    if (lane == 0) E.first[i] = first;
   }
 }
 
@@ -541,7 +591,7 @@ __device__ __forceinline__ unsigned long long khash_of_ints(const int *ints) {
 /* Generic serial relaxation of successors [i0, i1) in control order (lane 0 of warp 0): re-probes the table in
  * global memory, so it is correct under every hazard (duplicate siblings, slot collisions).  gs:79-143. */
 template <int DIM, int ORD, class SM>
-__device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, HeapEnt *spill, Slot *table, NodeHot *hot,
+__device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, typename SM::EB &E, HeapEnt *spill, Slot *table, NodeHot *hot,
                                           unsigned char *rows, int i0, int i1, bool wide) {
   const HeapView<SM> H{S, spill, hot}; /* built here: a view whose address escapes would turn heap accesses generic */
   constexpr int NS = DIM * ORD;
@@ -550,25 +600,25 @@ __device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, HeapEnt *spill
   const int cn = S.cur_node;
   const double cg = S.cur_g;
   for (int idx = i0; idx < i1; idx++) {
-    int v = S.verdict[idx];
-    if (v == 5) v = (S.first[idx] == 0x7fffffff) ? 3 : 2;
+    int v = E.verdict[idx];
+    if (v == 5) v = (E.first[idx] == 0x7fffffff) ? 3 : 2;
     if (v < 3) continue;
-    const unsigned long long k0 = S.k0[idx], k1 = S.k1[idx];
+    const unsigned long long k0 = E.k0[idx], k1 = E.k1[idx];
     int slot; double gold = kInf, pgold = 0.0;
     int nid = table_find_from(table, S.tsize, table_hash(k0, k1), k0, k1, wide, rows, ROWB, &slot, &gold, &pgold);
     NodeHot hn;
     if (nid < 0) { /* gs:84-88 */
       nid = S.n_nodes++;
-      hn.g = kInf; hn.h = heuristic<DIM, ORD>(c, S, &S.es[idx * NS], k0, k1); hn.pg = 0.0; hn.heap_pos = -1; hn.action = -1;
+      hn.g = kInf; hn.h = heuristic<DIM, ORD>(c, S, &E.es[idx * NS], k0, k1); hn.pg = 0.0; hn.heap_pos = -1; hn.action = -1;
       hn.flags = 0; hn.pad0 = 0;
       RowHdr *rh = reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB);
       rh->k0 = k0; rh->k1 = k1; rh->parent = -1; rh->slot = slot; rh->pad = 0;
       double *rs = reinterpret_cast<double *>(rows + (size_t)nid * ROWB + sizeof(RowHdr));
-      for (int f = 0; f < NS; f++) rs[f] = S.es[idx * NS + f];
+      for (int f = 0; f < NS; f++) rs[f] = E.es[idx * NS + f];
       Slot sl; sl.k0 = k0; sl.k1lo = (unsigned int)k1; sl.node1 = (unsigned)(nid + 1); sl.g = kInf; sl.pg = 0.0;
       table[slot] = sl;
     } else hn = hot[nid];
-    S.nid[idx] = nid;
+    E.nid[idx] = nid;
     double tentative = dadd(cg, S.cost[idx]); /* gs:107 */
     if (tentative < hn.g) { /* gs:109-141 */
       double f = dadd(tentative, dmul(c.eps, hn.h));
@@ -601,41 +651,41 @@ __device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, HeapEnt *spill
 
 /* B2, flat form: thread `t` of `nthreads` sampling threads takes sample (t & 7) of granule (t >> 3) + k*(nthreads/8);
  * R granules are processed per pass with their loads issued together (independent dependency chains). */
-template <int DIM, int ORD, class SM>
-__device__ __forceinline__ void sample_granules(const DevCfg &c, SM &S, int t, int nthreads) {
+template <int DIM, int ORD, class SM, class EBT>
+__device__ __forceinline__ void sample_granules(const DevCfg &c, const SM &S, EBT &E, int t, int nthreads) {
   const int gstep = nthreads >> 3;
   const int sub = t & 7;
   constexpr int R = 4; /* granules in flight per thread */
-  for (int g0 = t >> 3; g0 < S.n_gran; g0 += R * gstep) {
+  for (int g0 = t >> 3; g0 < E.n_gran; g0 += R * gstep) {
     unsigned info[R];
     double st[R];
     bool act[R], blk[R], sure[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
       const int g = g0 + gstep * r;
-      const bool in = g < S.n_gran;
-      info[r] = in ? S.gl[g] : 0u;
+      const bool in = g < E.n_gran;
+      info[r] = in ? E.gl[g] : 0u;
       const int k = (int)((info[r] >> 8) & 0xffu) + sub;
       act[r] = in && k < (int)(info[r] >> 16);
-      st[r] = act[r] ? S.tts[(int)S.gl_t[in ? g : 0] + sub] : 0.0;
+      st[r] = act[r] ? S.tts[(int)E.gl_t[in ? g : 0] + sub] : 0.0;
     }
 #pragma unroll
     for (int r = 0; r < R; r++) {
       sure[r] = true;
-      blk[r] = act[r] && sample_blocked_filtered<DIM, ORD>(c, S, (int)(info[r] & 0xffu), st[r], &sure[r]);
+      blk[r] = act[r] && sample_blocked_filtered<DIM, ORD>(c, S, E, (int)(info[r] & 0xffu), st[r], &sure[r]);
     }
 #pragma unroll
     for (int r = 0; r < R; r++) {
       const int u = (int)(info[r] & 0xffu);
-      if (act[r] && !sure[r]) blk[r] = sample_blocked_exact<DIM, ORD>(c, S, u, st[r], nullptr);
-      if (blk[r]) atomicMin(&S.first[u], (int)((info[r] >> 8) & 0xffu) + sub);
+      if (act[r] && !sure[r]) blk[r] = sample_blocked_exact<DIM, ORD>(c, S, E.st, u, st[r], nullptr);
+      if (blk[r]) atomicMin(&E.first[u], (int)((info[r] >> 8) & 0xffu) + sub);
     }
   }
 }
 
 /* ---------------------------------------------------------------- the kernel */
 template <int DIM, int ORD, int NB>
-__global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ BatchArgs a) {
+__global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ BatchArgs a) {
   constexpr int NS = DIM * ORD;
   constexpr int NW = MPLB_NT / 32;
   using SM = PlanSmem<DIM, ORD, NB>;
@@ -688,7 +738,9 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
       const mplb_waypoint &st = a.starts[pid];
       const mplb_waypoint &gl = a.goals[pid];
       S.tsize = 1024; S.n_nodes = 0; S.n_heap = 0; S.pops = 0; S.n_closed = 0; S.status = -1;
-      S.key_bad = 0; S.n_samples = 0; S.n_valid = 0; S.n_before = 0; S.sd_pending = 0; S.pf_node = -1;
+      S.n_samples = 0; S.n_valid = 0; S.n_before = 0; S.sd_pending = 0; S.pf_node = -1;
+      S.cur_buf = 0;
+      for (int q = 0; q < SM::NBUF; q++) { S.eb[q].ready = 0; S.eb[q].node = -1; S.eb[q].key_bad = 0; }
       S.pop_hash = 0ull; S.closed_hash = 0ull; S.goal_hit = 0;
       for (int ax = 0; ax < 3; ax++) { S.goal_pos[ax] = gl.pos[ax]; S.goal_vel[ax] = gl.vel[ax]; S.goal_acc[ax] = gl.acc[ax]; }
       double s0[NS];
@@ -796,10 +848,21 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
       }
 
       /* ================= P1/P2 ================= */
-      /* per-control registers of warp 0 (probe results), one set per 32-control batch */
-      unsigned long long rk0[NB], rk1[NB];
+      const int cb = S.cur_buf; /* read once per iteration: the search warp flips it at the pop */
+      typename SM::EB &E = S.eb[cb];
+      const bool hit = (SM::NBUF > 1) && E.ready && (E.node == S.cur_node); /* B1 of this node was done one pop ahead */
+      if (!hit) { /* ---- P1 on the critical path: the search warp runs B1 for the current node */
+        if (warp == 0) {
+          if (lane < NS) { E.st[lane] = S.cur[lane]; E.ints[lane] = S.cur_ints[lane]; }
+          __syncwarp();
+          b1_warp<DIM, ORD, NB>(c, S, E, lane, fast);
+          if (lane == 0) { E.node = S.cur_node; E.ready = 1; }
+        }
+        if (warp != NW - 1) asm volatile("bar.sync 1, %0;" ::"n"(MPLB_NT - 32) : "memory"); /* B1 outputs visible to the sampling warps */
+      }
+      MPLB_TICK(0);
       if (warp == NW - 1) {
-        /* ---- heap warp: finish the previous pop's sift-down, then prefetch the new root's state row */
+        /* ---- heap warp: finish the previous pop's sift-down, prefetch the new root's state row ... */
         if (lane == 0) {
           if (S.sd_pending) { H.sift_down(S.n_heap, 0, S.sd_f, S.sd_g, S.sd_n); S.sd_pending = 0; }
           int pf = -1;
@@ -813,46 +876,24 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
           }
           S.pf_node = pf;
         }
-      } else {
-        if (warp == 0) {
-          /* ---- B1 + probe issue, batch by batch */
-          int gbase = 0;
+        __syncwarp();
+        asm volatile("bar.arrive 3, 64;" ::: "memory"); /* heap and prefetched row are ready for the search warp's P3 */
+        /* ---- ... and run B1 for that node into the other expansion record while the others work on the current one */
+        if (SM::NBUF > 1) {
+          typename SM::EB &E2 = S.eb[(cb ^ 1) & (SM::NBUF - 1)];
+          const int pf = S.pf_node;
+          if (pf >= 0) {
+            if (lane == 0) {
 #pragma unroll
-          for (int b = 0; b < NB; b++) {
-            const int i = b * 32 + lane;
-            int ng = 0;
-            rk0[b] = 0; rk1[b] = 0;
-            if (i < c.nU) {
-              expand_b1<DIM, ORD>(c, S, i, rk0[b], rk1[b]);
-              if (fast && S.verdict[i] == 5) ng = (S.cnt[i] + 7) >> 3;
+              for (int f = 0; f < NS; f++) E2.st[f] = S.pf_st[f];
+              unpack_ints<NS>(c, S.pf_k0, S.pf_k1, E2.ints);
             }
-            int incl = ng; /* warp scan of the granule counts */
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-            int excl = gbase + incl - ng;
-            for (int q = 0; q < ng; q++) {
-              S.gl[excl + q] = (unsigned)i | ((unsigned)(q * 8) << 8) | ((unsigned)S.cnt[i] << 16);
-              S.gl_t[excl + q] = (unsigned short)(S.toff_s[S.nsamp[i]] + q * 8);
-            }
-            gbase += __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            b1_warp<DIM, ORD, NB>(c, S, E2, lane, fast);
           }
-          if (lane == 0) { S.n_gran = gbase; S.n_before = S.n_nodes; MPLB_COUNT(2, gbase); MPLB_COUNT(0, fast ? 1 : 0); }
-        } else if (warp == 1) {
-          /* ---- per-pop sampling base of the fast path (cells): parent cell coordinate and lower coefficients */
-          if (fast && lane < DIM) {
-            const int ax = lane;
-            S.y0[ax] = dmul(dsub(S.cur[ax], c.origin[ax]), c.inv_res);
-            if (ORD >= 2) S.Ap[0 * 3 + ax] = dmul(S.cur[DIM + ax], c.inv_res);
-            if (ORD >= 3) S.Ap[1 * 3 + ax] = dmul(dmul(S.cur[2 * DIM + ax], 0.5), c.inv_res);
-            if (ORD >= 4) S.Ap[2 * 3 + ax] = dmul(ddiv(S.cur[3 * DIM + ax], 6.0), c.inv_res);
-          }
-        } else if (warp == 2) {
-          /* ---- goal test (gs:146) and parity hash of the current node */
-          bool gh = goal_test_warp<DIM, ORD>(c, S, S.cur, lane);
-          if (lane == 0) { S.goal_hit = gh ? 1 : 0; S.cur_kh = khash_of_ints<NS>(S.cur_ints); }
+          if (lane == 0) { E2.node = pf; E2.ready = (pf >= 0) ? 1 : 0; }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(MPLB_NT - 32) : "memory"); /* all but the heap warp: B1 outputs, sampling base, goal flag visible */
-        MPLB_TICK(0);
+      } else {
         if (warp == 0) {
           /* issue the table probes — WIN consecutive 32-byte slots per candidate, one HBM round trip in all but a
            * few per cent of the cases at load factor <= 1/4 — and compute h while they fly */
@@ -860,16 +901,17 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
 #pragma unroll
           for (int b = 0; b < NB; b++) {
             const int i = b * 32 + lane;
-            const bool probing = (i < c.nU) && (S.verdict[i] >= 4);
+            const bool probing = (i < c.nU) && (E.verdict[i] >= 4);
+            const unsigned long long k0 = probing ? E.k0[i] : 0ull, k1 = probing ? E.k1[i] : 0ull;
             const unsigned mask = (unsigned)S.tsize - 1u;
-            const unsigned h0 = table_hash(rk0[b], rk1[b]) & mask;
+            const unsigned h0 = table_hash(k0, k1) & mask;
             Slot sw[WIN];
             if (probing) {
 #pragma unroll
               for (int q = 0; q < WIN; q++) sw[q] = load_slot_cg(&table[(h0 + q) & mask]);
             }
             double hv = 0.0;
-            if (probing) hv = heuristic<DIM, ORD>(c, S, &S.es[i * NS], rk0[b], rk1[b]);
+            if (probing) hv = heuristic<DIM, ORD>(c, S, &E.es[i * NS], k0, k1);
             int nid = -1, slot = -1;
             double g = kInf, pg = 0.0;
             if (probing) {
@@ -878,40 +920,45 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
               for (int q = 0; q < WIN; q++) {
                 if (!done) {
                   if (sw[q].node1 == 0u) { slot = (int)((h0 + q) & mask); done = true; }
-                  else if (slot_matches(sw[q], rk0[b], rk1[b], wide, rows, ROWB)) {
+                  else if (slot_matches(sw[q], k0, k1, wide, rows, ROWB)) {
                     nid = (int)sw[q].node1 - 1; slot = (int)((h0 + q) & mask); g = sw[q].g; pg = sw[q].pg; done = true;
                   }
                 }
               }
-              if (!done) nid = table_find_from(table, S.tsize, h0 + WIN, rk0[b], rk1[b], wide, rows, ROWB, &slot, &g, &pg);
+              if (!done) nid = table_find_from(table, S.tsize, h0 + WIN, k0, k1, wide, rows, ROWB, &slot, &g, &pg);
             }
             if (i < c.nU) { S.p_nid[i] = nid; S.p_slot[i] = slot; S.p_g[i] = g; S.p_pg[i] = pg; S.p_h[i] = hv; }
           }
           MPLB_TICK(1);
-        }
-        /* ---- B2: all collision samples of all controls, flat over 8-sample granules (warps 1..NW-2) */
-        if (warp != 0) {
+        } else {
+          if (warp == 1) { /* ---- goal test (gs:146) and parity hash of the current node (needed only in P3) */
+            bool gh = goal_test_warp<DIM, ORD>(c, S, S.cur, lane);
+            if (lane == 0) { S.goal_hit = gh ? 1 : 0; S.cur_kh = khash_of_ints<NS>(S.cur_ints); }
+          }
+          /* ---- B2: all collision samples of all controls, flat over 8-sample granules (warps 1..NW-2) */
 #ifndef MPLB_EXPERIMENT_NOSAMPLE
-          if (fast) sample_granules<DIM, ORD>(c, S, tid - 32, MPLB_NT - 64);
+          if (fast) sample_granules<DIM, ORD>(c, S, E, tid - 32, MPLB_NT - 64);
           else
 #else
           if (!fast)
 #endif
-          expand_b2_percontrol<DIM, ORD>(c, S, warp - 1, lane, NW - 2);
+          expand_b2_percontrol<DIM, ORD>(c, S, E, warp - 1, lane, NW - 2);
         }
+        MPLB_TICK(2);
+        asm volatile("bar.sync 2, %0;" ::"n"(MPLB_NT - 32) : "memory"); /* probes + collision outcomes visible to the search warp */
+        MPLB_TICK(3);
       }
-      MPLB_TICK(2);
-      __syncthreads();
-      MPLB_TICK(3);
 
       /* ================= P3 (warp 0): relax (gs:79-143), terminate (gs:146-161), take the next node (gs:64-68) */
       if (warp == 0) {
 #if defined(MPLB_PHASE_TIMING) && MPLB_PHASE_TIMING == 2
         tlast2 = clock64();
 #endif
+        asm volatile("bar.sync 3, 64;" ::: "memory"); /* the heap warp has finished the sift-down and the root prefetch */
         const int cn = S.cur_node;
         const double cg = S.cur_g;
         if (lane == 0) { /* bookkeeping of the current pop */
+          S.n_before = S.n_nodes;
           unsigned long long kh = S.cur_kh;
           S.pop_hash = (S.pop_hash ^ kh) * 0x100000001B3ull;
           if (!S.cur_tag) { S.n_closed++; S.closed_hash += kh; }
@@ -921,11 +968,11 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
 #pragma unroll
         for (int b = 0; b < NB; b++) {
           const int i = b * 32 + lane;
-          int v = (i < c.nU) ? S.verdict[i] : 0;
+          int v = (i < c.nU) ? E.verdict[i] : 0;
           if (v == 5) {
-            int first = S.first[i];
+            int first = E.first[i];
             v = (first == 0x7fffffff) ? 3 : 2;
-            ns_acc += (v == 3) ? S.cnt[i] : first + 1;
+            ns_acc += (v == 3) ? E.cnt[i] : first + 1;
           }
           const bool valid = v >= 3;
           const int r_nid_b = (i < c.nU) ? S.p_nid[i] : -1;
@@ -933,7 +980,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
           const double r_g_b = (i < c.nU) ? S.p_g[i] : kInf;
           const double r_pg_b = (i < c.nU) ? S.p_pg[i] : 0.0;
           const double r_h_b = (i < c.nU) ? S.p_h[i] : 0.0;
-          const unsigned long long rk0_b = (i < c.nU) ? S.k0[i] : 0ull, rk1_b = (i < c.nU) ? S.k1[i] : 0ull;
+          const unsigned long long rk0_b = (i < c.nU) ? E.k0[i] : 0ull, rk1_b = (i < c.nU) ? E.k1[i] : 0ull;
           MPLB_TICK2(0);
           const unsigned vmask = __ballot_sync(0xffffffffu, valid);
           nv_acc += __popc(vmask);
@@ -953,12 +1000,12 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
             if (found) { unsigned m3 = __match_any_sync(fndm, r_nid_b); hazard = hazard || (__popc(m3) > 1); }
             if (NB > 1 && created_any && isnew) hazard = true; /* probe predates nodes created by earlier batches */
             if (NB > 1 && found) /* an earlier batch of this pop may already have relaxed the same node */
-              for (int q = 0; q < b * 32; q++) hazard = hazard || (S.nid[q] == r_nid_b);
+              for (int q = 0; q < b * 32; q++) hazard = hazard || (E.nid[q] == r_nid_b);
             hazard = __any_sync(0xffffffffu, hazard);
           }
           MPLB_TICK2(1);
           if (hazard) {
-            if (lane == 0) { MPLB_COUNT(3, 1); relax_serial<DIM, ORD>(c, S, spill, table, hot, rows, b * 32, min(c.nU, b * 32 + 32), wide); }
+            if (lane == 0) { MPLB_COUNT(3, 1); relax_serial<DIM, ORD>(c, S, E, spill, table, hot, rows, b * 32, min(c.nU, b * 32 + 32), wide); }
             __syncwarp();
             created_any = true;
             continue;
@@ -971,7 +1018,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
           if (isnew) nid = S.n_nodes + __popc(newm & lt_mask);
           const int n_new = __popc(newm);
           created_any = created_any || (n_new > 0);
-          if (valid) S.nid[i] = nid;
+          if (valid) E.nid[i] = nid;
           double hval = r_h_b;
           int fl = 0, hpos = -1;
           if (improve) { const NodeHot hn = load_hot_cg(&hot[nid]); hval = hn.h; fl = hn.flags; hpos = hn.heap_pos; } /* rare dependent load */
@@ -983,7 +1030,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
             rh->k0 = rk0_b; rh->k1 = rk1_b; rh->parent = cn; rh->slot = r_slot_b; rh->pad = 0;
             double *rs = reinterpret_cast<double *>(rows + (size_t)nid * ROWB + sizeof(RowHdr));
 #pragma unroll
-            for (int q = 0; q < NS; q++) rs[q] = S.es[i * NS + q];
+            for (int q = 0; q < NS; q++) rs[q] = E.es[i * NS + q];
             Slot sl; sl.k0 = rk0_b; sl.k1lo = (unsigned int)rk1_b; sl.node1 = (unsigned)(nid + 1); sl.g = tentative; sl.pg = cg;
             table[r_slot_b] = sl;
             NodeHot hn; hn.g = tentative; hn.h = hval; hn.pg = cg; hn.heap_pos = -1; hn.action = (short)i; hn.flags = 1; hn.pad0 = 0;
@@ -1036,7 +1083,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
           S.n_samples += ns_acc;
           S.n_valid += nv_acc;
           int status = -1;
-          if (S.key_bad) status = MPLB_PLAN_KEY_RANGE;
+          if (E.key_bad) status = MPLB_PLAN_KEY_RANGE;
           else if (S.goal_hit) status = MPLB_PLAN_OK;
           else if (c.max_num > 0 && S.pops >= c.max_num) status = MPLB_PLAN_MAX_EXPAND;
           else if (S.n_heap == 0) status = MPLB_PLAN_QUEUE_EMPTY;
@@ -1051,10 +1098,10 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
             unsigned long long k0, k1;
             if (nx >= S.n_before) { /* created in this expansion: forward its state from shared memory */
               int j = 0;
-              for (int q = 0; q < c.nU; q++) if (S.nid[q] == nx) { j = q; break; }
-              k0 = S.k0[j]; k1 = S.k1[j];
+              for (int q = 0; q < c.nU; q++) if (E.nid[q] == nx) { j = q; break; }
+              k0 = E.k0[j]; k1 = E.k1[j];
 #pragma unroll
-              for (int f = 0; f < NS; f++) S.cur[f] = S.es[j * NS + f];
+              for (int f = 0; f < NS; f++) S.cur[f] = E.es[j * NS + f];
             } else if (nx == S.pf_node) {
               k0 = S.pf_k0; k1 = S.pf_k1;
 #pragma unroll
@@ -1073,6 +1120,7 @@ __global__ void __launch_bounds__(MPLB_NT) astar_batch_kernel(const __grid_const
             hot[nx].flags = 3; /* iterationclosed = true (gs:68); a popped node is always opened */
             if (a.want_poplog && S.pops < a.cap) poplog[S.pops] = nx;
             S.pops++;
+            if (SM::NBUF > 1) S.cur_buf = cb ^ 1; /* the next pop's expansion record is the one the heap warp filled */
           }
         }
         MPLB_TICK(6);
@@ -1154,45 +1202,46 @@ __global__ void __launch_bounds__(MPLB_NT) expand_trace_kernel(const __grid_cons
     S.cost[i] = dadd(J, dmul(c.w, c.dt));
   }
   if (c.use_fast) for (int i = tid; i < MPLB_NCAP; i += MPLB_NT) S.tcnt_s[i] = (i <= c.n_hi) ? c.tcnt[i] : 0;
+  typename SM::EB &E = S.eb[0];
   for (int s = blockIdx.x; s < n_states; s += gridDim.x) {
     __syncthreads();
     if (tid == 0) {
       const mplb_waypoint &st = states[s];
       for (int ax = 0; ax < DIM; ax++) {
-        S.cur[ax] = st.pos[ax];
-        if (ORD >= 2) S.cur[DIM + ax] = st.vel[ax];
-        if (ORD >= 3) S.cur[2 * DIM + ax] = st.acc[ax];
-        if (ORD >= 4) S.cur[3 * DIM + ax] = st.jrk[ax];
+        E.st[ax] = st.pos[ax];
+        if (ORD >= 2) E.st[DIM + ax] = st.vel[ax];
+        if (ORD >= 3) E.st[2 * DIM + ax] = st.acc[ax];
+        if (ORD >= 4) E.st[3 * DIM + ax] = st.jrk[ax];
       }
-      lattice_ints<DIM, ORD>(S.cur, S.cur_ints);
-      S.key_bad = 0;
+      lattice_ints<DIM, ORD>(E.st, E.ints);
+      E.key_bad = 0;
     }
     __syncthreads();
-    for (int i = tid; i < c.nU; i += MPLB_NT) { unsigned long long k0, k1; expand_b1<DIM, ORD>(c, S, i, k0, k1); }
+    for (int i = tid; i < c.nU; i += MPLB_NT) expand_b1<DIM, ORD>(c, S, E, i);
     __syncthreads();
-    expand_b2_percontrol<DIM, ORD>(c, S, warp, lane, NW);
+    expand_b2_percontrol<DIM, ORD>(c, S, E, warp, lane, NW);
     __syncthreads();
     for (int i = tid; i < c.nU; i += MPLB_NT) {
       mplb_prim_trace r;
-      int v = S.verdict[i];
-      if (v == 5) v = (S.first[i] == 0x7fffffff) ? 3 : 2;
+      int v = E.verdict[i];
+      if (v == 5) v = (E.first[i] == 0x7fffffff) ? 3 : 2;
       r.verdict = v;
-      r.n = (v == 2 || v == 3) ? S.nsamp[i] : 0;
-      r.n_tested = (v == 3) ? S.cnt[i] : (v == 2 ? S.first[i] + 1 : 0);
+      r.n = (v == 2 || v == 3) ? E.nsamp[i] : 0;
+      r.n_tested = (v == 3) ? E.cnt[i] : (v == 2 ? E.first[i] + 1 : 0);
       r.block_idx = -1;
       if (v == 2) {
         int cell = -1;
-        sample_blocked_exact<DIM, ORD>(c, S, i, c.ttab[c.toff[S.nsamp[i]] + S.first[i]], &cell);
+        sample_blocked_exact<DIM, ORD>(c, S, E.st, i, c.ttab[c.toff[E.nsamp[i]] + E.first[i]], &cell);
         r.block_idx = cell;
       }
       r.cost = (v >= 3) ? S.cost[i] : (v == 2 ? __longlong_as_double(0x7ff0000000000000ll) : 0.0);
       for (int q = 0; q < 13; q++) r.succ[q] = 0.0;
       for (int ax = 0; ax < DIM; ax++) { /* tn carries every derivative (pr:321-331) */
-        Axis<ORD> A(&S.cur[ax], DIM, S.U[i * 3 + ax]);
+        Axis<ORD> A(&E.st[ax], DIM, S.U[i * 3 + ax]);
         r.succ[ax] = A.p(c.dt); r.succ[3 + ax] = A.v(c.dt); r.succ[6 + ax] = A.a(c.dt); r.succ[9 + ax] = A.j(c.dt);
       }
       int ints[NS];
-      lattice_ints<DIM, ORD>(&S.es[i * NS], ints);
+      lattice_ints<DIM, ORD>(&E.es[i * NS], ints);
       for (int q = 0; q < 16; q++) r.key[q] = 0;
       for (int f = 0; f < NS; f++) r.key[f] = ints[f];
       r.key[15] = NS;
