@@ -402,7 +402,7 @@ __device__ __forceinline__ void expand_b1(const DevCfg &c, const SM &S, EBT &E, 
 /* B1 for all controls of one node by ONE warp, plus the flat sample list (granules) and the sampling base.
  * E.st / E.ints must hold the node's state and lattice ints. */
 template <int DIM, int ORD, int NB, class SM, class EBT>
-__device__ __forceinline__ void b1_warp(const DevCfg &c, const SM &S, EBT &E, int lane, bool fast) {
+__device__ __noinline__ void b1_warp(const DevCfg &c, const SM &S, EBT &E, int lane, bool fast) {
   if (lane == 0) E.key_bad = 0;
   if (fast && lane < DIM) { /* sampling base (cells): parent cell coordinate and lower polynomial coefficients */
     const int ax = lane;
@@ -655,7 +655,7 @@ template <int DIM, int ORD, class SM, class EBT>
 __device__ __forceinline__ void sample_granules(const DevCfg &c, const SM &S, EBT &E, int t, int nthreads) {
   const int gstep = nthreads >> 3;
   const int sub = t & 7;
-  constexpr int R = 4; /* granules in flight per thread */
+  constexpr int R = 2; /* granules in flight per thread (4 doubled the code of the hot loop for no measurable gain) */
   for (int g0 = t >> 3; g0 < E.n_gran; g0 += R * gstep) {
     unsigned info[R];
     double st[R];

@@ -224,3 +224,23 @@ def test_jrk_125_controls_3d():
     for i in range(len(S)):
         assert_results_equal(rg[i], ro2[i], i)
     assert np.array_equal(ag, ao)
+
+
+@pytest.mark.parametrize("name,dim,ctrl_u", [("skir", 3, 1.0), ("corridor", 2, 0.5)])
+def test_large_batch_uses_longest_first_order(name, dim, ctrl_u):
+    """Batches larger than half the resident CTAs are pulled longest-first (free-space component labels + distance);
+    the order is a scheduling hint only, so every result must still equal the oracle's, in input order."""
+    m = maps.load_fixture(name)
+    U = maps.make_U(ctrl_u, 1, dim)
+    params = dict(v_max=2.0 if dim == 3 else 1.0, a_max=1.0, dt=1.0, max_num=150, tol_pos=0.5)
+    pl, op = make_pair(m, dim, params, U)
+    n = 700
+    S, G = maps.sample_queries(m, n, seed=11, min_dist=1.0)
+    sg, so = waypoint_pair(S, mp.ACC)
+    gg, go = waypoint_pair(G, mp.ACC)
+    rg, ag, _ = pl.plan_batch(sg, gg, max_seg=32)
+    ro, ao = op.plan_batch(so, go, nthreads=8, max_seg=32)
+    for i in range(n):
+        assert_results_equal(rg[i], ro[i], (name, i))
+    assert np.array_equal(ag, ao)
+    assert pl.last_batch_stats()["launches"] >= 3  # keys + order + search kernel
