@@ -110,13 +110,7 @@ struct BatchArgs {
 #ifdef MPLB_PHASE_TIMING
 #define MPLB_TICK(k) do { if (tid == 0) { long long t__ = clock64(); ph[k] += t__ - tlast; tlast = t__; } } while (0)
 #define MPLB_COUNT(k, v) atomicAdd(&S.dbg[k], (unsigned long long)(v))
-#if MPLB_PHASE_TIMING == 2
-#define MPLB_TICK2(k) do { if (tid == 0) { long long t__ = clock64(); S.dbg[k] += (unsigned long long)(t__ - tlast2); tlast2 = t__; } } while (0)
 #else
-#define MPLB_TICK2(k) do { } while (0)
-#endif
-#else
-#define MPLB_TICK2(k) do { } while (0)
 #define MPLB_COUNT(k, v) do { } while (0)
 #define MPLB_TICK(k) do { } while (0)
 #endif
@@ -818,7 +812,6 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
 #ifdef MPLB_PHASE_TIMING
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
-    long long tlast2 = tlast;
     if (tid < 8) S.dbg[tid] = 0;
 #endif
     /* ---------------- main loop (gs:63-162): S.cur* always holds the node popped last */
@@ -936,13 +929,8 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
             if (lane == 0) { S.goal_hit = gh ? 1 : 0; S.cur_kh = khash_of_ints<NS>(S.cur_ints); }
           }
           /* ---- B2: all collision samples of all controls, flat over 8-sample granules (warps 1..NW-2) */
-#ifndef MPLB_EXPERIMENT_NOSAMPLE
           if (fast) sample_granules<DIM, ORD>(c, S, E, tid - 32, MPLB_NT - 64);
-          else
-#else
-          if (!fast)
-#endif
-          expand_b2_percontrol<DIM, ORD>(c, S, E, warp - 1, lane, NW - 2);
+          else expand_b2_percontrol<DIM, ORD>(c, S, E, warp - 1, lane, NW - 2);
         }
         MPLB_TICK(2);
         asm volatile("bar.sync 2, %0;" ::"n"(MPLB_NT - 32) : "memory"); /* probes + collision outcomes visible to the search warp */
@@ -951,9 +939,6 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
 
       /* ================= P3 (warp 0): relax (gs:79-143), terminate (gs:146-161), take the next node (gs:64-68) */
       if (warp == 0) {
-#if defined(MPLB_PHASE_TIMING) && MPLB_PHASE_TIMING == 2
-        tlast2 = clock64();
-#endif
         asm volatile("bar.sync 3, 64;" ::: "memory"); /* the heap warp has finished the sift-down and the root prefetch */
         const int cn = S.cur_node;
         const double cg = S.cur_g;
@@ -981,7 +966,6 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
           const double r_pg_b = (i < c.nU) ? S.p_pg[i] : 0.0;
           const double r_h_b = (i < c.nU) ? S.p_h[i] : 0.0;
           const unsigned long long rk0_b = (i < c.nU) ? E.k0[i] : 0ull, rk1_b = (i < c.nU) ? E.k1[i] : 0ull;
-          MPLB_TICK2(0);
           const unsigned vmask = __ballot_sync(0xffffffffu, valid);
           nv_acc += __popc(vmask);
           if (vmask == 0u) continue;
@@ -1003,7 +987,6 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
               for (int q = 0; q < b * 32; q++) hazard = hazard || (E.nid[q] == r_nid_b);
             hazard = __any_sync(0xffffffffu, hazard);
           }
-          MPLB_TICK2(1);
           if (hazard) {
             if (lane == 0) { MPLB_COUNT(3, 1); relax_serial<DIM, ORD>(c, S, E, spill, table, hot, rows, b * 32, min(c.nU, b * 32 + 32), wide); }
             __syncwarp();
@@ -1023,7 +1006,6 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
           int fl = 0, hpos = -1;
           if (improve) { const NodeHot hn = load_hot_cg(&hot[nid]); hval = hn.h; fl = hn.flags; hpos = hn.heap_pos; } /* rare dependent load */
           const double f = dadd(tentative, dmul(c.eps, hval));
-          MPLB_TICK2(2);
           /* lane-parallel stores */
           if (isnew) { /* gs:84-88: the node's coord is this (first) discoverer's state */
             RowHdr *rh = reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB);
@@ -1047,7 +1029,6 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
             reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB)->parent = cn;
           }
           if (lane == 0) S.n_nodes += n_new;
-          MPLB_TICK2(3);
           MPLB_TICK(4);
           /* heap operations in control order (gs:129-141) */
           unsigned hm = __ballot_sync(0xffffffffu, isnew || improve);

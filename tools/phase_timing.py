@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
 """Diagnostics: build libmplb with -DMPLB_PHASE_TIMING into a separate .so, run the bench batch once and print
-the per-phase clock64() cycle shares of thread 0 (the serial chain of a plan).  Not part of the product."""
+the clock64() cycle accumulators of thread 0 (search warp).  The TOTAL cycles per pop is reliable; the per-phase
+split is only indicative (clock64 is not ordered with barriers) — use the barrier-stall samples of an ncu capture for
+phase durations (see profiles/README.md).  Not part of the product."""
 import ctypes as C
 import os
 import subprocess
@@ -42,8 +44,8 @@ ph = ph16[:, :8]
 dbg = ph16[:, 8:]
 print('dbg per pop', (dbg.sum(axis=0) / res['pops'].sum()).astype(int).tolist())
 print('counters per pop: fast_on %.3f samples %.1f granules %.1f hazards %.4f exact_samples %.3f' % tuple(dbg[:, k].sum() / res['pops'].sum() for k in (0, 1, 2, 3, 4)))
-names = ["P1 B1+scan+bar1", "P2 probe issue + h", "P2 probe resolve", "P2 barrier wait", "P3 relax: decide+stores",
-         "P3 relax: heap ops", "P3 terminate+pop", "loop top (sync+checks)"]
+names = ["P1 (miss path only) + bar1", "P2 probe issue + h + resolve", "P2 (unused)", "P2 wait at bar 2", "P3 relax: decide+stores",
+         "P3 relax: heap ops", "P3 terminate+pop", "loop top (barrier C + checks)"]
 pops = res["pops"].astype(np.float64)
 tot = ph.sum()
 print("total pops", int(pops.sum()), "cycles/pop (all plans)", tot / pops.sum())
