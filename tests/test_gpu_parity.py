@@ -244,3 +244,23 @@ def test_large_batch_uses_longest_first_order(name, dim, ctrl_u):
         assert_results_equal(rg[i], ro[i], (name, i))
     assert np.array_equal(ag, ao)
     assert pl.last_batch_stats()["launches"] >= 3  # keys + order + search kernel
+
+
+def test_synthetic_boxes_jrk125_batch():
+    """BASELINE configs[4] shape at test size: synthetic box map (seeded generator of SURVEY.md section 8d), jerk control,
+    |U| = 125, dt = 0.5, max_num bound.  Every plan here stops at MaxExpandStep with > 32 768 nodes, so the whole batch
+    goes through the second arena tier; counters and the pop-order hash must still match the oracle."""
+    m = maps.synthetic_boxes(n=96, occupied_frac=0.2, seed=1, res=0.1)
+    U = maps.make_U(2.0, 2, 3)
+    params = dict(v_max=3.0, a_max=2.0, dt=0.5, max_num=300, tol_pos=0.5)
+    pl, op = make_pair(m, 3, params, U)
+    n = 16
+    S, G = maps.sample_queries(m, n, seed=2, min_dist=3.0, max_dist=9.0)
+    sg, so = waypoint_pair(S, mp.JRK)
+    gg, go = waypoint_pair(G, mp.JRK)
+    rg, ag, _ = pl.plan_batch(sg, gg, max_seg=16)
+    ro, ao = op.plan_batch(so, go, nthreads=8, max_seg=16)
+    assert set(np.unique(ro["status"])) == {2} and ro["n_nodes"].max() > 32768
+    for i in range(n):
+        assert_results_equal(rg[i], ro[i], i)
+    assert pl.last_batch_stats()["tiers"] == 2
