@@ -16,7 +16,9 @@
 
 namespace mplb {
 
-#define MPLB_NT 256   /* threads per CTA: one CTA owns one plan (warp 0 search, warps 1-6 sampling, warp 7 heap) */
+#ifndef MPLB_NT
+#define MPLB_NT 256   /* threads per CTA: one CTA owns one plan (warp 0 search, warps 1..NW-2 sampling, last warp heap) */
+#endif
 #define MPLB_MAXU 128 /* max |U| */
 #ifndef MPLB_MIN_CTAS
 #define MPLB_MIN_CTAS 3 /* resident CTAs per SM the search kernel is compiled for (4 caps registers at 64 and spills: measured no faster) */

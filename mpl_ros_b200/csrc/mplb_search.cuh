@@ -39,6 +39,23 @@
 
 namespace mplb {
 
+/* tuning knobs (measured on the bench workload with tools/phase_timing.py, cycles per pop) */
+#ifndef MPLB_R
+#define MPLB_R 1 /* collision granules in flight per sampling thread: 1 -> 10.2k, 2 -> 10.9k, 4 -> 12.2k cycles per pop */
+#endif
+#ifndef MPLB_WIN
+#define MPLB_WIN 2 /* table slots fetched per probe: 2 -> 9.9k, 4 -> 10.9k cycles per pop (load factor <= 1/4) */
+#endif
+#ifndef MPLB_HCAP
+#define MPLB_HCAP 1536 /* heap entries kept in shared memory (|U| <= 32 instantiations) */
+#endif
+#ifndef MPLB_B1_INLINE
+#define MPLB_B1_INLINE __forceinline__ /* __noinline__ costs ~2k cycles per pop */
+#endif
+#ifndef MPLB_SIFTUP_INLINE
+#define MPLB_SIFTUP_INLINE __forceinline__ /* __noinline__ costs ~1k cycles per pop */
+#endif
+
 #define MPLB_INTERNAL_OVERFLOW 100 /* arena too small: host retries the plan in a larger tier */
 #define MPLB_INTERNAL_BADCTRL 9
 #define MPLB_TT_CAP 1024           /* float sample times kept in shared memory */
@@ -124,7 +141,7 @@ struct ExpBuf {
   static constexpr int NS = DIM * ORD;
   static constexpr int GCAP = MAXU * 8; /* 8-sample granules */
   double st[NS];     /* state of the expanded node */
-  int ints[NS];      /* its lattice ints */
+  unsigned long long pk0, pk1; /* its packed lattice key (a successor with the same key is the self-loop of em:158) */
   int node, ready, key_bad, n_gran;
   double y0[3];      /* filtered sampling: cell coordinate of the parent and lower coefficients, in cells */
   double Ap[3 * 3];
@@ -147,13 +164,13 @@ struct PlanSmem {
   typedef ExpBuf<DIM, ORD, MAXU> EB;
   EB eb[NBUF];
   int cur_buf;
-  static constexpr int HCAP = (NB == 1) ? 1536 : 1024; /* heap entries kept in shared memory */
+  static constexpr int HCAP = (NB == 1) ? MPLB_HCAP : 1024; /* heap entries kept in shared memory */
   /* heap top (SoA) */
   double hf[HCAP], hg[HCAP];
   int hn[HCAP];
   /* current node */
   double cur[NS];
-  int cur_ints[NS];
+  unsigned long long cur_k0, cur_k1; /* packed lattice key of the current node */
   double cur_g;
   unsigned long long cur_kh;
   int cur_node, cur_tag, goal_hit;
@@ -215,7 +232,7 @@ struct HeapView {
     set(pos, f, g, n);
   }
   /* warp-cooperative sift up: lane k examines ancestor k+1; identical result to the serial loop */
-  __device__ __forceinline__ void sift_up_warp(int pos, double f, double g, int n, int lane) const {
+  __device__ MPLB_SIFTUP_INLINE void sift_up_warp(int pos, double f, double g, int n, int lane) const {
     int p1 = pos + 1;
     int depth = 31 - __clz(p1);            /* number of ancestors */
     int my = (p1 >> (lane + 1)) - 1;       /* ancestor lane+1 */
@@ -368,13 +385,13 @@ __device__ __forceinline__ void expand_b1(const DevCfg &c, const SM &S, EBT &E, 
     for (int d = 0; d < ORD; d++)
       ints[ax * ORD + d] = (d == 0) ? lattice_int(es[ax], 0.01, 100.0) : lattice_int(es[d * DIM + ax], 0.1, 10.0);
   }
-  bool self = true;
-#pragma unroll
-  for (int f = 0; f < NS; f++) self = self && (ints[f] == E.ints[f]);
 #pragma unroll
   for (int f = 0; f < NS; f++) E.es[i * NS + f] = es[f];
   unsigned long long k0, k1;
   bool key_ok = pack_key_nohash<DIM, ORD>(c, ints, k0, k1);
+  /* tn == curr (em:158, wp:132-135): equal lattice tuples <=> equal packed keys (the packing is injective inside the
+   * key range; a tuple outside it is reported through key_bad before it can matter) */
+  const bool self = key_ok && (k0 == E.pk0) && (k1 == E.pk1);
   E.k0[i] = k0; E.k1[i] = k1;
   E.first[i] = 0x7fffffff;
   int verdict, n = 0, cnt = 0;
@@ -394,9 +411,9 @@ __device__ __forceinline__ void expand_b1(const DevCfg &c, const SM &S, EBT &E, 
 }
 
 /* B1 for all controls of one node by ONE warp, plus the flat sample list (granules) and the sampling base.
- * E.st / E.ints must hold the node's state and lattice ints. */
+ * E.st / E.pk0 / E.pk1 must hold the node's state and packed lattice key. */
 template <int DIM, int ORD, int NB, class SM, class EBT>
-__device__ __noinline__ void b1_warp(const DevCfg &c, const SM &S, EBT &E, int lane, bool fast) {
+__device__ MPLB_B1_INLINE void b1_warp(const DevCfg &c, const SM &S, EBT &E, int lane, bool fast) {
   if (lane == 0) E.key_bad = 0;
   if (fast && lane < DIM) { /* sampling base (cells): parent cell coordinate and lower polynomial coefficients */
     const int ax = lane;
@@ -649,7 +666,7 @@ template <int DIM, int ORD, class SM, class EBT>
 __device__ __forceinline__ void sample_granules(const DevCfg &c, const SM &S, EBT &E, int t, int nthreads) {
   const int gstep = nthreads >> 3;
   const int sub = t & 7;
-  constexpr int R = 2; /* granules in flight per thread (4 doubled the code of the hot loop for no measurable gain) */
+  constexpr int R = MPLB_R; /* granules in flight per thread */
   for (int g0 = t >> 3; g0 < E.n_gran; g0 += R * gstep) {
     unsigned info[R];
     double st[R];
@@ -801,7 +818,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
         for (int f = 0; f < NS; f++) rs[f] = S.cur[f];
         S.n_nodes = 1; S.n_heap = 0;
         S.cur_node = 0; S.cur_g = 0.0; S.cur_tag = 0;
-        for (int f = 0; f < NS; f++) S.cur_ints[f] = ints[f];
+        S.cur_k0 = k0; S.cur_k1 = k1;
         S.pop_hash = 0xCBF29CE484222325ull;
         if (a.want_poplog) poplog[0] = 0;
         S.pops = 1;
@@ -846,7 +863,8 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
       const bool hit = (SM::NBUF > 1) && E.ready && (E.node == S.cur_node); /* B1 of this node was done one pop ahead */
       if (!hit) { /* ---- P1 on the critical path: the search warp runs B1 for the current node */
         if (warp == 0) {
-          if (lane < NS) { E.st[lane] = S.cur[lane]; E.ints[lane] = S.cur_ints[lane]; }
+          if (lane < NS) E.st[lane] = S.cur[lane];
+          if (lane == 0) { E.pk0 = S.cur_k0; E.pk1 = S.cur_k1; }
           __syncwarp();
           b1_warp<DIM, ORD, NB>(c, S, E, lane, fast);
           if (lane == 0) { E.node = S.cur_node; E.ready = 1; }
@@ -879,7 +897,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
             if (lane == 0) {
 #pragma unroll
               for (int f = 0; f < NS; f++) E2.st[f] = S.pf_st[f];
-              unpack_ints<NS>(c, S.pf_k0, S.pf_k1, E2.ints);
+              E2.pk0 = S.pf_k0; E2.pk1 = S.pf_k1;
             }
             __syncwarp();
             b1_warp<DIM, ORD, NB>(c, S, E2, lane, fast);
@@ -890,7 +908,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
         if (warp == 0) {
           /* issue the table probes — WIN consecutive 32-byte slots per candidate, one HBM round trip in all but a
            * few per cent of the cases at load factor <= 1/4 — and compute h while they fly */
-          constexpr int WIN = (NB == 1) ? 4 : 2;
+          constexpr int WIN = (NB == 1) ? MPLB_WIN : 2;
 #pragma unroll
           for (int b = 0; b < NB; b++) {
             const int i = b * 32 + lane;
@@ -926,7 +944,11 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
         } else {
           if (warp == 1) { /* ---- goal test (gs:146) and parity hash of the current node (needed only in P3) */
             bool gh = goal_test_warp<DIM, ORD>(c, S, S.cur, lane);
-            if (lane == 0) { S.goal_hit = gh ? 1 : 0; S.cur_kh = khash_of_ints<NS>(S.cur_ints); }
+            if (lane == 0) { /* parity hash of the lattice ints (off the serial chain) */
+              int ints[NS];
+              unpack_ints<NS>(c, S.cur_k0, S.cur_k1, ints);
+              S.goal_hit = gh ? 1 : 0; S.cur_kh = khash_of_ints<NS>(ints);
+            }
           }
           /* ---- B2: all collision samples of all controls, flat over 8-sample granules (warps 1..NW-2) */
           if (fast) sample_granules<DIM, ORD>(c, S, E, tid - 32, MPLB_NT - 64);
@@ -1094,7 +1116,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
 #pragma unroll
               for (int f = 0; f < NS; f++) S.cur[f] = rs[f];
             }
-            unpack_ints<NS>(c, k0, k1, S.cur_ints);
+            S.cur_k0 = k0; S.cur_k1 = k1;
             S.cur_node = nx;
             S.cur_g = topg;
             S.cur_tag = (tagged & 0x80000000) ? 1 : 0;
@@ -1194,7 +1216,9 @@ __global__ void __launch_bounds__(MPLB_NT) expand_trace_kernel(const __grid_cons
         if (ORD >= 3) E.st[2 * DIM + ax] = st.acc[ax];
         if (ORD >= 4) E.st[3 * DIM + ax] = st.jrk[ax];
       }
-      lattice_ints<DIM, ORD>(E.st, E.ints);
+      int ints0[NS];
+      lattice_ints<DIM, ORD>(E.st, ints0);
+      if (!pack_key_nohash<DIM, ORD>(c, ints0, E.pk0, E.pk1)) { E.pk0 = ~0ull; E.pk1 = ~0ull; } /* out-of-range state: nothing is its self-loop */
       E.key_bad = 0;
     }
     __syncthreads();

@@ -14,9 +14,9 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 from mpl_ros_b200 import build as B  # noqa: E402
 
-out = os.path.join(ROOT, "mpl_ros_b200", "libmplb_prof.so")
+out = os.path.join(ROOT, "mpl_ros_b200", os.environ.get("MPLB_PROF_SO", "libmplb_prof.so"))
 if "--build-only" in sys.argv or not os.path.exists(out):
-    subprocess.check_call([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")] + B.NVCC_FLAGS + ["-DMPLB_PHASE_TIMING=" + os.environ.get("MPLB_PT", "1"), "-o", out, B.SRC])
+    subprocess.check_call([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")] + B.NVCC_FLAGS + ["-DMPLB_PHASE_TIMING=" + os.environ.get("MPLB_PT", "1")] + os.environ.get("MPLB_DEFS", "").split() + ["-o", out, B.SRC])
     if "--build-only" in sys.argv:
         sys.exit(0)
 from mpl_ros_b200 import _lib  # noqa: E402
