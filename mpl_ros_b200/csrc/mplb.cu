@@ -250,8 +250,8 @@ struct Layout {
 
 Layout make_layout(int cap, int ns, int nU) {
   Layout L;
-  int ts = 1024;
-  while ((long long)ts < 4ll * (cap + nU)) ts <<= 1;
+  int ts = MPLB_TINIT;
+  while ((long long)ts < (long long)MPLB_LOAD_INV * (cap + nU)) ts <<= 1;
   L.tsize_max = ts;
   size_t o = 0;
   L.row_bytes = (sizeof(RowHdr) + (size_t)ns * sizeof(double) + 15) & ~(size_t)15;

@@ -46,6 +46,12 @@ namespace mplb {
 #ifndef MPLB_WIN
 #define MPLB_WIN 2 /* table slots fetched per probe: 2 -> 9.9k, 4 -> 10.9k cycles per pop (load factor <= 1/4) */
 #endif
+#ifndef MPLB_LOAD_INV
+#define MPLB_LOAD_INV 4 /* table load factor bound 1/4 */
+#endif
+#ifndef MPLB_TINIT
+#define MPLB_TINIT 1024 /* initial table slots (<= smallest tsize_max the host allocates) */
+#endif
 #ifndef MPLB_HCAP
 #define MPLB_HCAP 1536 /* heap entries kept in shared memory (|U| <= 32 instantiations) */
 #endif
@@ -743,12 +749,12 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
     /* ---------------- per-plan init (pb:275-306, gs:44-60) */
     {
       unsigned long long *t64 = reinterpret_cast<unsigned long long *>(table);
-      for (int i = tid; i < 4 * 1024; i += MPLB_NT) t64[i] = 0ull;
+      for (int i = tid; i < 4 * MPLB_TINIT; i += MPLB_NT) t64[i] = 0ull;
     }
     if (tid == 0) {
       const mplb_waypoint &st = a.starts[pid];
       const mplb_waypoint &gl = a.goals[pid];
-      S.tsize = 1024; S.n_nodes = 0; S.n_heap = 0; S.pops = 0; S.n_closed = 0; S.status = -1;
+      S.tsize = MPLB_TINIT; S.n_nodes = 0; S.n_heap = 0; S.pops = 0; S.n_closed = 0; S.status = -1;
       S.n_samples = 0; S.n_valid = 0; S.n_before = 0; S.sd_pending = 0; S.pf_node = -1;
       S.cur_buf = 0;
       for (int q = 0; q < SM::NBUF; q++) { S.eb[q].ready = 0; S.eb[q].node = -1; S.eb[q].key_bad = 0; }
@@ -841,9 +847,9 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
         __syncthreads();
         break;
       }
-      if ((S.n_nodes + c.nU) * 4 > S.tsize) { /* keep the load factor <= 1/4: grow in place and re-insert every node */
+      if ((S.n_nodes + c.nU) * MPLB_LOAD_INV > S.tsize) { /* keep the load factor <= 1/MPLB_LOAD_INV: grow in place and re-insert every node */
         int nt = S.tsize;
-        while ((S.n_nodes + c.nU) * 4 > nt) nt <<= 1;
+        while ((S.n_nodes + c.nU) * MPLB_LOAD_INV > nt) nt <<= 1;
         __syncthreads();
         if (nt > a.tsize_max) { if (tid == 0) S.status = MPLB_INTERNAL_OVERFLOW; __syncthreads(); break; }
         unsigned long long *t64 = reinterpret_cast<unsigned long long *>(table);
