@@ -203,6 +203,8 @@ struct mplb_planner {
   int max_num = -1;
   double mem_fraction = 0.6;
   int max_slots = 0; /* 0 = as many CTAs as are resident */
+  int resident_sig = -1, resident_cached = 0;
+  size_t budget_bytes = 0; /* arena budget, measured at the first batch (reset by MPLB_MEM_FRACTION) */
   std::vector<double> U; /* nU x 3 */
   int nU = 0;
 
@@ -471,14 +473,25 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
   CUDA_TRY(p->d_work.reserve((size_t)n));
   if (retain) CUDA_TRY(p->d_slot.reserve((size_t)n));
 
-  int resident = 0;
-#define RES_CALL(D, O, M) resident = resident_ctas<D, O, M>(p->device)
-  DISPATCH(c.dim, c.ord, c.nU, RES_CALL);
+  /* resident CTAs of this kernel instantiation and the memory budget are looked up once per configuration: both
+   * calls cost on the order of a millisecond, comparable to a small batch */
+  const int cfg_sig = c.dim * 100 + c.ord * 10 + (c.nU <= 32 ? 1 : 4);
+  if (p->resident_sig != cfg_sig) {
+    int r = 0;
+#define RES_CALL(D, O, M) r = resident_ctas<D, O, M>(p->device)
+    DISPATCH(c.dim, c.ord, c.nU, RES_CALL);
+    p->resident_cached = r;
+    p->resident_sig = cfg_sig;
+  }
+  const int resident = p->resident_cached;
   if (resident <= 0) return fail(MPLB_ERR_CUDA, "no resident CTA for the search kernel (is this an sm_100 device?)");
 
-  size_t free_b = 0, total_b = 0;
-  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-  size_t budget = (size_t)((double)(free_b + p->arena.n) * p->mem_fraction);
+  if (p->budget_bytes == 0) {
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    p->budget_bytes = (size_t)((double)(free_b + p->arena.n) * p->mem_fraction);
+  }
+  const size_t budget = p->budget_bytes;
 
   int n_work = n;
   bool identity = true;
@@ -785,6 +798,7 @@ int mplb_planner_set_param(mplb_planner *p, int key, double v) {
     case MPLB_MEM_FRACTION:
       if (!(v > 0 && v <= 0.95)) return fail(MPLB_ERR_ARG, "mem fraction must be in (0, 0.95]");
       p->mem_fraction = v;
+      p->budget_bytes = 0;
       break;
     case MPLB_MAX_SLOTS: p->max_slots = (int)v; break;
     default: return fail(MPLB_ERR_ARG, "unknown parameter key");
