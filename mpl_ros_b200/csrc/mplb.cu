@@ -496,6 +496,10 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
   int n_work = n;
   bool identity = true;
   int cap = 32768;
+  if (c.max_num > 0) { /* MaxExpandStep bounds the node count by max_num * |U|: start in the tier that is likely to fit */
+    long long est = (long long)c.max_num * c.nU + c.nU + 64;
+    while (cap < est && cap < 262144) cap *= 8;
+  }
   p->last_launches = 0; p->last_tiers = 0;
   bool ev0_done = false;
   if (n > resident / 2 && n <= 8192) { /* longest-first order (scheduling only): see k_plan_keys */

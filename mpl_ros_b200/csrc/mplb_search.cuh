@@ -636,6 +636,7 @@ __device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, typename SM::E
       table[slot] = sl;
     } else hn = hot[nid];
     E.nid[idx] = nid;
+    S.p_slot[idx] = slot; /* later batches of this pop test their empty slots against it */
     double tentative = dadd(cg, S.cost[idx]); /* gs:107 */
     if (tentative < hn.g) { /* gs:109-141 */
       double f = dadd(tentative, dmul(c.eps, hn.h));
@@ -977,7 +978,6 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
           if (!S.cur_tag) { S.n_closed++; S.closed_hash += kh; }
         }
         int ns_acc = 0, nv_acc = 0;
-        bool created_any = false;
 #pragma unroll
         for (int b = 0; b < NB; b++) {
           const int i = b * 32 + lane;
@@ -1010,15 +1010,18 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
               hazard = (__popc(m1) > 1) || (__popc(m2) > 1);
             }
             if (found) { unsigned m3 = __match_any_sync(fndm, r_nid_b); hazard = hazard || (__popc(m3) > 1); }
-            if (NB > 1 && created_any && isnew) hazard = true; /* probe predates nodes created by earlier batches */
-            if (NB > 1 && found) /* an earlier batch of this pop may already have relaxed the same node */
-              for (int q = 0; q < b * 32; q++) hazard = hazard || (E.nid[q] == r_nid_b);
+            if (NB > 1 && b > 0) { /* the probes predate everything earlier batches of this pop did */
+              if (found) /* an earlier batch may already have relaxed the same node */
+                for (int q = 0; q < b * 32; q++) hazard = hazard || (E.nid[q] == r_nid_b);
+              if (isnew) /* an earlier batch may have created this key, or taken this empty slot: both show as the same slot
+                            (equal keys share the probe sequence, hence its first empty slot) */
+                for (int q = 0; q < b * 32; q++) hazard = hazard || (E.nid[q] >= S.n_before && S.p_slot[q] == r_slot_b);
+            }
             hazard = __any_sync(0xffffffffu, hazard);
           }
           if (hazard) {
             if (lane == 0) { MPLB_COUNT(3, 1); relax_serial<DIM, ORD>(c, S, E, spill, table, hot, rows, b * 32, min(c.nU, b * 32 + 32), wide); }
             __syncwarp();
-            created_any = true;
             continue;
           }
           const double tentative = dadd(cg, valid ? S.cost[i] : 0.0); /* gs:107 */
@@ -1028,7 +1031,6 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
           int nid = r_nid_b;
           if (isnew) nid = S.n_nodes + __popc(newm & lt_mask);
           const int n_new = __popc(newm);
-          created_any = created_any || (n_new > 0);
           if (valid) E.nid[i] = nid;
           double hval = r_h_b;
           int fl = 0, hpos = -1;

