@@ -71,6 +71,10 @@ typedef Vecf<2> Vec2f;
 typedef Vecf<3> Vec3f;
 typedef Veci<2> Vec2i;
 typedef Veci<3> Vec3i;
+typedef vec_Vecf<2> vec_Vec2f; /* data_type.h:89-95 */
+typedef vec_Vecf<3> vec_Vec3f;
+typedef vec_Veci<2> vec_Vec2i;
+typedef vec_Veci<3> vec_Vec3i;
 
 namespace Control { /* control.h:10-20 */
 enum Control { NONE = 0, VEL = 0b00001, ACC = 0b00011, JRK = 0b00111, SNP = 0b01111,
@@ -341,6 +345,69 @@ class MapPlanner {
   const mplb_result &result() const { return last_; }
   mplb_planner *handle() const { return h_; }
 
+  /* ---- cost shaping: search region + potential map (map_planner.h:27-54,77-87; env_map.h:104-128) */
+  void setSearchRadius(const Vecf<Dim> &radius) { search_radius_ = radius; }            /* map_planner.cpp:41-43 */
+  void setPotentialRadius(const Vecf<Dim> &radius) { potential_radius_ = radius; }      /* map_planner.cpp:20-23 */
+  void setPotentialMapRange(const Vecf<Dim> &range) { potential_map_range_ = range; }   /* map_planner.cpp:25-28 */
+  void setPotentialWeight(decimal_t w) { set(MPLB_POTENTIAL_WEIGHT, w); }               /* map_planner.cpp:30-33 */
+  void setGradientWeight(decimal_t w) { set(MPLB_GRADIENT_WEIGHT, w); }                 /* map_planner.cpp:35-38 */
+  void setSearchRegion(const vec_Vecf<Dim> &path, bool dense = false) {                 /* map_planner.cpp:46-95 */
+    std::vector<double> flat(path.size() * 3, 0.0);
+    for (size_t i = 0; i < path.size(); i++) for (int k = 0; k < Dim; k++) flat[i * 3 + k] = path[i](k);
+    double r[3] = {0, 0, 0};
+    for (int k = 0; k < Dim; k++) r[k] = search_radius_(k);
+    if (h_ && mplb_planner_set_search_region_path(h_, flat.data(), (int)path.size(), dense ? 1 : 0, r) != MPLB_OK) report();
+  }
+  vec_Vecf<Dim> getSearchRegion() const {                                               /* map_planner.cpp:97-122 */
+    vec_Vecf<Dim> pts;
+    if (!h_ || !map_util_) return pts;
+    const int64_t n = mplb_planner_get_search_region(h_, nullptr, 0);
+    if (n <= 0) return pts;
+    std::vector<uint8_t> in_region((size_t)n);
+    mplb_planner_get_search_region(h_, in_region.data(), in_region.size());
+    const Veci<Dim> dim = map_util_->getDim();
+    Veci<Dim> c;
+    const int nz = Dim == 3 ? dim(Dim - 1) : 1;
+    for (int x = 0; x < dim(0); x++)
+      for (int y = 0; y < dim(1); y++)
+        for (int z = 0; z < nz; z++) {
+          c(0) = x; c(1) = y;
+          if (Dim == 3) c(Dim - 1) = z;
+          if (in_region[(size_t)x + (size_t)dim(0) * y + (size_t)dim(0) * dim(1) * z]) pts.push_back(map_util_->intToFloat(c));
+        }
+    return pts;
+  }
+  void updatePotentialMap(const Vecf<Dim> &pos) {                                       /* map_planner.cpp:327-391 */
+    double p3[3] = {0, 0, 0}, r[3] = {0, 0, 0}, g[3] = {0, 0, 0};
+    for (int k = 0; k < Dim; k++) { p3[k] = pos(k); r[k] = potential_radius_(k); g[k] = potential_map_range_(k); }
+    if (h_ && mplb_planner_update_potential_map(h_, p3, r, g, pow_) != MPLB_OK) report();
+  }
+  bool iterativePlan(const Coord &start, const Coord &goal, const Trajectory<Dim> &raw_traj, int max_num) { /* map_planner.cpp:394-434 */
+    const bool verbose = planner_verbose_;
+    planner_verbose_ = false;
+    traj_ = raw_traj;
+    decimal_t prev_traj_cost = 0;
+    int cnt = 0;
+    while (cnt < max_num) {
+      cnt++;
+      vec_Vecf<Dim> path;
+      for (const auto &w : traj_.getWaypoints()) path.push_back(w.pos);
+      setSearchRegion(path, false);
+      if (!plan(start, goal)) {
+        if (verbose) std::printf("[MapPlanner] fails the [%d] plan!\n", cnt);
+        planner_verbose_ = verbose;
+        return false;
+      }
+      if (prev_traj_cost == traj_cost_) {
+        if (verbose) std::printf("[MapPlanner] Converged after %d iterations! Trajectory cost: %f\n", cnt, traj_cost_);
+        break;
+      }
+      prev_traj_cost = traj_cost_;
+    }
+    planner_verbose_ = verbose;
+    return true;
+  }
+
  protected:
   void set(int key, double v) { if (h_ && mplb_planner_set_param(h_, key, v) != MPLB_OK) report(); }
   void report() const { if (planner_verbose_) std::printf("[MapPlanner] %s\n", mplb_last_error()); }
@@ -379,6 +446,9 @@ class MapPlanner {
   mplb_result last_{};
   bool initialized_ = false;
   bool planner_verbose_;
+  Vecf<Dim> search_radius_ = zero_vec(), potential_radius_ = zero_vec(), potential_map_range_ = zero_vec(); /* map_planner.h:106-111 */
+  decimal_t pow_ = 1.0;                                                                                     /* map_planner.h:113 */
+  static Vecf<Dim> zero_vec() { Vecf<Dim> v; for (int k = 0; k < Dim; k++) v(k) = 0; return v; }
 };
 typedef MapPlanner<2> OccMapPlanner;   /* map_planner.h:122 */
 typedef MapPlanner<3> VoxelMapPlanner; /* map_planner.h:125 */

@@ -131,12 +131,33 @@ enum mplb_param {
   MPLB_TOL_VEL = 9,
   MPLB_TOL_ACC = 10,
   MPLB_T_MAX = 11,  /* setTmax   :203 (accepted, ignored exactly like env_map::is_goal does, env_map.h:25-45) */
+  MPLB_POTENTIAL_WEIGHT = 12, /* setPotentialWeight map_planner.cpp:30-33, default 0.1 (env_map.h:196) */
+  MPLB_GRADIENT_WEIGHT = 13,  /* setGradientWeight  map_planner.cpp:35-38, default 0.0 (env_map.h:197) */
   MPLB_MEM_FRACTION = 100, /* fraction of free device memory the search arenas may take (default 0.6) */
   MPLB_MAX_SLOTS = 101     /* tuning: cap on concurrently resident plans (CTAs); 0 = all resident CTAs */
 };
 int mplb_planner_set_param(mplb_planner *p, int key, double value);
 /* setU (planner_base.h:246): n rows of udim (= Dim) doubles; the row index is the action id. */
 int mplb_planner_set_controls(mplb_planner *p, const double *U, int n, int udim);
+
+/* ---- cost shaping of env_map: search region and potential map, env_map.h:104-128.
+ * Both are per-planner state like ENV_->search_region_ / potential_map_ and stay set until replaced or cleared.
+ * Shaped plans need |U| <= 32 and a map that was scrubbed of unknown cells or not (either works). */
+/* env_base::set_search_region (env_base.h:301-303): one byte (0/1) per map cell, x fastest.  NULL or n = 0 clears. */
+int mplb_planner_set_search_region(mplb_planner *p, const uint8_t *in_region, size_t n);
+/* MapPlanner::setSearchRegion (map_planner.cpp:46-95): tunnel of half-width `radius` (Dim doubles, setSearchRadius
+ * map_planner.cpp:41-43) around the polyline `path` (npts rows of 3 doubles); dense = the path is already cell-dense. */
+int mplb_planner_set_search_region_path(mplb_planner *p, const double *path, int npts, int dense, const double *radius);
+/* env_base::get_search_region (env_base.h:365): returns the cell count (0 when no region is set), fills out[0..cap). */
+int64_t mplb_planner_get_search_region(mplb_planner *p, uint8_t *out, size_t cap);
+/* env_map::set_potential_map (env_map.h:182): one int8 per map cell.  NULL or n = 0 clears. */
+int mplb_planner_set_potential_map(mplb_planner *p, const int8_t *pot, size_t n);
+/* MapPlanner::createMask + updatePotentialMap (map_planner.cpp:286-391): stamps the radial mask of height H_MAX = 100
+ * and exponent `pow` (map_planner.h:104,113) around every cell > 0 inside pos +- range (whole map when range is all
+ * zero), REWRITES THE PLANNER'S MAP with the result (like map_util_->setMap(dmap)) and installs it as this planner's
+ * potential map.  radius/range: 3 doubles (radius[0] = xy radius, radius[2] = z half-height in 3D). */
+int mplb_planner_update_potential_map(mplb_planner *p, const double *pos, const double *radius, const double *range,
+                                      double pow);
 
 /* plan (planner_base.h:275-325).  Returns MPLB_OK when the call itself worked; the reference's bool is
  * (out->status == MPLB_PLAN_OK || out->status == MPLB_PLAN_START_IS_GOAL).  The search state of this plan

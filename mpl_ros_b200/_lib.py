@@ -40,6 +40,11 @@ SYMBOLS = {
     "mplb_planner_set_map": (_I, [_VP, _VP]),
     "mplb_planner_set_param": (_I, [_VP, _I, _D]),
     "mplb_planner_set_controls": (_I, [_VP, _VP, _I, _I]),
+    "mplb_planner_set_search_region": (_I, [_VP, _VP, C.c_size_t]),
+    "mplb_planner_set_search_region_path": (_I, [_VP, _VP, _I, _I, _VP]),
+    "mplb_planner_get_search_region": (C.c_int64, [_VP, _VP, C.c_size_t]),
+    "mplb_planner_set_potential_map": (_I, [_VP, _VP, C.c_size_t]),
+    "mplb_planner_update_potential_map": (_I, [_VP, _VP, _VP, _VP, _D]),
     "mplb_plan": (_I, [_VP, _VP, _VP, _VP]),
     "mplb_plan_batch": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _I]),
     "mplb_plan_batch_device": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP]),
@@ -53,7 +58,7 @@ SYMBOLS = {
 }
 
 PARAM = dict(v_max=0, a_max=1, j_max=2, yaw_max=3, dt=4, w=5, epsilon=6, max_num=7, tol_pos=8, tol_vel=9,
-             tol_acc=10, t_max=11, mem_fraction=100, max_slots=101)
+             tol_acc=10, t_max=11, potential_weight=12, gradient_weight=13, mem_fraction=100, max_slots=101)
 
 _LIB = None
 

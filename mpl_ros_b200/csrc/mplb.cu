@@ -164,6 +164,52 @@ __global__ void k_plan_order(const unsigned *keys, int n, int *order) {
   order[rank] = i;
 }
 
+
+/* ---- potential map (map_planner.cpp:286-391).  tmp[q] collects max over sources s of mask[q - s]; the reference's
+ * sequential loop is order independent because the mask values never exceed H_MAX = 100. */
+__global__ void k_pot_stamp(const int8_t *src, int *tmp, int dim, int nx, int ny, int nz, int x1, int y1, int z1, int x2,
+                            int y2, int z2, const int *moff, const int *mval, int nmask) {
+  __shared__ int list[256];
+  __shared__ int cnt;
+  const long long bx = x2 - x1, by = y2 - y1, bz = z2 - z1;
+  const long long total = bx * by * bz;
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    long long i = base + threadIdx.x;
+    if (i < total) {
+      int x = x1 + (int)(i % bx), y = y1 + (int)((i / bx) % by), z = z1 + (int)(i / (bx * by));
+      size_t idx = (size_t)x + (size_t)nx * y + (size_t)nx * ny * z;
+      if (src[idx] > 0) list[atomicAdd(&cnt, 1)] = (int)i;
+    }
+    __syncthreads();
+    const long long work = (long long)cnt * nmask;
+    for (long long w = threadIdx.x; w < work; w += blockDim.x) {
+      const long long si = list[(int)(w / nmask)];
+      const int m = (int)(w % nmask);
+      int x = x1 + (int)(si % bx) + moff[m * 3], y = y1 + (int)((si / bx) % by) + moff[m * 3 + 1],
+          z = z1 + (int)(si / (bx * by)) + moff[m * 3 + 2];
+      if (x < 0 || x >= nx || y < 0 || y >= ny || z < 0 || z >= nz) continue;
+      atomicMax(&tmp[(size_t)x + (size_t)nx * y + (size_t)nx * ny * z], mval[m]);
+    }
+    __syncthreads();
+  }
+}
+__global__ void k_pot_merge(int8_t *grid, const int *tmp, int nx, int ny, int nz, int x1, int y1, int z1, int x2, int y2,
+                            int z2) {
+  size_t total = (size_t)nx * ny * nz;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((size_t)nx * ny));
+    int v = (int)grid[i];
+    bool src = v > 0 && x >= x1 && x < x2 && y >= y1 && y < y2 && z >= z1 && z < z2;
+    int t = tmp[i];
+    grid[i] = (int8_t)(src ? 100 : (t > v ? t : v));
+  }
+}
+__global__ void k_fill_int(int *a, int v, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = v;
+}
+
 }  // namespace
 
 /* ================================================================== objects */
@@ -207,6 +253,12 @@ struct mplb_planner {
   size_t budget_bytes = 0; /* arena budget, measured at the first batch (reset by MPLB_MEM_FRACTION) */
   std::vector<double> U; /* nU x 3 */
   int nU = 0;
+  /* cost shaping (em:104-128): defaults em:196-197 */
+  double pot_w = 0.1, grad_w = 0.0;
+  DevBuf<int8_t> d_pot;
+  size_t pot_cells = 0; /* 0 = no potential map */
+  DevBuf<unsigned> d_region;
+  std::vector<uint8_t> h_region; /* empty = no search region */
 
   /* device-side configuration, rebuilt when dirty */
   bool dirty = true;
@@ -362,6 +414,16 @@ int build_cfg(mplb_planner *p, int control) {
     c.use_fast = (known && n_hi < MPLB_NCAP && c.tt_total <= MPLB_TT_CAP && delta <= 1e-6) ? 1 : 0;
     c.fast_delta = delta;
   }
+  /* cost shaping (em:104-128) */
+  c.pot = nullptr; c.region = nullptr; c.pot_w = p->pot_w; c.grad_w = p->grad_w;
+  if (p->pot_cells || !p->h_region.empty()) {
+    if (p->pot_cells && p->pot_cells != m->ncell) return fail(MPLB_ERR_STATE, "potential map size does not match the planner's map");
+    if (!p->h_region.empty() && p->h_region.size() != m->ncell) return fail(MPLB_ERR_STATE, "search region size does not match the planner's map");
+    if (p->nU > 32) return fail(MPLB_ERR_ARG, "search region / potential map need a control set of at most 32 rows");
+    if (!c.use_fast) return fail(MPLB_ERR_ARG, "search region / potential map need positive dynamic bounds for every derivative of the control order");
+    if (p->pot_cells) c.pot = p->d_pot.p;
+    if (!p->h_region.empty()) c.region = p->d_region.p;
+  }
   {
     int e = 0;
     double mant = std::frexp(p->v_max, &e);
@@ -402,10 +464,10 @@ int build_cfg(mplb_planner *p, int control) {
   return MPLB_OK;
 }
 
-template <int DIM, int ORD, int MAXU>
+template <int DIM, int ORD, int MAXU, bool POT>
 int launch_batch(const DevCfg &c, const BatchArgs &a, int grid, cudaStream_t s) {
-  size_t smem = sizeof(PlanSmem<DIM, ORD, MAXU>);
-  auto kern = astar_batch_kernel<DIM, ORD, MAXU>;
+  size_t smem = sizeof(PlanSmem<DIM, ORD, MAXU, POT>);
+  auto kern = astar_batch_kernel<DIM, ORD, MAXU, POT>;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   /* the occupancy bricks are the only data with reuse across pops and plans: keep them resident in L2 */
   cudaLaunchConfig_t cfg;
@@ -440,15 +502,27 @@ int launch_batch(const DevCfg &c, const BatchArgs &a, int grid, cudaStream_t s) 
   return MPLB_OK;
 }
 
-template <int DIM, int ORD, int MAXU>
+template <int DIM, int ORD, int MAXU, bool POT>
 int resident_ctas(int device) {
   int per_sm = 0, sms = 0;
-  size_t smem = sizeof(PlanSmem<DIM, ORD, MAXU>);
-  auto kern = astar_batch_kernel<DIM, ORD, MAXU>;
+  size_t smem = sizeof(PlanSmem<DIM, ORD, MAXU, POT>);
+  auto kern = astar_batch_kernel<DIM, ORD, MAXU, POT>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MPLB_NT, smem) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
   return per_sm * sms;
+}
+
+/* the cost-shaping kernels exist for |U| <= 32 only (build_cfg rejects larger control sets with shaping) */
+template <int DIM, int ORD, int MAXU>
+int launch_any(bool shaped, const DevCfg &c, const BatchArgs &a, int grid, cudaStream_t s) {
+  if constexpr (MAXU == 1) { if (shaped) return launch_batch<DIM, ORD, MAXU, true>(c, a, grid, s); }
+  return launch_batch<DIM, ORD, MAXU, false>(c, a, grid, s);
+}
+template <int DIM, int ORD, int MAXU>
+int resident_any(bool shaped, int device) {
+  if constexpr (MAXU == 1) { if (shaped) return resident_ctas<DIM, ORD, MAXU, true>(device); }
+  return resident_ctas<DIM, ORD, MAXU, false>(device);
 }
 
 #define DISPATCH_U(D, O, nu, CALL) do { if ((nu) <= 32) { CALL(D, O, 1); } else { CALL(D, O, 4); } } while (0)
@@ -475,10 +549,11 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
 
   /* resident CTAs of this kernel instantiation and the memory budget are looked up once per configuration: both
    * calls cost on the order of a millisecond, comparable to a small batch */
-  const int cfg_sig = c.dim * 100 + c.ord * 10 + (c.nU <= 32 ? 1 : 4);
+  const bool shaped = c.pot != nullptr || c.region != nullptr;
+  const int cfg_sig = (shaped ? 1000 : 0) + c.dim * 100 + c.ord * 10 + (c.nU <= 32 ? 1 : 4);
   if (p->resident_sig != cfg_sig) {
     int r = 0;
-#define RES_CALL(D, O, M) r = resident_ctas<D, O, M>(p->device)
+#define RES_CALL(D, O, M) r = resident_any<D, O, M>(shaped, p->device)
     DISPATCH(c.dim, c.ord, c.nU, RES_CALL);
     p->resident_cached = r;
     p->resident_sig = cfg_sig;
@@ -578,7 +653,7 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
     CUDA_TRY(p->d_phase.reserve((size_t)n * 16));
     a.phase_cycles = p->d_phase.p;
 #endif
-#define LAUNCH_CALL(D, O, M) rc = launch_batch<D, O, M>(c, a, slots, s)
+#define LAUNCH_CALL(D, O, M) rc = launch_any<D, O, M>(shaped, c, a, slots, s)
     DISPATCH(c.dim, c.ord, c.nU, LAUNCH_CALL);
     if (rc != MPLB_OK) return rc;
     p->last_launches++; p->last_tiers++;
@@ -799,6 +874,8 @@ int mplb_planner_set_param(mplb_planner *p, int key, double v) {
     case MPLB_TOL_VEL: p->tol_vel = v; break;
     case MPLB_TOL_ACC: p->tol_acc = v; break;
     case MPLB_T_MAX: p->t_max = v; break;
+    case MPLB_POTENTIAL_WEIGHT: p->pot_w = v; break;
+    case MPLB_GRADIENT_WEIGHT: p->grad_w = v; break;
     case MPLB_MEM_FRACTION:
       if (!(v > 0 && v <= 0.95)) return fail(MPLB_ERR_ARG, "mem fraction must be in (0, 0.95]");
       p->mem_fraction = v;
@@ -820,6 +897,196 @@ int mplb_planner_set_controls(mplb_planner *p, const double *U, int n, int udim)
   for (int i = 0; i < n; i++)
     for (int k = 0; k < udim; k++) p->U[(size_t)i * 3 + k] = U[(size_t)i * udim + k];
   p->nU = n;
+  p->dirty = true;
+  return MPLB_OK;
+}
+
+
+/* ---- cost shaping: search region (eb:301-303, map_planner.cpp:46-95) and potential map (em:182, map_planner.cpp:286-391) */
+namespace {
+void host_float_to_int(const mplb_map *m, const double *pt, int *pn) { /* mu:106-111 */
+  pn[0] = pn[1] = pn[2] = 0;
+  for (int i = 0; i < m->dim; i++) pn[i] = (int)std::round((pt[i] - m->origin[i]) / m->res - 0.5);
+}
+bool host_outside(const mplb_map *m, const int *pn) {
+  for (int i = 0; i < m->dim; i++)
+    if (pn[i] < 0 || pn[i] >= m->nd[i]) return true;
+  return false;
+}
+int upload_region(mplb_planner *p) {
+  const size_t n = p->h_region.size();
+  std::vector<unsigned> bits((n + 31) / 32, 0u);
+  for (size_t i = 0; i < n; i++)
+    if (p->h_region[i]) bits[i >> 5] |= 1u << (i & 31);
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  CUDA_TRY(p->d_region.reserve(bits.size()));
+  CUDA_TRY(cudaMemcpy(p->d_region.p, bits.data(), bits.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  p->dirty = true;
+  return MPLB_OK;
+}
+}  // namespace
+
+int mplb_planner_set_search_region(mplb_planner *p, const uint8_t *in_region, size_t n) {
+  if (!p) return fail(MPLB_ERR_ARG, "null planner");
+  if (!in_region || n == 0) { p->h_region.clear(); p->dirty = true; return MPLB_OK; }
+  if (!p->map) return fail(MPLB_ERR_STATE, "planner has no map (setMapUtil not called)");
+  if (n != p->map->ncell) return fail(MPLB_ERR_ARG, "search region must have one entry per map cell");
+  p->h_region.assign(in_region, in_region + n);
+  return upload_region(p);
+}
+
+int mplb_planner_set_search_region_path(mplb_planner *p, const double *path, int npts, int dense, const double *radius) {
+  if (!p || !radius || (npts > 0 && !path)) return fail(MPLB_ERR_ARG, "null argument");
+  if (!p->map) return fail(MPLB_ERR_STATE, "planner has no map (setMapUtil not called)");
+  const mplb_map *m = p->map;
+  const int D = m->dim;
+  /* cells along the path: rayTrace (mu:117-134) between consecutive points plus each end point */
+  std::vector<int> cells; /* 3 ints per cell */
+  auto push = [&](const int *pn) { cells.push_back(pn[0]); cells.push_back(pn[1]); cells.push_back(pn[2]); };
+  if (!dense) {
+    for (int i = 1; i < npts; i++) {
+      const double *a = path + (size_t)(i - 1) * 3, *b = path + (size_t)i * 3;
+      double diff[3] = {0, 0, 0}, q = 0;
+      for (int k = 0; k < D; k++) {
+        diff[k] = b[k] - a[k];
+        q = std::max(q, std::fabs(diff[k] / m->res));
+      }
+      const int max_diff = (int)(q / 0.8);
+      const double sc = 1.0 / max_diff;
+      double step[3] = {0, 0, 0};
+      for (int k = 0; k < D; k++) step[k] = diff[k] * sc;
+      int prev[3] = {-1, -1, -1};
+      for (int n = 1; n < max_diff; n++) {
+        double pt[3] = {0, 0, 0};
+        int pn[3];
+        for (int k = 0; k < D; k++) pt[k] = a[k] + step[k] * n;
+        host_float_to_int(m, pt, pn);
+        if (host_outside(m, pn)) break;
+        bool same = true;
+        for (int k = 0; k < D; k++) same = same && pn[k] == prev[k];
+        if (!same) push(pn);
+        for (int k = 0; k < D; k++) prev[k] = pn[k];
+      }
+      int pe[3];
+      host_float_to_int(m, b, pe);
+      push(pe);
+    }
+  } else {
+    for (int i = 0; i < npts; i++) { int pn[3]; host_float_to_int(m, path + (size_t)i * 3, pn); push(pn); }
+  }
+  int rn[3] = {0, 0, 0};
+  for (int k = 0; k < D; k++) rn[k] = (int)std::ceil(radius[k] / m->res);
+  p->h_region.assign(m->ncell, 0);
+  for (size_t ci = 0; ci + 2 < cells.size(); ci += 3) {
+    const int lo[3] = {std::max(cells[ci] - rn[0], 0), std::max(cells[ci + 1] - rn[1], 0), D == 3 ? std::max(cells[ci + 2] - rn[2], 0) : 0};
+    const int hi[3] = {std::min(cells[ci] + rn[0], m->nd[0] - 1), std::min(cells[ci + 1] + rn[1], m->nd[1] - 1),
+                       D == 3 ? std::min(cells[ci + 2] + rn[2], m->nd[2] - 1) : 0};
+    for (int z = lo[2]; z <= hi[2]; z++)
+      for (int y = lo[1]; y <= hi[1]; y++) {
+        if (lo[0] > hi[0]) continue;
+        uint8_t *row = p->h_region.data() + (size_t)m->nd[0] * y + (size_t)m->nd[0] * m->nd[1] * z;
+        std::memset(row + lo[0], 1, (size_t)(hi[0] - lo[0] + 1));
+      }
+  }
+  int rc = upload_region(p);
+  if (rc == MPLB_OK && p->verbose) std::printf("[MapPlanner] set search region\n");
+  return rc;
+}
+
+int64_t mplb_planner_get_search_region(mplb_planner *p, uint8_t *out, size_t cap) {
+  if (!p) { fail(MPLB_ERR_ARG, "null planner"); return 0; }
+  const size_t n = p->h_region.size();
+  if (out && n) std::memcpy(out, p->h_region.data(), std::min(cap, n));
+  return (int64_t)n;
+}
+
+int mplb_planner_set_potential_map(mplb_planner *p, const int8_t *pot, size_t n) {
+  if (!p) return fail(MPLB_ERR_ARG, "null planner");
+  if (!pot || n == 0) { p->pot_cells = 0; p->dirty = true; return MPLB_OK; }
+  if (!p->map) return fail(MPLB_ERR_STATE, "planner has no map (setMapUtil not called)");
+  if (n != p->map->ncell) return fail(MPLB_ERR_ARG, "potential map must have one entry per map cell");
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  CUDA_TRY(p->d_pot.reserve(n));
+  CUDA_TRY(cudaMemcpy(p->d_pot.p, pot, n, cudaMemcpyHostToDevice));
+  p->pot_cells = n;
+  p->dirty = true;
+  return MPLB_OK;
+}
+
+int mplb_planner_update_potential_map(mplb_planner *p, const double *pos, const double *radius, const double *range,
+                                      double pow_) {
+  if (!p || !pos || !radius || !range) return fail(MPLB_ERR_ARG, "null argument");
+  if (!p->map) return fail(MPLB_ERR_STATE, "planner has no map (setMapUtil not called)");
+  mplb_map *m = p->map;
+  if (m->device != p->device) return fail(MPLB_ERR_STATE, "map and planner live on different devices");
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  const int D = m->dim;
+  /* createMask (map_planner.cpp:286-325), evaluated on the host with the reference's libm calls */
+  std::vector<int> moff, mval;
+  const double h_max = 100.0;
+  const int rn = (int)std::ceil(radius[0] / m->res);
+  const int hn = D == 3 ? (int)std::ceil(radius[2] / m->res) : 0;
+  for (int nx = -rn; nx <= rn; nx++)
+    for (int ny = -rn; ny <= rn; ny++)
+      for (int nz = -hn; nz <= hn; nz++) {
+        const double r = std::hypot((double)nx, (double)ny);
+        if (r > rn) continue;
+        const double base = D == 2 ? (1 - r / rn) : (1 - r / rn) * (1 - (double)std::abs(nz) / hn);
+        const double h = h_max * std::pow(base, pow_);
+        if (h > 1e-3) { moff.push_back(nx); moff.push_back(ny); moff.push_back(nz); mval.push_back((int)(int8_t)h); }
+      }
+  /* the stamped box (map_planner.cpp:330-347): whole map, or the clamped cells of pos -+ range with an open upper end */
+  int c1[3] = {0, 0, 0}, c2[3] = {m->nd[0], m->nd[1], D == 3 ? m->nd[2] : 1};
+  double rnorm = 0;
+  for (int k = 0; k < D; k++) rnorm += range[k] * range[k];
+  if (std::sqrt(rnorm) > 0) {
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int k = 0; k < D; k++) { lo[k] = pos[k] - range[k]; hi[k] = pos[k] + range[k]; }
+    host_float_to_int(m, lo, c1);
+    host_float_to_int(m, hi, c2);
+    for (int k = 0; k < D; k++) {
+      c1[k] = std::min(std::max(c1[k], 0), m->nd[k] - 1);
+      c2[k] = std::min(std::max(c2[k], 0), m->nd[k] - 1);
+    }
+    if (D == 2) { c1[2] = 0; c2[2] = 1; }
+  }
+  int *d_tmp = nullptr, *d_moff = nullptr, *d_mval = nullptr;
+  const int nmask = (int)mval.size();
+  CUDA_TRY(cudaMalloc((void **)&d_tmp, m->ncell * sizeof(int)));
+  const int fill_blocks = (int)std::min<size_t>((m->ncell + 255) / 256, 148 * 16);
+  k_fill_int<<<fill_blocks, 256>>>(d_tmp, -1000, m->ncell);
+  g_launches++;
+  cudaError_t e = cudaGetLastError();
+  const long long box = (long long)std::max(c2[0] - c1[0], 0) * std::max(c2[1] - c1[1], 0) * std::max(c2[2] - c1[2], 0);
+  if (e == cudaSuccess && nmask > 0 && box > 0) {
+    e = cudaMalloc((void **)&d_moff, moff.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_mval, mval.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(d_moff, moff.data(), moff.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_mval, mval.data(), mval.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      const int blocks = (int)std::min<long long>((box + 255) / 256, 148 * 16);
+      k_pot_stamp<<<blocks, 256>>>(m->d_grid, d_tmp, D, m->nd[0], m->nd[1], m->nd[2], c1[0], c1[1], c1[2], c2[0], c2[1], c2[2],
+                                   d_moff, d_mval, nmask);
+      g_launches++;
+      e = cudaGetLastError();
+    }
+  }
+  if (e == cudaSuccess) {
+    k_pot_merge<<<fill_blocks, 256>>>(m->d_grid, d_tmp, m->nd[0], m->nd[1], m->nd[2], c1[0], c1[1], c1[2], c2[0], c2[1], c2[2]);
+    g_launches++;
+    e = cudaGetLastError();
+  }
+  int rc = MPLB_OK;
+  if (e == cudaSuccess) rc = m->rebuild_bricks(0); /* the map itself now holds dmap (map_planner.cpp:387) */
+  if (e == cudaSuccess && rc == MPLB_OK) e = p->d_pot.reserve(m->ncell);
+  if (e == cudaSuccess && rc == MPLB_OK) e = cudaMemcpy(p->d_pot.p, m->d_grid, m->ncell, cudaMemcpyDeviceToDevice); /* map_planner.cpp:388 */
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(d_tmp);
+  if (d_moff) cudaFree(d_moff);
+  if (d_mval) cudaFree(d_mval);
+  if (e != cudaSuccess) return fail(MPLB_ERR_CUDA, std::string("update_potential_map: ") + cudaGetErrorString(e));
+  if (rc != MPLB_OK) return rc;
+  p->pot_cells = m->ncell;
   p->dirty = true;
   return MPLB_OK;
 }
@@ -974,6 +1241,7 @@ int mplb_expand(mplb_planner *p, const mplb_waypoint *states, int n, mplb_prim_t
   int rc = build_cfg(p, states[0].control);
   if (rc != MPLB_OK) return rc;
   const DevCfg &c = p->cfg;
+  if (c.pot || c.region) return fail(MPLB_ERR_STATE, "mplb_expand traces the plain-map get_succ only; clear the search region / potential map first");
   mplb_waypoint *d_s = nullptr;
   mplb_prim_trace *d_r = nullptr;
   CUDA_TRY(cudaMalloc((void **)&d_s, (size_t)n * sizeof(mplb_waypoint)));

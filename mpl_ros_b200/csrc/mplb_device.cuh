@@ -74,6 +74,10 @@ struct DevCfg {
   int tt_total;     /* number of entries of ttab */
   double fast_delta; /* guard band around rounding ties of the filtered sampler, in cells */
   double vmax_rcp_exact; /* 1/v_max when v_max is a power of two (x / v_max == x * this, bit for bit), else 0 */
+  /* cost shaping of env_map (em:104-118): optional potential map (int8 per cell) and search-region bitmask */
+  const int8_t *pot;
+  const unsigned int *region;
+  double pot_w, grad_w;
 };
 
 /* ------------------------------------------------------------------------------------------------

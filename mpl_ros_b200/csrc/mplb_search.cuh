@@ -158,11 +158,13 @@ struct ExpBuf {
   int cnt[MAXU];     /* samples to test */
   int first[MAXU];   /* first blocked sample index or INT_MAX */
   int nid[MAXU];     /* node id of the successor after relaxation (for state forwarding) */
+  int gbase[MAXU];   /* first granule of the control in gl[] (cost-shaping kernels sum its sample terms in order) */
+  double dts[MAXU];  /* sample spacing T/n (em:98), cost-shaping kernels only */
   unsigned int gl[GCAP];     /* granule: control | first sample k0 << 8 | sample count << 16 ... */
   unsigned short gl_t[GCAP]; /* ... and index of its first sample time in tts */
 };
 
-template <int DIM, int ORD, int NB>
+template <int DIM, int ORD, int NB, bool POT = false>
 struct PlanSmem {
   static constexpr int NS = DIM * ORD;
   static constexpr int MAXU = 32 * NB;
@@ -193,6 +195,7 @@ struct PlanSmem {
   int p_nid[MAXU], p_slot[MAXU];
   double p_g[MAXU], p_pg[MAXU], p_h[MAXU];
   double tts[MPLB_TT_CAP]; /* accumulated sample times (em:98-99), all divisors */
+  double terms[POT ? MAXU * 64 : 1]; /* per-sample cost terms of the current expansion (potential map), by granule slot */
   int n_before;      /* n_nodes before this expansion */
   /* pending sift-down (heap warp) and prefetched root row */
   int sd_pending, sd_n;
@@ -442,6 +445,7 @@ __device__ MPLB_B1_INLINE void b1_warp(const DevCfg &c, const SM &S, EBT &E, int
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
     int excl = gbase + incl - ng;
+    if (i < c.nU) { E.gbase[i] = excl; if (c.pot && E.nsamp[i] > 0) E.dts[i] = ddiv(c.dt, (double)E.nsamp[i]); }
     for (int q = 0; q < ng; q++) {
       E.gl[excl + q] = (unsigned)i | ((unsigned)(q * 8) << 8) | ((unsigned)E.cnt[i] << 16);
       E.gl_t[excl + q] = (unsigned short)(S.toff_s[E.nsamp[i]] + q * 8);
@@ -637,7 +641,14 @@ __device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, typename SM::E
     } else hn = hot[nid];
     E.nid[idx] = nid;
     S.p_slot[idx] = slot; /* later batches of this pop test their empty slots against it */
-    double tentative = dadd(cg, S.cost[idx]); /* gs:107 */
+    double ecost = S.cost[idx];
+    if (c.pot && v == 3) { /* cost shaping (em:114-115); S.terms exists only in the POT instantiations, where c.pot may be set */
+      double acc = 0.0;
+      const int base_t = E.gbase[idx] * 8, cn_t = E.cnt[idx];
+      for (int q = 0; q < cn_t; q++) acc = dadd(acc, S.terms[base_t + q]);
+      ecost = dadd(acc, S.cost[idx]);
+    }
+    double tentative = dadd(cg, ecost); /* gs:107 */
     if (tentative < hn.g) { /* gs:109-141 */
       double f = dadd(tentative, dmul(c.eps, hn.h));
       hn.g = tentative; hn.pg = cg; hn.action = (short)idx;
@@ -701,12 +712,92 @@ __device__ __forceinline__ void sample_granules(const DevCfg &c, const SM &S, EB
   }
 }
 
+/* ---------------------------------------------------------------- cost shaping (em:104-128): search region + potential map
+ * Separate code path, compiled only into the POT instantiations so that the plain-map kernel keeps its size. */
+template <int DIM, int ORD, class SM>
+__device__ __noinline__ bool cell_exact(const DevCfg &c, const SM &S, const double *st, int i, double t, int *pn) {
+  bool outside = false;
+#pragma unroll
+  for (int ax = 0; ax < DIM; ax++) {
+    Axis<ORD> A(&st[ax], DIM, S.U[i * 3 + ax], S.Ut[i * 3 + ax]);
+    pn[ax] = float_to_cell(A.p(t), c.origin[ax], c.res);
+    outside = outside || pn[ax] < 0 || pn[ax] >= c.nd[ax];
+  }
+  return outside;
+}
+template <int DIM, int ORD, class SM, class EBT>
+__device__ __forceinline__ bool cell_filtered(const DevCfg &c, const SM &S, const EBT &E, int i, double t, int *pn, bool *sure) {
+  bool ok = true, outside = false;
+#pragma unroll
+  for (int ax = 0; ax < DIM; ax++) {
+    double dy = S.Au[i * 3 + ax];
+#pragma unroll
+    for (int d = ORD - 2; d >= 0; d--) dy = __fma_rn(dy, t, E.Ap[d * 3 + ax]);
+    double w = __dsub_rn(__fma_rn(dy, t, E.y0[ax]), 0.5);
+    double wm = magic_add(w);
+    ok = ok && (fabs(__dsub_rn(w, magic_rint(wm))) < 0.5 - c.fast_delta);
+    pn[ax] = magic_int(wm);
+    outside = outside || pn[ax] < 0 || pn[ax] >= c.nd[ax];
+  }
+  *sure = ok;
+  return outside;
+}
+/* One sample with cost shaping: returns blocked (em:104-106,116-120) and the cost term of em:114-115 (0 when none). */
+template <int DIM, int ORD, class SM, class EBT>
+__device__ __forceinline__ bool sample_shaped(const DevCfg &c, const SM &S, const EBT &E, int i, double t, double *term) {
+  int pn[3] = {0, 0, 0};
+  bool sure;
+  bool outside = cell_filtered<DIM, ORD>(c, S, E, i, t, pn, &sure);
+  if (!sure) outside = cell_exact<DIM, ORD>(c, S, E.st, i, t, pn);
+  *term = 0.0;
+  if (outside) return true;
+  const size_t idx = (DIM == 2) ? (size_t)pn[0] + (size_t)c.nd[0] * pn[1]
+                                : (size_t)pn[0] + (size_t)c.nd[0] * pn[1] + (size_t)c.nd[0] * c.nd[1] * pn[2];
+  if (c.region && !((c.region[idx >> 5] >> (idx & 31)) & 1u)) return true; /* not in the search region */
+  if (c.pot) {
+    const int p = (int)c.pot[idx];
+    if (p >= 100) return true;
+    if (p > 0) {
+      double vn = 0.0;
+      if (c.grad_w != 0.0) { /* pt.vel.norm() = sqrt of the left-to-right sum of squares */
+        double ss = 0.0;
+#pragma unroll
+        for (int ax = 0; ax < DIM; ax++) {
+          Axis<ORD> A(&E.st[ax], DIM, S.U[i * 3 + ax], S.Ut[i * 3 + ax]);
+          double v = A.v(t);
+          ss = (ax == 0) ? dmul(v, v) : dadd(ss, dmul(v, v));
+        }
+        vn = sqrt(ss);
+      }
+      *term = dmul(E.dts[i], dadd(dmul(c.pot_w, (double)p), dmul(c.grad_w, vn)));
+    }
+    return false;
+  }
+  return brick_occupied<DIM>(c, pn[0], pn[1], pn[2]);
+}
+template <int DIM, int ORD, class SM, class EBT>
+__device__ __forceinline__ void sample_granules_shaped(const DevCfg &c, SM &S, EBT &E, int t, int nthreads) {
+  const int gstep = nthreads >> 3;
+  const int sub = t & 7;
+  for (int g = t >> 3; g < E.n_gran; g += gstep) {
+    const unsigned info = E.gl[g];
+    const int u = (int)(info & 0xffu);
+    const int k = (int)((info >> 8) & 0xffu) + sub;
+    if (k < (int)(info >> 16)) {
+      double term;
+      const bool blk = sample_shaped<DIM, ORD>(c, S, E, u, S.tts[(int)E.gl_t[g] + sub], &term);
+      S.terms[g * 8 + sub] = term;
+      if (blk) atomicMin(&E.first[u], k);
+    }
+  }
+}
+
 /* ---------------------------------------------------------------- the kernel */
-template <int DIM, int ORD, int NB>
+template <int DIM, int ORD, int NB, bool POT>
 __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ BatchArgs a) {
   constexpr int NS = DIM * ORD;
   constexpr int NW = MPLB_NT / 32;
-  using SM = PlanSmem<DIM, ORD, NB>;
+  using SM = PlanSmem<DIM, ORD, NB, POT>;
   constexpr size_t ROWB = (sizeof(RowHdr) + NS * sizeof(double) + 15) & ~(size_t)15; /* 16-byte aligned rows */
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM &S = *reinterpret_cast<SM *>(smem_raw);
@@ -958,7 +1049,8 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
             }
           }
           /* ---- B2: all collision samples of all controls, flat over 8-sample granules (warps 1..NW-2) */
-          if (fast) sample_granules<DIM, ORD>(c, S, E, tid - 32, MPLB_NT - 64);
+          if (POT) sample_granules_shaped<DIM, ORD>(c, S, E, tid - 32, MPLB_NT - 64); /* host guarantees the fast tables */
+          else if (fast) sample_granules<DIM, ORD>(c, S, E, tid - 32, MPLB_NT - 64);
           else expand_b2_percontrol<DIM, ORD>(c, S, E, warp - 1, lane, NW - 2);
         }
         MPLB_TICK(2);
@@ -1024,7 +1116,14 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
             __syncwarp();
             continue;
           }
-          const double tentative = dadd(cg, valid ? S.cost[i] : 0.0); /* gs:107 */
+          double ecost = valid ? S.cost[i] : 0.0;
+          if (POT && c.pot && v == 3 && valid) { /* em:114-115: accumulate the sample terms in sample order, then eb:343-345 */
+            double acc = 0.0;
+            const int base_t = E.gbase[i] * 8, cn_t = E.cnt[i];
+            for (int q = 0; q < cn_t; q++) acc = dadd(acc, S.terms[base_t + q]);
+            ecost = dadd(acc, S.cost[i]);
+          }
+          const double tentative = dadd(cg, ecost); /* gs:107 */
           const bool improve = found && tentative < r_g_b;
           const bool tie = found && tentative == r_g_b && cg > r_pg_b; /* recoverTraj tie rule (gs:398-403) */
           const unsigned newm = __ballot_sync(0xffffffffu, isnew);

@@ -210,6 +210,11 @@ class MapPlanner:
         self._control = None
         self.traj_cost_ = None
         self._initialized = False
+        # map_planner.h:104-113
+        self.search_radius_ = np.zeros(3)
+        self.potential_radius_ = np.zeros(3)
+        self.potential_map_range_ = np.zeros(3)
+        self.pow_ = 1.0
 
     def __del__(self):
         try:
@@ -252,6 +257,83 @@ class MapPlanner:
 
     def initialized(self):
         return self._initialized
+
+    # ---- cost shaping (map_planner.h:27-54,77-87)
+    def _vec3(self, v):
+        out = np.zeros(3)
+        v = np.asarray(v, dtype=np.float64).ravel()
+        out[:len(v)] = v
+        return out
+
+    def setSearchRadius(self, radius):  # map_planner.cpp:41-43
+        self.search_radius_ = self._vec3(radius)
+
+    def setPotentialRadius(self, radius):  # map_planner.cpp:20-23
+        self.potential_radius_ = self._vec3(radius)
+
+    def setPotentialMapRange(self, rng):  # map_planner.cpp:25-28
+        self.potential_map_range_ = self._vec3(rng)
+
+    def setPotentialWeight(self, w): self._set("potential_weight", w)  # map_planner.cpp:30-33
+    def setGradientWeight(self, w): self._set("gradient_weight", w)    # map_planner.cpp:35-38
+
+    def setSearchRegion(self, path, dense=False):  # map_planner.cpp:46-95
+        pts = np.zeros((len(path), 3))
+        for i, q in enumerate(path):
+            q = np.asarray(q, dtype=np.float64).ravel()
+            pts[i, :len(q)] = q
+        check(lib().mplb_planner_set_search_region_path(self._h, ptr(pts), len(pts), int(bool(dense)),
+                                                        ptr(self.search_radius_)))
+
+    def setSearchRegionMask(self, in_region):  # env_base::set_search_region, env_base.h:301-303 (None clears)
+        if in_region is None:
+            check(lib().mplb_planner_set_search_region(self._h, None, 0))
+            return
+        m = np.ascontiguousarray(in_region, dtype=np.uint8).ravel()
+        check(lib().mplb_planner_set_search_region(self._h, ptr(m), m.size))
+
+    def getSearchRegionMask(self):  # env_base::get_search_region, env_base.h:365
+        n = int(lib().mplb_planner_get_search_region(self._h, None, 0))
+        out = np.zeros(n, dtype=np.uint8)
+        if n:
+            lib().mplb_planner_get_search_region(self._h, ptr(out), n)
+        return out
+
+    def getSearchRegion(self):  # map_planner.cpp:97-114: centres of the in-region cells
+        mask = self.getSearchRegionMask()
+        if mask.size == 0:
+            return np.zeros((0, self.dim))
+        nd = np.asarray(self.map_util_.getDim())
+        idx = np.flatnonzero(mask)
+        cells = np.stack(np.unravel_index(idx, tuple(nd[::-1])), axis=1)[:, ::-1]  # x fastest
+        cells = cells[np.lexsort(cells[:, ::-1].T)]  # the reference walks x outermost
+        return (cells + 0.5) * self.map_util_.getRes() + np.asarray(self.map_util_.getOrigin())[:self.dim]
+
+    def setPotentialMap(self, pot):  # env_map::set_potential_map, env_map.h:182 (None clears)
+        if pot is None:
+            check(lib().mplb_planner_set_potential_map(self._h, None, 0))
+            return
+        m = np.ascontiguousarray(pot, dtype=np.int8).ravel()
+        check(lib().mplb_planner_set_potential_map(self._h, ptr(m), m.size))
+
+    def updatePotentialMap(self, pos):  # map_planner.cpp:327-391 (rewrites the shared map, like the reference)
+        check(lib().mplb_planner_update_potential_map(self._h, ptr(self._vec3(pos)), ptr(self.potential_radius_),
+                                                      ptr(self.potential_map_range_), float(self.pow_)))
+
+    def iterativePlan(self, start, goal, raw_traj, max_num):  # map_planner.cpp:394-434
+        traj = raw_traj
+        prev_cost = 0.0
+        cnt = 0
+        while cnt < max_num:
+            cnt += 1
+            self.setSearchRegion([w.pos for w in traj.getWaypoints()], False)
+            if not self.plan(start, goal):
+                return False
+            traj = self.getTraj()
+            if prev_cost == self.traj_cost_:
+                break
+            prev_cost = self.traj_cost_
+        return True
 
     # ---- plan (planner_base.h:275-325)
     def plan(self, start, goal):

@@ -46,6 +46,14 @@ def lib():
         L.orc_planner_set_map.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_planner_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.orc_planner_set_controls.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_planner_set_vec.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        L.orc_planner_set_search_region.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_planner_clear_shaping.argtypes = [C.c_void_p]
+        L.orc_planner_get_search_region.restype = C.c_int64
+        L.orc_planner_get_search_region.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.orc_planner_update_potential_map.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_map_get_data.restype = C.c_int64
+        L.orc_map_get_data.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_get_actions.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_get_seg_states.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -76,6 +84,11 @@ class OracleMap:
 
     def free_unknown(self):
         lib().orc_map_free_unknown(self.h)
+
+    def get_data(self, n):
+        out = np.zeros(n, dtype=np.int8)
+        lib().orc_map_get_data(self.h, _ptr(out), n)
+        return out
 
     def float_to_int(self, pt):
         pt = np.ascontiguousarray(pt, dtype=np.float64)
@@ -116,6 +129,27 @@ class OraclePlanner:
         U = np.ascontiguousarray(U, dtype=np.float64)
         self.nU = U.shape[0]
         lib().orc_planner_set_controls(self.h, _ptr(U), U.shape[0], U.shape[1])
+
+    # ---- cost shaping (MapPlanner members, map_planner.h:27-49)
+    def set_vec(self, key, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        lib().orc_planner_set_vec(self.h, key.encode(), _ptr(v))
+
+    def set_search_region(self, path, dense=False):
+        path = np.ascontiguousarray(path, dtype=np.float64)
+        lib().orc_planner_set_search_region(self.h, _ptr(path), path.shape[0], int(dense))
+
+    def get_search_region(self, ncell):
+        out = np.zeros(ncell, dtype=np.uint8)
+        n = lib().orc_planner_get_search_region(self.h, _ptr(out), ncell)
+        return out[:n]
+
+    def update_potential_map(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        lib().orc_planner_update_potential_map(self.h, _ptr(pos))
+
+    def clear_shaping(self):
+        lib().orc_planner_clear_shaping(self.h)
 
     def plan(self, start, goal):
         res = np.zeros(1, dtype=RESULT_DTYPE)

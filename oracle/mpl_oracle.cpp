@@ -24,6 +24,7 @@
 #include "mpl_oracle.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -287,6 +288,31 @@ struct Map {
     for (auto &v : data)
       if (v == -1) v = 0;
   }
+  /* mu:117-134, the cell list itself (used by MapPlanner::setSearchRegion, map_planner.cpp:50-53) */
+  void ray_trace(const double *pt1, const double *pt2, std::vector<std::array<int, 3>> &pns) const {
+    double diff[3] = {0, 0, 0}, q = 0;
+    for (int i = 0; i < dim; i++) {
+      diff[i] = pt2[i] - pt1[i];
+      double a = std::abs(diff[i] / res);
+      if (i == 0 || a > q) q = a;
+    }
+    int max_diff = (int)(q / 0.8);
+    double s = 1.0 / max_diff;
+    double step[3] = {0, 0, 0};
+    for (int i = 0; i < dim; i++) step[i] = diff[i] * s;
+    int prev[3] = {-1, -1, -1};
+    for (int n = 1; n < max_diff; n++) {
+      double pt[3] = {0, 0, 0};
+      int pn[3] = {0, 0, 0};
+      for (int i = 0; i < dim; i++) pt[i] = pt1[i] + step[i] * n;
+      float_to_int(pt, pn);
+      if (outside(pn)) break;
+      bool same = true;
+      for (int i = 0; i < dim; i++) same = same && pn[i] == prev[i];
+      if (!same) pns.push_back({pn[0], pn[1], pn[2]});
+      for (int i = 0; i < dim; i++) prev[i] = pn[i];
+    }
+  }
   /* mu:117-134; returns true iff some traced cell is occupied (what em:38-42 asks). */
   bool ray_hits_occupied(const double *pt1, const double *pt2) const {
     double diff[3], q = 0;
@@ -397,6 +423,13 @@ struct Planner {
   int max_num = -1;
   std::vector<std::vector<double>> U;
   WP goal;
+  // cost shaping (em:104-118, eb:395-396; MapPlanner members map_planner.h:104-118)
+  std::vector<int8_t> potential_map;
+  std::vector<bool> search_region;
+  double potential_weight = 0.1, gradient_weight = 0.0;  // em:294-296
+  double search_radius[3] = {0, 0, 0}, potential_radius[3] = {0, 0, 0}, potential_map_range[3] = {0, 0, 0};
+  double pow_ = 1.0;
+  int8_t H_MAX = 100;
 
   // state of the last plan
   std::vector<Node> nodes;
@@ -437,7 +470,7 @@ struct Planner {
     return w * m;
   }
 
-  /* em:90-132, plain map (no potential map, no search region, no yaw) */
+  /* em:90-132 (no yaw) */
   double traverse(const Prim &pr, orc_prim_trace *tr, int64_t *n_samples) const {
     double max_v = 0;
     for (int i = 0; i < dim; i++)
@@ -452,13 +485,25 @@ struct Planner {
       int pn[3] = {0, 0, 0};
       map->float_to_int(pt.pos, pn);
       tested++;
-      if (map->outside(pn)) {
-        if (tr) tr->n_tested = tested;
+      const bool out = map->outside(pn);
+      const int idx = out ? -1 : map->index(pn);
+      if (out || (!search_region.empty() && !search_region[idx])) {  // em:104-106
+        if (tr) { tr->n_tested = tested; tr->block_idx = idx; }
         *n_samples += tested;
         return kInf;
       }
-      if (map->data[map->index(pn)] == 100) {
-        if (tr) { tr->n_tested = tested; tr->block_idx = map->index(pn); }
+      if (!potential_map.empty()) {  // em:113-118
+        if (potential_map[idx] < 100 && potential_map[idx] > 0) {
+          double vn = 0;
+          for (int k = 0; k < dim; k++) vn += pt.vel[k] * pt.vel[k];  // Eigen norm(): sqrt of the left-to-right sum of squares
+          c += dts * (potential_weight * potential_map[idx] + gradient_weight * std::sqrt(vn));
+        } else if (potential_map[idx] >= 100) {
+          if (tr) { tr->n_tested = tested; tr->block_idx = idx; }
+          *n_samples += tested;
+          return kInf;
+        }
+      } else if (map->data[idx] == 100) {  // em:119-120
+        if (tr) { tr->n_tested = tested; tr->block_idx = idx; }
         *n_samples += tested;
         return kInf;
       }
@@ -466,6 +511,91 @@ struct Planner {
     if (tr) tr->n_tested = tested;
     *n_samples += tested;
     return c;
+  }
+
+  /* MapPlanner::setSearchRegion, map_planner.cpp:46-95 */
+  void set_search_region_path(const std::vector<std::array<double, 3>> &path, bool dense) {
+    std::vector<std::array<int, 3>> ps;
+    if (!dense) {
+      for (size_t i = 1; i < path.size(); i++) {
+        map->ray_trace(path[i - 1].data(), path[i].data(), ps);
+        int pn[3] = {0, 0, 0};
+        map->float_to_int(path[i].data(), pn);
+        ps.push_back({pn[0], pn[1], pn[2]});
+      }
+    } else {
+      for (const auto &pt : path) { int pn[3] = {0, 0, 0}; map->float_to_int(pt.data(), pn); ps.push_back({pn[0], pn[1], pn[2]}); }
+    }
+    int rn[3] = {0, 0, 0};
+    for (int i = 0; i < dim; i++) rn[i] = (int)std::ceil(search_radius[i] / map->res);
+    size_t ncell = 1;
+    for (int i = 0; i < dim; i++) ncell *= (size_t)map->nd[i];
+    std::vector<bool> in_region(ncell, false);
+    for (const auto &it : ps)
+      for (int dx = -rn[0]; dx <= rn[0]; dx++)
+        for (int dy = -rn[1]; dy <= rn[1]; dy++)
+          for (int dz = (dim == 3 ? -rn[2] : 0); dz <= (dim == 3 ? rn[2] : 0); dz++) {
+            int pn[3] = {it[0] + dx, it[1] + dy, it[2] + dz};
+            if (map->outside(pn)) continue;
+            in_region[map->index(pn)] = true;
+          }
+    search_region = in_region;
+  }
+
+  /* MapPlanner::createMask + updatePotentialMap, map_planner.cpp:286-391.  Rewrites the map itself (setMap(dmap)) and
+   * hands the result to the environment as its potential map, exactly like the reference. */
+  void update_potential_map(const double *pos) {
+    std::vector<std::pair<std::array<int, 3>, int8_t>> mask;
+    double res = map->res, h_max = H_MAX;
+    int rn = (int)std::ceil(potential_radius[0] / res);
+    if (dim == 2) {
+      for (int nx = -rn; nx <= rn; nx++)
+        for (int ny = -rn; ny <= rn; ny++) {
+          if (std::hypot(nx, ny) > rn) continue;
+          double h = h_max * std::pow((1 - (double)std::hypot(nx, ny) / rn), pow_);
+          if (h > 1e-3) mask.push_back({{nx, ny, 0}, (int8_t)h});
+        }
+    } else {
+      int hn = (int)std::ceil(potential_radius[2] / res);
+      for (int nx = -rn; nx <= rn; nx++)
+        for (int ny = -rn; ny <= rn; ny++)
+          for (int nz = -hn; nz <= hn; nz++) {
+            if (std::hypot(nx, ny) > rn) continue;
+            double h = h_max * std::pow((1 - (double)std::hypot(nx, ny) / rn) * (1 - (double)std::abs(nz) / hn), pow_);
+            if (h > 1e-3) mask.push_back({{nx, ny, nz}, (int8_t)h});
+          }
+    }
+    int c1[3] = {0, 0, 0}, c2[3] = {map->nd[0], map->nd[1], dim == 3 ? map->nd[2] : 1};
+    double rnorm = 0;
+    for (int i = 0; i < dim; i++) rnorm += potential_map_range[i] * potential_map_range[i];
+    if (std::sqrt(rnorm) > 0) {
+      double lo[3], hi[3];
+      for (int i = 0; i < dim; i++) { lo[i] = pos[i] - potential_map_range[i]; hi[i] = pos[i] + potential_map_range[i]; }
+      map->float_to_int(lo, c1);
+      map->float_to_int(hi, c2);
+      for (int i = 0; i < dim; i++) {
+        if (c1[i] < 0) c1[i] = 0; else if (c1[i] >= map->nd[i]) c1[i] = map->nd[i] - 1;
+        if (c2[i] < 0) c2[i] = 0; else if (c2[i] >= map->nd[i]) c2[i] = map->nd[i] - 1;
+      }
+      if (dim == 2) { c1[2] = 0; c2[2] = 1; }
+    }
+    const std::vector<int8_t> src = map->data;
+    std::vector<int8_t> dmap = src;
+    for (int x = c1[0]; x < c2[0]; x++)
+      for (int y = c1[1]; y < c2[1]; y++)
+        for (int z = c1[2]; z < c2[2]; z++) {
+          int pn[3] = {x, y, z};
+          int idx = map->index(pn);
+          if (src[idx] > 0) {
+            dmap[idx] = H_MAX;
+            for (const auto &it : mask) {
+              int q[3] = {x + it.first[0], y + it.first[1], z + it.first[2]};
+              if (!map->outside(q)) { int qi = map->index(q); dmap[qi] = std::max(dmap[qi], it.second); }
+            }
+          }
+        }
+    map->data = dmap;
+    potential_map = dmap;
   }
 
   /* em:147-172.  Emits rows for every u when `trace` is given; succ lists hold only the entries the
@@ -653,6 +783,8 @@ int orc_planner_set_param(void *pp, const char *key, double v) {
   else if (k == "yaw_max") p->yaw_max = v; else if (k == "dt") p->dt = v; else if (k == "w") p->w = v;
   else if (k == "epsilon") p->eps = v; else if (k == "max_num") p->max_num = (int)v;
   else if (k == "tol_pos") p->tol_pos = v; else if (k == "tol_vel") p->tol_vel = v; else if (k == "tol_acc") p->tol_acc = v;
+  else if (k == "potential_weight") p->potential_weight = v; else if (k == "gradient_weight") p->gradient_weight = v;
+  else if (k == "pow") p->pow_ = v;
   else return -1;
   return 0;
 }
@@ -660,6 +792,33 @@ void orc_planner_set_controls(void *pp, const double *U, int n, int udim) {
   Planner *p = (Planner *)pp;
   p->U.clear();
   for (int i = 0; i < n; i++) p->U.emplace_back(U + (size_t)i * udim, U + (size_t)(i + 1) * udim);
+}
+
+void orc_planner_set_vec(void *pp, const char *key, const double *v) {
+  Planner *p = (Planner *)pp;
+  std::string k(key);
+  double *dst = k == "search_radius" ? p->search_radius : k == "potential_radius" ? p->potential_radius : p->potential_map_range;
+  for (int i = 0; i < p->dim; i++) dst[i] = v[i];
+}
+void orc_planner_set_search_region(void *pp, const double *path, int n, int dense) {
+  Planner *p = (Planner *)pp;
+  std::vector<std::array<double, 3>> pts(n);
+  for (int i = 0; i < n; i++) { pts[i] = {0, 0, 0}; for (int k = 0; k < p->dim; k++) pts[i][k] = path[(size_t)i * 3 + k]; }
+  p->set_search_region_path(pts, dense != 0);
+}
+void orc_planner_clear_shaping(void *pp) { Planner *p = (Planner *)pp; p->search_region.clear(); p->potential_map.clear(); }
+int64_t orc_planner_get_search_region(void *pp, uint8_t *out, int64_t cap) {
+  Planner *p = (Planner *)pp;
+  int64_t n = (int64_t)p->search_region.size();
+  for (int64_t i = 0; i < n && i < cap; i++) out[i] = p->search_region[i] ? 1 : 0;
+  return n;
+}
+void orc_planner_update_potential_map(void *pp, const double *pos) { ((Planner *)pp)->update_potential_map(pos); }
+int64_t orc_map_get_data(void *map, int8_t *out, int64_t cap) {
+  Map *m = (Map *)map;
+  int64_t n = (int64_t)m->data.size();
+  for (int64_t i = 0; i < n && i < cap; i++) out[i] = m->data[i];
+  return n;
 }
 
 int orc_plan(void *pp, const orc_waypoint *start, const orc_waypoint *goal, orc_result *out) {
@@ -730,6 +889,8 @@ int orc_plan_batch(void *pp, const orc_waypoint *starts, const orc_waypoint *goa
     local.tol_vel = base->tol_vel; local.tol_acc = base->tol_acc; local.v_max = base->v_max; local.a_max = base->a_max;
     local.j_max = base->j_max; local.yaw_max = base->yaw_max; local.dt = base->dt; local.eps = base->eps;
     local.max_num = base->max_num; local.U = base->U;
+    local.potential_map = base->potential_map; local.search_region = base->search_region;
+    local.potential_weight = base->potential_weight; local.gradient_weight = base->gradient_weight;
     for (int i = tid; i < n; i += nthreads) {
       local.plan(from_c(starts[i]), from_c(goals[i]));
       results[i] = local.last;

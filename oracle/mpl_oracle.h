@@ -76,10 +76,18 @@ int orc_map_float_to_int(void *map, const double *pt, int32_t *pn); /* returns l
 void *orc_planner_create(int dim);
 void orc_planner_destroy(void *p);
 void orc_planner_set_map(void *p, void *map);
-/* keys: "v_max" "a_max" "j_max" "yaw_max" "dt" "w" "epsilon" "max_num" "tol_pos" "tol_vel" "tol_acc" */
+/* keys: "v_max" "a_max" "j_max" "yaw_max" "dt" "w" "epsilon" "max_num" "tol_pos" "tol_vel" "tol_acc"
+ *       "potential_weight" "gradient_weight" "pow" */
 int orc_planner_set_param(void *p, const char *key, double v);
 void orc_planner_set_controls(void *p, const double *U, int n, int udim);
 
+/* cost shaping of env_map / MapPlanner: keys "search_radius" "potential_radius" "potential_map_range" */
+void orc_planner_set_vec(void *p, const char *key, const double *v);
+void orc_planner_set_search_region(void *p, const double *path, int n, int dense); /* map_planner.cpp:46-95; n rows of 3 doubles */
+void orc_planner_clear_shaping(void *p);
+int64_t orc_planner_get_search_region(void *p, uint8_t *out, int64_t cap);
+void orc_planner_update_potential_map(void *p, const double *pos);                 /* map_planner.cpp:286-391 (rewrites the map) */
+int64_t orc_map_get_data(void *map, int8_t *out, int64_t cap);
 int orc_plan(void *p, const orc_waypoint *start, const orc_waypoint *goal, orc_result *out);
 /* getters for the last orc_plan on this planner */
 int orc_get_actions(void *p, int32_t *actions, int cap);                 /* returns n_seg */

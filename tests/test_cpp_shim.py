@@ -10,18 +10,44 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(tmp_path):
+def _build(tmp_path, name="test_planner_2d"):
     from mpl_ros_b200.build import build_lib
     so = build_lib()
-    exe = str(tmp_path / "test_planner_2d")
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "test_planner_2d.cpp"), "-o", exe, so,
+    exe = str(tmp_path / name)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe, so,
                            "-Wl,-rpath," + os.path.dirname(so)])
     return exe
 
 
-def test_cpp_shim_compiles_and_links(tmp_path):
-    assert os.path.exists(_build(tmp_path))
+def _write_corridor(tmp_path):
+    from mpl_ros_b200 import maps
+    m = maps.load_fixture("corridor")
+    p = str(tmp_path / "corridor.bin")
+    with open(p, "wb") as f:
+        f.write(struct.pack("<2i", *m.dim.tolist()))
+        f.write(struct.pack("<2d", *m.origin.tolist()))
+        f.write(struct.pack("<d", m.res))
+        f.write(struct.pack("<2d", *m.extra["start"].tolist()))
+        f.write(struct.pack("<2d", *m.extra["goal"].tolist()))
+        f.write(m.data.tobytes())
+    return p
+
+
+@pytest.mark.parametrize("name", ["test_planner_2d", "test_distance_map_planner_2d"])
+def test_cpp_shim_compiles_and_links(tmp_path, name):
+    assert os.path.exists(_build(tmp_path, name))
+
+
+@pytest.mark.gpu
+def test_cpp_distance_map_planner_2d(tmp_path):
+    """tests/cpp/test_distance_map_planner_2d.cpp (the reference's test_distance_map_planner_2d.cpp flow) against the
+    oracle's answer for the same flow (tests/test_oracle_shaping.py pins it on the CPU)."""
+    exe = _build(tmp_path, "test_distance_map_planner_2d")
+    out = subprocess.check_output([exe, _write_corridor(tmp_path)]).decode()
+    assert "MPL Planner expanded states: 615" in out, out
+    assert "distance: cost 647.1000000000 pops 2732 segs 36" in out, out
+    assert "iterative: ok 1" in out, out
 
 
 @pytest.mark.gpu

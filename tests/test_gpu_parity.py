@@ -264,3 +264,34 @@ def test_synthetic_boxes_jrk125_batch():
     for i in range(n):
         assert_results_equal(rg[i], ro[i], i)
     assert pl.last_batch_stats()["tiers"] >= 1
+
+
+def test_full_bench_batch_parity():
+    """BASELINE configs[1] at FULL size: the 1024-query levine-256 batch of bench.py, every plan compared with the
+    oracle (status, cost, counters, pop-order hash, closed hash, action rows), plus size-independent invariants."""
+    import os
+    import bench
+    m = maps.levine256()
+    U = maps.make_U(1.0, 1, 3)
+    pl, op = make_pair(m, 3, dict(bench.PLAN_PARAMS), U)
+    s, g = bench.make_queries(m, 0)
+    so, go = oracle.make_waypoints(len(s)), oracle.make_waypoints(len(s))
+    for f in ("pos", "control"):
+        so[f], go[f] = s[f], g[f]
+    rg, ag, _ = pl.plan_batch(s, g, max_seg=bench.MAX_SEG)
+    ro, ao = op.plan_batch(so, go, nthreads=os.cpu_count() or 8, max_seg=bench.MAX_SEG)
+    for f in RESULT_FIELDS:
+        a, b = rg[f], ro[f]
+        if f == "cost":
+            assert np.array_equal(np.isinf(a), np.isinf(b)) and np.array_equal(a[np.isfinite(a)], b[np.isfinite(b)])
+        else:
+            assert np.array_equal(a, b), f
+    assert np.array_equal(ag, ao)
+    ok = rg["status"] == 0
+    # invariants: cost = w*dt*n_seg + sum of u^2*dt along the action row; exhausted searches closed every node
+    J = (U ** 2).sum(axis=1)
+    for i in np.flatnonzero(ok)[:200]:
+        acts = ag[i][: rg["n_seg"][i]]
+        assert rg["cost"][i] == 10.0 * rg["n_seg"][i] + J[acts].sum()
+    ex = rg["status"] == 3
+    assert np.all(rg["n_open"][ex] == 0) and np.all(rg["n_closed"][ex] == rg["n_nodes"][ex])
