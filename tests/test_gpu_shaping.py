@@ -213,7 +213,7 @@ def test_shaped_batch_parity():
     for i in range(n):
         assert_results_equal(rg[i], ro[i], ("shaped batch", i))
     assert np.array_equal(ag, ao)
-    assert (ro["status"] == 0).sum() > n // 4
+    assert (ro["status"] == 0).sum() >= 8 and (ro["status"] == 3).sum() >= 8  # both outcomes are exercised
 
 
 def test_shaping_errors():
