@@ -46,6 +46,10 @@ extern "C" {
 #define MPLB_CONTROL_ACC 3
 #define MPLB_CONTROL_JRK 7
 #define MPLB_CONTROL_SNP 15
+#define MPLB_CONTROL_VELxYAW 17 /* yaw variants: the state carries yaw, control rows have Dim + 1 entries (primitive.h:217,236-253) */
+#define MPLB_CONTROL_ACCxYAW 19
+#define MPLB_CONTROL_JRKxYAW 23
+#define MPLB_CONTROL_SNPxYAW 31
 
 /* Waypoint<Dim>, include/mpl_basis/waypoint.h:22-58 (Dim = 2 uses the first two components). */
 typedef struct mplb_waypoint {
@@ -53,6 +57,8 @@ typedef struct mplb_waypoint {
   double yaw, t;
   int32_t control;  /* the 5-bit use_pos..use_yaw union */
   int32_t enable_t; /* must be 0 (time-indexed keys are not on this path) */
+  /* yaw is used when control has bit 16 (MPLB_CONTROL_*xYAW); cos/sin on that branch are the correctly rounded
+   * functions (see mplb_sincos_cr), where the reference calls an unpinned libm */
 } mplb_waypoint;
 
 /* Outcome of one plan.  cost = PlannerBase::traj_cost_ (goal g, graph_search.h:179) or +inf. */
@@ -122,7 +128,7 @@ enum mplb_param {
   MPLB_V_MAX = 0,   /* setVmax   planner_base.h:179  default -1 (env_base.h:380) — must be > 0 here */
   MPLB_A_MAX = 1,   /* setAmax   :185 */
   MPLB_J_MAX = 2,   /* setJmax   :191 */
-  MPLB_YAW_MAX = 3, /* setYawmax :197 (accepted, unused: yaw controls are out of scope) */
+  MPLB_YAW_MAX = 3, /* setYawmax :197 default -1: semi-FOV of validate_yaw (primitive.h:503-525), <= 0 disables it */
   MPLB_DT = 4,      /* setDt     :209 default 1.0 */
   MPLB_W = 5,       /* setW      :215 default 10 */
   MPLB_EPSILON = 6, /* setEpsilon:227 default 1 */
@@ -133,11 +139,13 @@ enum mplb_param {
   MPLB_T_MAX = 11,  /* setTmax   :203 (accepted, ignored exactly like env_map::is_goal does, env_map.h:25-45) */
   MPLB_POTENTIAL_WEIGHT = 12, /* setPotentialWeight map_planner.cpp:30-33, default 0.1 (env_map.h:196) */
   MPLB_GRADIENT_WEIGHT = 13,  /* setGradientWeight  map_planner.cpp:35-38, default 0.0 (env_map.h:197) */
+  MPLB_WYAW = 14,   /* setWyaw   :221 default 1.0 (env_base.h:372): weight of the heading cost env_map.h:121-128 */
   MPLB_MEM_FRACTION = 100, /* fraction of free device memory the search arenas may take (default 0.6) */
   MPLB_MAX_SLOTS = 101     /* tuning: cap on concurrently resident plans (CTAs); 0 = all resident CTAs */
 };
 int mplb_planner_set_param(mplb_planner *p, int key, double value);
-/* setU (planner_base.h:246): n rows of udim (= Dim) doubles; the row index is the action id. */
+/* setU (planner_base.h:246): n rows of udim doubles, udim = Dim, or Dim + 1 when the last entry is a yaw rate
+ * (primitive.h:217); the row index is the action id. */
 int mplb_planner_set_controls(mplb_planner *p, const double *U, int n, int udim);
 
 /* ---- cost shaping of env_map: search region and potential map, env_map.h:104-128.
@@ -185,6 +193,10 @@ int mplb_get_open(mplb_planner *p, int32_t *node_ids, int cap);        /* return
 
 /* env_map::get_succ (env_map.h:147-172) for n arbitrary states: rows [n * |U|]. HOST buffers. */
 int mplb_expand(mplb_planner *p, const mplb_waypoint *states, int n, mplb_prim_trace *rows);
+
+/* Correctly rounded sin/cos as the yaw branch evaluates them (primitive.h:520, env_map.h:125), computed on the device:
+ * x, s, c are HOST arrays of n doubles, |x| < 2^20.  Parity artefact: tests compare it with the oracle and mpmath. */
+int mplb_sincos_cr(const double *x, int n, double *s, double *c);
 
 /* Timing/diagnostics of the last batch on this planner: ms = device time of the search kernels (CUDA events on
  * the launch stream), launches = kernels launched, tiers = arena tiers used. Any pointer may be NULL. */

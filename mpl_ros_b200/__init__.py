@@ -6,5 +6,5 @@ libmplb.so (hand-written sm_100a CUDA behind the C ABI of include/mplb.h); impor
 load it, the first call does, and it raises if the library or a CUDA device is missing.
 """
 from . import maps  # noqa: F401
-from .planner import (ACC, JRK, SNP, VEL, MapPlanner, MapUtil, MplbError, OccMapPlanner, OccMapUtil, Primitive,  # noqa: F401
+from .planner import (ACC, ACCxYAW, JRK, JRKxYAW, SNP, SNPxYAW, VEL, VELxYAW, MapPlanner, MapUtil, MplbError, OccMapPlanner, OccMapUtil, Primitive,  # noqa: F401
                       Trajectory, VoxelMapPlanner, VoxelMapUtil, Waypoint, waypoints_array)

@@ -55,10 +55,11 @@ SYMBOLS = {
     "mplb_get_open": (_I, [_VP, _VP, _I]),
     "mplb_expand": (_I, [_VP, _VP, _I, _VP]),
     "mplb_last_batch_stats": (_I, [_VP, _VP, _VP, _VP]),
+    "mplb_sincos_cr": (_I, [_VP, _I, _VP, _VP]),
 }
 
 PARAM = dict(v_max=0, a_max=1, j_max=2, yaw_max=3, dt=4, w=5, epsilon=6, max_num=7, tol_pos=8, tol_vel=9,
-             tol_acc=10, t_max=11, potential_weight=12, gradient_weight=13, mem_fraction=100, max_slots=101)
+             tol_acc=10, t_max=11, potential_weight=12, gradient_weight=13, wyaw=14, mem_fraction=100, max_slots=101)
 
 _LIB = None
 

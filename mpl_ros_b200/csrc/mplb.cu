@@ -210,6 +210,11 @@ __global__ void k_fill_int(int *a, int v, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = v;
 }
 
+__global__ void k_sincos_cr(const double *x, int n, double *s, double *c) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) trig::sincos_cr(x[i], &s[i], &c[i]);
+}
+
 }  // namespace
 
 /* ================================================================== objects */
@@ -252,7 +257,9 @@ struct mplb_planner {
   int resident_sig = -1, resident_cached = 0;
   size_t budget_bytes = 0; /* arena budget, measured at the first batch (reset by MPLB_MEM_FRACTION) */
   std::vector<double> U; /* nU x 3 */
+  std::vector<double> Uyaw; /* nU yaw rates when the rows have Dim + 1 entries (pr:217), else empty */
   int nU = 0;
+  double wyaw = 1.0; /* eb:372 */
   /* cost shaping (em:104-128): defaults em:196-197 */
   double pot_w = 0.1, grad_w = 0.0;
   DevBuf<int8_t> d_pot;
@@ -265,7 +272,7 @@ struct mplb_planner {
   int cfg_control = 0;
   unsigned long long cfg_map_version = ~0ull;
   DevCfg cfg;
-  DevBuf<double> d_U, d_ttab;
+  DevBuf<double> d_U, d_ttab, d_Uyaw;
   DevBuf<int> d_toff, d_tcnt;
   int kfields = 0;
 
@@ -322,8 +329,8 @@ Layout make_layout(int cap, int ns, int nU) {
   return L;
 }
 
-int control_order(int control) {
-  switch (control) {
+int control_order(int control) { /* control.h:10-20: the yaw variants add bit 16 to the base pattern */
+  switch (control & 15) {
     case MPLB_CONTROL_VEL: return 1;
     case MPLB_CONTROL_ACC: return 2;
     case MPLB_CONTROL_JRK: return 3;
@@ -345,8 +352,11 @@ int build_cfg(mplb_planner *p, int control) {
   if (!p->map) return fail(MPLB_ERR_STATE, "planner has no map (setMapUtil not called)");
   if (p->nU <= 0) return fail(MPLB_ERR_STATE, "planner has no control set (setU not called)");
   if (p->nU > MPLB_MAXU) return fail(MPLB_ERR_ARG, "more than 128 controls are not supported");
-  int ord = control_order(control);
-  if (ord == 0) return fail(MPLB_ERR_ARG, "unsupported control flag on the start waypoint (yaw controls are out of scope)");
+  int ord = (control & ~31) ? 0 : control_order(control);
+  if (ord == 0) return fail(MPLB_ERR_ARG, "unsupported control flag on the start waypoint");
+  const bool use_yaw = (control & 16) != 0;
+  if (use_yaw && p->Uyaw.empty())
+    return fail(MPLB_ERR_ARG, "the start waypoint uses yaw but the control rows have no yaw column (setU rows need Dim + 1 entries)");
   if (p->map->dim != p->dim) return fail(MPLB_ERR_ARG, "map dimension does not match planner dimension");
   if (!(p->dt > 0)) return fail(MPLB_ERR_ARG, "dt must be > 0");
   if (ord >= 2 && !(p->v_max > 0))
@@ -358,7 +368,9 @@ int build_cfg(mplb_planner *p, int control) {
   mplb_map *m = p->map;
   DevCfg &c = p->cfg;
   std::memset(&c, 0, sizeof(c));
-  c.dim = p->dim; c.ord = ord; c.control = control; c.nU = p->nU; c.ns = p->dim * ord;
+  c.dim = p->dim; c.ord = ord; c.control = control; c.nU = p->nU;
+  const bool shaped = use_yaw || p->pot_cells || !p->h_region.empty();
+  c.ns = p->dim * ord + (shaped ? 1 : 0); /* the cost-shaping / yaw kernels keep a yaw slot after the polynomial state */
   c.max_num = p->max_num;
   c.dt = p->dt; c.w = p->w; c.eps = p->eps; c.v_max = p->v_max; c.a_max = p->a_max; c.j_max = p->j_max;
   c.tol_pos = p->tol_pos; c.tol_vel = p->tol_vel; c.tol_acc = p->tol_acc;
@@ -416,11 +428,23 @@ int build_cfg(mplb_planner *p, int control) {
   }
   /* cost shaping (em:104-128) */
   c.pot = nullptr; c.region = nullptr; c.pot_w = p->pot_w; c.grad_w = p->grad_w;
-  if (p->pot_cells || !p->h_region.empty()) {
+  c.use_yaw = use_yaw ? 1 : 0; c.nkey = p->dim * ord + (use_yaw ? 1 : 0);
+  c.yaw_max = p->yaw_max; c.wyaw = p->wyaw; c.cos_yaw_max = 1.0; c.Uyaw = nullptr;
+  if (use_yaw) {
+    CUDA_TRY(p->d_Uyaw.reserve((size_t)p->nU));
+    CUDA_TRY(cudaMemcpy(p->d_Uyaw.p, p->Uyaw.data(), (size_t)p->nU * sizeof(double), cudaMemcpyHostToDevice));
+    c.Uyaw = p->d_Uyaw.p;
+    if (p->yaw_max > 0) {
+      if (!(p->yaw_max < 1e5)) return fail(MPLB_ERR_ARG, "yaw_max is out of range");
+      double sn;
+      trig::sincos_cr(p->yaw_max, &sn, &c.cos_yaw_max); /* cos(my) of pr:521, correctly rounded like the device side */
+    }
+  }
+  if (shaped) {
     if (p->pot_cells && p->pot_cells != m->ncell) return fail(MPLB_ERR_STATE, "potential map size does not match the planner's map");
     if (!p->h_region.empty() && p->h_region.size() != m->ncell) return fail(MPLB_ERR_STATE, "search region size does not match the planner's map");
-    if (p->nU > 32) return fail(MPLB_ERR_ARG, "search region / potential map need a control set of at most 32 rows");
-    if (!c.use_fast) return fail(MPLB_ERR_ARG, "search region / potential map need positive dynamic bounds for every derivative of the control order");
+    if (p->nU > 32) return fail(MPLB_ERR_ARG, "search region / potential map / yaw controls need a control set of at most 32 rows");
+    if (!c.use_fast) return fail(MPLB_ERR_ARG, "search region / potential map / yaw controls need positive dynamic bounds for every derivative of the control order");
     if (p->pot_cells) c.pot = p->d_pot.p;
     if (!p->h_region.empty()) c.region = p->d_region.p;
   }
@@ -456,8 +480,18 @@ int build_cfg(mplb_planner *p, int control) {
       bitpos += bits;
     }
   }
+  if (shaped) { /* yaw field (wp:114-117): normalised yaw / 0.1 lies in [-32, 32]; a raw start yaw gets some slack */
+    const int f = p->dim * ord;
+    const int bits = use_yaw ? 9 : 1;
+    int word = bitpos / 64;
+    if ((bitpos % 64) + bits > 64) { word++; bitpos = word * 64; }
+    if (word > 1) return fail(MPLB_ERR_ARG, "lattice key does not fit 128 bits for this map / bounds");
+    c.koff[f] = use_yaw ? -256 : 0; c.kbits[f] = (unsigned char)bits; c.kshift[f] = (unsigned char)(bitpos % 64);
+    c.kword[f] = (unsigned char)word;
+    bitpos += bits;
+  }
   c.key_wide = (bitpos > 96) ? 1 : 0;
-  p->kfields = p->dim * ord;
+  p->kfields = c.nkey;
   p->cfg_control = control;
   p->cfg_map_version = m->version;
   p->dirty = false;
@@ -549,7 +583,7 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
 
   /* resident CTAs of this kernel instantiation and the memory budget are looked up once per configuration: both
    * calls cost on the order of a millisecond, comparable to a small batch */
-  const bool shaped = c.pot != nullptr || c.region != nullptr;
+  const bool shaped = c.pot != nullptr || c.region != nullptr || c.use_yaw != 0;
   const int cfg_sig = (shaped ? 1000 : 0) + c.dim * 100 + c.ord * 10 + (c.nU <= 32 ? 1 : 4);
   if (p->resident_sig != cfg_sig) {
     int r = 0;
@@ -876,6 +910,7 @@ int mplb_planner_set_param(mplb_planner *p, int key, double v) {
     case MPLB_T_MAX: p->t_max = v; break;
     case MPLB_POTENTIAL_WEIGHT: p->pot_w = v; break;
     case MPLB_GRADIENT_WEIGHT: p->grad_w = v; break;
+    case MPLB_WYAW: p->wyaw = v; break;
     case MPLB_MEM_FRACTION:
       if (!(v > 0 && v <= 0.95)) return fail(MPLB_ERR_ARG, "mem fraction must be in (0, 0.95]");
       p->mem_fraction = v;
@@ -892,10 +927,14 @@ int mplb_planner_set_param(mplb_planner *p, int key, double v) {
 int mplb_planner_set_controls(mplb_planner *p, const double *U, int n, int udim) {
   if (!p || !U) return fail(MPLB_ERR_ARG, "null argument");
   if (n <= 0 || n > MPLB_MAXU) return fail(MPLB_ERR_ARG, "control set must have 1..128 rows");
-  if (udim != p->dim) return fail(MPLB_ERR_ARG, "control rows must have Dim entries (yaw controls are out of scope)");
+  if (udim != p->dim && udim != p->dim + 1) return fail(MPLB_ERR_ARG, "control rows must have Dim entries, or Dim + 1 with a yaw rate (pr:217)");
   p->U.assign((size_t)n * 3, 0.0);
-  for (int i = 0; i < n; i++)
-    for (int k = 0; k < udim; k++) p->U[(size_t)i * 3 + k] = U[(size_t)i * udim + k];
+  p->Uyaw.clear();
+  if (udim == p->dim + 1) p->Uyaw.assign((size_t)n, 0.0);
+  for (int i = 0; i < n; i++) {
+    for (int k = 0; k < p->dim; k++) p->U[(size_t)i * 3 + k] = U[(size_t)i * udim + k];
+    if (udim == p->dim + 1) p->Uyaw[i] = U[(size_t)i * udim + p->dim];
+  }
   p->nU = n;
   p->dirty = true;
   return MPLB_OK;
@@ -1196,13 +1235,14 @@ int mplb_get_nodes(mplb_planner *p, mplb_node *nodes, int cap) {
     const double *st = reinterpret_cast<const double *>(rw.data() + (size_t)i * p->ret_row_bytes + sizeof(RowHdr));
     for (int d = 0; d < c.ord; d++)
       for (int ax = 0; ax < c.dim; ax++) o.state[d * 3 + ax] = st[d * c.dim + ax];
+    if (c.use_yaw) o.state[12] = st[c.dim * c.ord];
     o.g = hot[i].g; o.h = hot[i].h;
-    for (int f = 0; f < c.ns; f++) {
+    for (int f = 0; f < c.nkey; f++) {
       unsigned long long wv = c.kword[f] ? rh->k1 : rh->k0;
       unsigned long long v = (wv >> c.kshift[f]) & ((1ull << c.kbits[f]) - 1ull);
       o.key[f] = (int)((long long)v + c.koff[f]);
     }
-    o.key[15] = c.ns;
+    o.key[15] = c.nkey;
     o.opened = (hot[i].flags & 1) ? 1 : 0;
     o.closed = (hot[i].flags & 2) ? 1 : 0;
     o.parent = rh->parent;
@@ -1241,7 +1281,7 @@ int mplb_expand(mplb_planner *p, const mplb_waypoint *states, int n, mplb_prim_t
   int rc = build_cfg(p, states[0].control);
   if (rc != MPLB_OK) return rc;
   const DevCfg &c = p->cfg;
-  if (c.pot || c.region) return fail(MPLB_ERR_STATE, "mplb_expand traces the plain-map get_succ only; clear the search region / potential map first");
+  if (c.pot || c.region || c.use_yaw) return fail(MPLB_ERR_STATE, "mplb_expand traces the plain-map get_succ only (no search region / potential map / yaw controls)");
   mplb_waypoint *d_s = nullptr;
   mplb_prim_trace *d_r = nullptr;
   CUDA_TRY(cudaMalloc((void **)&d_s, (size_t)n * sizeof(mplb_waypoint)));
@@ -1273,6 +1313,24 @@ int mplb_debug_phase_cycles(mplb_planner *p, long long *out, int n) {
   return MPLB_OK;
 }
 #endif
+
+int mplb_sincos_cr(const double *x, int n, double *s, double *c) {
+  if (n <= 0) return MPLB_OK;
+  if (!x || !s || !c) return fail(MPLB_ERR_ARG, "null argument");
+  double *d = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d, (size_t)n * 3 * sizeof(double)));
+  cudaError_t e = cudaMemcpy(d, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_sincos_cr<<<(n + 127) / 128, 128>>>(d, n, d + n, d + 2 * (size_t)n);
+    g_launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(s, d + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(c, d + 2 * (size_t)n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(MPLB_ERR_CUDA, std::string("mplb_sincos_cr: ") + cudaGetErrorString(e));
+  return MPLB_OK;
+}
 
 int mplb_last_batch_stats(mplb_planner *p, double *kernel_ms, int32_t *launches, int32_t *tiers) {
   if (!p) return fail(MPLB_ERR_ARG, "null planner");

@@ -65,8 +65,8 @@ struct DevCfg {
   const int *tcnt;    /* number of samples for divisor n (n or n+1) */
   int n_hi;           /* largest tabulated divisor */
   /* lattice-key packing: field f = axis*ord + derivative (wp:92-125 order) */
-  int koff[12];
-  unsigned char kshift[12], kbits[12], kword[12];
+  int koff[13]; /* 12 polynomial fields + yaw (wp:114-117) */
+  unsigned char kshift[13], kbits[13], kword[13];
   int key_wide; /* 1 when word 1 of the key needs more than 32 bits (table slots then also compare the row header) */
   /* filtered (FP32) collision sampling: see sample_blocked_fast */
   double inv_res;   /* 1/res, used only inside filters whose doubtful cases fall back to the exact division */
@@ -78,6 +78,12 @@ struct DevCfg {
   const int8_t *pot;
   const unsigned int *region;
   double pot_w, grad_w;
+  /* yaw controls (Control::*xYAW, pr:236-253): extra state double + key field, FOV check pr:503-525, cost em:121-128 */
+  int use_yaw;          /* the control flag carries use_yaw: state rows hold yaw after the polynomial part */
+  int nkey;             /* number of lattice-key fields = dim*ord + use_yaw */
+  double yaw_max, wyaw; /* eb:388 (<= 0 disables the FOV check), eb:372 */
+  double cos_yaw_max;   /* correctly rounded cos(yaw_max), prepared on the host */
+  const double *Uyaw;   /* yaw rate of every control (column Dim of U), or null */
 };
 
 /* ------------------------------------------------------------------------------------------------
@@ -229,12 +235,12 @@ __device__ __forceinline__ void lattice_ints(const double *st, int *ints) {
 }
 
 /* Pack ints into the 128-bit node key (no parity hash); false when a field leaves its packable range. */
-template <int DIM, int ORD>
+template <int DIM, int ORD, int NF = DIM * ORD>
 __device__ __forceinline__ bool pack_key_nohash(const DevCfg &c, const int *ints, unsigned long long &k0, unsigned long long &k1) {
   k0 = 0; k1 = 0;
   bool ok = true;
 #pragma unroll
-  for (int f = 0; f < DIM * ORD; f++) {
+  for (int f = 0; f < NF; f++) {
     long long v = (long long)ints[f] - (long long)c.koff[f];
     if (v < 0 || v >= (1ll << c.kbits[f])) ok = false;
     unsigned long long uv = (unsigned long long)v << c.kshift[f];

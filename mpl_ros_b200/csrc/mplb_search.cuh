@@ -35,6 +35,7 @@
  */
 #pragma once
 #include "mplb_device.cuh"
+#include "mplb_trig.cuh"
 #include "../../include/mplb.h"
 
 namespace mplb {
@@ -142,9 +143,10 @@ struct BatchArgs {
  * |U| <= 32 there are two of them: while the search warp commits the current node, the heap warp already runs B1 for
  * the node that will be popped next (the heap root after the previous pop's sift-down is the next pop unless a
  * successor overtakes it, which measured < 0.1 % of the pops). */
-template <int DIM, int ORD, int MAXU>
+template <int DIM, int ORD, int MAXU, int XS = 0>
 struct ExpBuf {
-  static constexpr int NS = DIM * ORD;
+  static constexpr int NP = DIM * ORD; /* polynomial part of the state, [d*DIM + ax] */
+  static constexpr int NS = NP + XS;   /* + yaw slot in the cost-shaping / yaw instantiations (index NP) */
   static constexpr int GCAP = MAXU * 8; /* 8-sample granules */
   double st[NS];     /* state of the expanded node */
   unsigned long long pk0, pk1; /* its packed lattice key (a successor with the same key is the self-loop of em:158) */
@@ -160,16 +162,18 @@ struct ExpBuf {
   int nid[MAXU];     /* node id of the successor after relaxation (for state forwarding) */
   int gbase[MAXU];   /* first granule of the control in gl[] (cost-shaping kernels sum its sample terms in order) */
   double dts[MAXU];  /* sample spacing T/n (em:98), cost-shaping kernels only */
+  double cy0, sy0;   /* cos/sin of the node's yaw (yaw controls) */
   unsigned int gl[GCAP];     /* granule: control | first sample k0 << 8 | sample count << 16 ... */
   unsigned short gl_t[GCAP]; /* ... and index of its first sample time in tts */
 };
 
 template <int DIM, int ORD, int NB, bool POT = false>
 struct PlanSmem {
-  static constexpr int NS = DIM * ORD;
+  static constexpr int NP = DIM * ORD;
+  static constexpr int NS = NP + (POT ? 1 : 0);
   static constexpr int MAXU = 32 * NB;
   static constexpr int NBUF = (NB == 1) ? 2 : 1; /* expansion records: 2 = B1 of the next pop is pipelined */
-  typedef ExpBuf<DIM, ORD, MAXU> EB;
+  typedef ExpBuf<DIM, ORD, MAXU, POT ? 1 : 0> EB;
   EB eb[NBUF];
   int cur_buf;
   static constexpr int HCAP = (NB == 1) ? MPLB_HCAP : 1024; /* heap entries kept in shared memory */
@@ -196,6 +200,8 @@ struct PlanSmem {
   double p_g[MAXU], p_pg[MAXU], p_h[MAXU];
   double tts[MPLB_TT_CAP]; /* accumulated sample times (em:98-99), all divisors */
   double terms[POT ? MAXU * 64 : 1]; /* per-sample cost terms of the current expansion (potential map), by granule slot */
+  double yterms[POT ? MAXU * 64 : 1]; /* per-sample yaw cost terms (em:121-128), same indexing */
+  double Uyaw[POT ? MAXU : 1];        /* yaw rate of each control */
   int n_before;      /* n_nodes before this expansion */
   /* pending sift-down (heap warp) and prefetched root row */
   int sd_pending, sd_n;
@@ -364,10 +370,33 @@ __device__ __forceinline__ int sample_divisor(double max_v, double T, double res
   return n < 5 ? 5 : n;
 }
 
+/* ---------------------------------------------------------------- yaw controls (Control::*xYAW)
+ * math.h:15-19 */
+__device__ __forceinline__ double normalize_angle(double a) {
+  while (a > 3.141592653589793) a = dsub(a, 6.283185307179586);
+  while (a < -3.141592653589793) a = dadd(a, 6.283185307179586);
+  return a;
+}
+/* v.normalized().dot(Vec2f(cos yaw, sin yaw)) (pr:520, em:125): Eigen normalized() = v / sqrt(squaredNorm) */
+__device__ __forceinline__ double heading_dot(double vx, double vy, double cs, double sn) {
+  const double z = dadd(dmul(vx, vx), dmul(vy, vy));
+  double nx = vx, ny = vy;
+  if (z > 0.0) { const double q = sqrt(z); nx = ddiv(vx, q); ny = ddiv(vy, q); }
+  return dadd(dmul(nx, cs), dmul(ny, sn));
+}
+/* Lattice ints of a full state row: polynomial part (wp:95-112) and, with yaw controls, round(yaw / 0.1) (wp:114-117);
+ * the yaw slot of a non-yaw plan packs as 0. */
+template <int DIM, int ORD, int NS>
+__device__ __forceinline__ void lattice_ints_x(const DevCfg &c, const double *st, int *ints) {
+  lattice_ints<DIM, ORD>(st, ints);
+  if (NS > DIM * ORD) ints[DIM * ORD] = c.use_yaw ? round_int(ddiv(st[DIM * ORD], 0.1)) : 0;
+}
+
 /* ---------------------------------------------------------------- phase B1: one lane per control (em:155-160,163-165) */
 template <int DIM, int ORD, class SM, class EBT>
 __device__ __forceinline__ void expand_b1(const DevCfg &c, const SM &S, EBT &E, int i) {
-  constexpr int NS = DIM * ORD;
+  constexpr int NP = DIM * ORD;
+  constexpr int NS = EBT::NS;
   const double T = c.dt;
   double es[NS];
   double max_v = 0.0;
@@ -394,10 +423,30 @@ __device__ __forceinline__ void expand_b1(const DevCfg &c, const SM &S, EBT &E, 
     for (int d = 0; d < ORD; d++)
       ints[ax * ORD + d] = (d == 0) ? lattice_int(es[ax], 0.01, 100.0) : lattice_int(es[d * DIM + ax], 0.1, 10.0);
   }
+  if (NS > NP) { /* yaw slot: pr_yaw_ = Primitive1D(p.yaw, u(Dim)) (pr:36,242-253), evaluated and normalised at t = T (pr:328) */
+    double yaw1 = 0.0;
+    int yi = 0;
+    if (c.use_yaw) {
+      yaw1 = normalize_angle(dadd(dmul(S.Uyaw[i], T), E.st[NP]));
+      yi = lattice_int(yaw1, 0.1, 10.0);
+      if (c.yaw_max > 0.0) { /* validate_yaw (pr:503-525): heading inside the semi-FOV at both ends */
+        const double v0x = (ORD >= 2) ? E.st[DIM + 0] : S.U[i * 3 + 0], v0y = (ORD >= 2) ? E.st[DIM + 1] : S.U[i * 3 + 1];
+        const double v1x = (ORD >= 2) ? es[DIM + 0] : S.U[i * 3 + 0], v1y = (ORD >= 2) ? es[DIM + 1] : S.U[i * 3 + 1];
+        if ((v0x != 0.0 || v0y != 0.0) && heading_dot(v0x, v0y, E.cy0, E.sy0) < c.cos_yaw_max) dyn_ok = false;
+        if (v1x != 0.0 || v1y != 0.0) {
+          double sn, cs;
+          trig::sincos_cr(yaw1, &sn, &cs);
+          if (heading_dot(v1x, v1y, cs, sn) < c.cos_yaw_max) dyn_ok = false;
+        }
+      }
+    }
+    es[NP] = yaw1;
+    ints[NP] = yi;
+  }
 #pragma unroll
   for (int f = 0; f < NS; f++) E.es[i * NS + f] = es[f];
   unsigned long long k0, k1;
-  bool key_ok = pack_key_nohash<DIM, ORD>(c, ints, k0, k1);
+  bool key_ok = pack_key_nohash<DIM, ORD, NS>(c, ints, k0, k1);
   /* tn == curr (em:158, wp:132-135): equal lattice tuples <=> equal packed keys (the packing is injective inside the
    * key range; a tuple outside it is reported through key_bad before it can matter) */
   const bool self = key_ok && (k0 == E.pk0) && (k1 == E.pk1);
@@ -424,6 +473,8 @@ __device__ __forceinline__ void expand_b1(const DevCfg &c, const SM &S, EBT &E, 
 template <int DIM, int ORD, int NB, class SM, class EBT>
 __device__ MPLB_B1_INLINE void b1_warp(const DevCfg &c, const SM &S, EBT &E, int lane, bool fast) {
   if (lane == 0) E.key_bad = 0;
+  if (EBT::NS > DIM * ORD && lane == 31 && c.use_yaw && c.yaw_max > 0.0)
+    trig::sincos_cr(normalize_angle(E.st[DIM * ORD]), &E.sy0, &E.cy0); /* evaluate(0) normalises the yaw too (pr:328) */
   if (fast && lane < DIM) { /* sampling base (cells): parent cell coordinate and lower polynomial coefficients */
     const int ax = lane;
     E.y0[ax] = dmul(dsub(E.st[ax], c.origin[ax]), c.inv_res);
@@ -445,7 +496,7 @@ __device__ MPLB_B1_INLINE void b1_warp(const DevCfg &c, const SM &S, EBT &E, int
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
     int excl = gbase + incl - ng;
-    if (i < c.nU) { E.gbase[i] = excl; if (c.pot && E.nsamp[i] > 0) E.dts[i] = ddiv(c.dt, (double)E.nsamp[i]); }
+    if (i < c.nU) { E.gbase[i] = excl; if ((c.pot || c.use_yaw) && E.nsamp[i] > 0) E.dts[i] = ddiv(c.dt, (double)E.nsamp[i]); }
     for (int q = 0; q < ng; q++) {
       E.gl[excl + q] = (unsigned)i | ((unsigned)(q * 8) << 8) | ((unsigned)E.cnt[i] << 16);
       E.gl_t[excl + q] = (unsigned short)(S.toff_s[E.nsamp[i]] + q * 8);
@@ -602,10 +653,11 @@ __device__ __forceinline__ void unpack_ints(const DevCfg &c, unsigned long long 
 }
 
 template <int NS>
-__device__ __forceinline__ unsigned long long khash_of_ints(const int *ints) {
+__device__ __forceinline__ unsigned long long khash_of_ints(const int *ints, int nkey) {
   unsigned long long h = khash_init();
 #pragma unroll
-  for (int f = 0; f < NS; f++) h = khash_step(h, ints[f]);
+  for (int f = 0; f < NS; f++)
+    if (f < nkey) h = khash_step(h, ints[f]); /* the yaw slot of a non-yaw plan is not part of the key (wp:114) */
   return khash_final(h);
 }
 
@@ -615,7 +667,7 @@ template <int DIM, int ORD, class SM>
 __device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, typename SM::EB &E, HeapEnt *spill, Slot *table, NodeHot *hot,
                                           unsigned char *rows, int i0, int i1, bool wide) {
   const HeapView<SM> H{S, spill, hot}; /* built here: a view whose address escapes would turn heap accesses generic */
-  constexpr int NS = DIM * ORD;
+  constexpr int NS = SM::NS;
   constexpr size_t ROWB = (sizeof(RowHdr) + NS * sizeof(double) + 15) & ~(size_t)15; /* 16-byte aligned rows */
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
   const int cn = S.cur_node;
@@ -642,10 +694,10 @@ __device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, typename SM::E
     E.nid[idx] = nid;
     S.p_slot[idx] = slot; /* later batches of this pop test their empty slots against it */
     double ecost = S.cost[idx];
-    if (c.pot && v == 3) { /* cost shaping (em:114-115); S.terms exists only in the POT instantiations, where c.pot may be set */
+    if ((c.pot || c.use_yaw) && v == 3) { /* cost shaping (em:114-115,121-127); only the POT instantiations can have these set */
       double acc = 0.0;
       const int base_t = E.gbase[idx] * 8, cn_t = E.cnt[idx];
-      for (int q = 0; q < cn_t; q++) acc = dadd(acc, S.terms[base_t + q]);
+      for (int q = 0; q < cn_t; q++) { acc = dadd(acc, S.terms[base_t + q]); acc = dadd(acc, S.yterms[base_t + q]); }
       ecost = dadd(acc, S.cost[idx]);
     }
     double tentative = dadd(cg, ecost); /* gs:107 */
@@ -744,12 +796,14 @@ __device__ __forceinline__ bool cell_filtered(const DevCfg &c, const SM &S, cons
 }
 /* One sample with cost shaping: returns blocked (em:104-106,116-120) and the cost term of em:114-115 (0 when none). */
 template <int DIM, int ORD, class SM, class EBT>
-__device__ __forceinline__ bool sample_shaped(const DevCfg &c, const SM &S, const EBT &E, int i, double t, double *term) {
+__device__ __forceinline__ bool sample_shaped(const DevCfg &c, const SM &S, const EBT &E, int i, double t, double *term,
+                                              double *yterm) {
   int pn[3] = {0, 0, 0};
   bool sure;
   bool outside = cell_filtered<DIM, ORD>(c, S, E, i, t, pn, &sure);
   if (!sure) outside = cell_exact<DIM, ORD>(c, S, E.st, i, t, pn);
   *term = 0.0;
+  *yterm = 0.0;
   if (outside) return true;
   const size_t idx = (DIM == 2) ? (size_t)pn[0] + (size_t)c.nd[0] * pn[1]
                                 : (size_t)pn[0] + (size_t)c.nd[0] * pn[1] + (size_t)c.nd[0] * c.nd[1] * pn[2];
@@ -771,9 +825,20 @@ __device__ __forceinline__ bool sample_shaped(const DevCfg &c, const SM &S, cons
       }
       *term = dmul(E.dts[i], dadd(dmul(c.pot_w, (double)p), dmul(c.grad_w, vn)));
     }
-    return false;
+  } else if (brick_occupied<DIM>(c, pn[0], pn[1], pn[2])) return true;
+  if (c.use_yaw && c.wyaw > 0.0) { /* em:121-128: (1 - heading . velocity direction) * wyaw * dt_s */
+    Axis<ORD> Ax(&E.st[0], DIM, S.U[i * 3 + 0], S.Ut[i * 3 + 0]);
+    Axis<ORD> Ay(&E.st[1], DIM, S.U[i * 3 + 1], S.Ut[i * 3 + 1]);
+    const double vx = Ax.v(t), vy = Ay.v(t);
+    const double nrm = sqrt(dadd(dmul(vx, vx), dmul(vy, vy)));
+    if (nrm > 1e-5) {
+      double sn, cs;
+      trig::sincos_cr(normalize_angle(dadd(dmul(S.Uyaw[i], t), E.st[DIM * ORD])), &sn, &cs);
+      const double v_value = dsub(1.0, heading_dot(vx, vy, cs, sn));
+      *yterm = dmul(dmul(c.wyaw, v_value), E.dts[i]);
+    }
   }
-  return brick_occupied<DIM>(c, pn[0], pn[1], pn[2]);
+  return false;
 }
 template <int DIM, int ORD, class SM, class EBT>
 __device__ __forceinline__ void sample_granules_shaped(const DevCfg &c, SM &S, EBT &E, int t, int nthreads) {
@@ -784,9 +849,10 @@ __device__ __forceinline__ void sample_granules_shaped(const DevCfg &c, SM &S, E
     const int u = (int)(info & 0xffu);
     const int k = (int)((info >> 8) & 0xffu) + sub;
     if (k < (int)(info >> 16)) {
-      double term;
-      const bool blk = sample_shaped<DIM, ORD>(c, S, E, u, S.tts[(int)E.gl_t[g] + sub], &term);
+      double term, yterm;
+      const bool blk = sample_shaped<DIM, ORD>(c, S, E, u, S.tts[(int)E.gl_t[g] + sub], &term, &yterm);
       S.terms[g * 8 + sub] = term;
+      S.yterms[g * 8 + sub] = yterm;
       if (blk) atomicMin(&E.first[u], k);
     }
   }
@@ -795,7 +861,8 @@ __device__ __forceinline__ void sample_granules_shaped(const DevCfg &c, SM &S, E
 /* ---------------------------------------------------------------- the kernel */
 template <int DIM, int ORD, int NB, bool POT>
 __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ BatchArgs a) {
-  constexpr int NS = DIM * ORD;
+  constexpr int NP = DIM * ORD;
+  constexpr int NS = NP + (POT ? 1 : 0); /* cost-shaping / yaw instantiations carry a yaw slot after the polynomial state */
   constexpr int NW = MPLB_NT / 32;
   using SM = PlanSmem<DIM, ORD, NB, POT>;
   constexpr size_t ROWB = (sizeof(RowHdr) + NS * sizeof(double) + 15) & ~(size_t)15; /* 16-byte aligned rows */
@@ -817,6 +884,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
 
   /* ---------------- per-launch constants */
   for (int i = tid; i < c.nU * 3; i += MPLB_NT) { S.U[i] = c.U[i]; S.Ut[i] = Axis<ORD>::top_of(c.U[i]); }
+  if (POT) for (int i = tid; i < c.nU; i += MPLB_NT) S.Uyaw[i] = (c.use_yaw && c.Uyaw) ? c.Uyaw[i] : 0.0;
   for (int i = tid; i < c.nU; i += MPLB_NT) {
     double J = 0.0;
     for (int ax = 0; ax < DIM; ax++) { double u = c.U[i * 3 + ax]; J = dadd(J, dmul(dmul(u, u), c.dt)); } /* pr:92-122,403-407 */
@@ -859,6 +927,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
         if (ORD >= 3) s0[2 * DIM + ax] = st.acc[ax];
         if (ORD >= 4) s0[3 * DIM + ax] = st.jrk[ax];
       }
+      if (NS > NP) s0[NP] = c.use_yaw ? st.yaw : 0.0;
       for (int f = 0; f < NS; f++) S.cur[f] = s0[f];
       /* goal lattice key: comparable only when the goal carries the same control flags (wp:92-125) */
       S.goal_key_ok = 0;
@@ -870,9 +939,10 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
           if (ORD >= 3) gs[2 * DIM + ax] = gl.acc[ax];
           if (ORD >= 4) gs[3 * DIM + ax] = gl.jrk[ax];
         }
+        if (NS > NP) gs[NP] = c.use_yaw ? gl.yaw : 0.0;
         int gi[NS];
-        lattice_ints<DIM, ORD>(gs, gi);
-        S.goal_key_ok = pack_key_nohash<DIM, ORD>(c, gi, S.gk0, S.gk1) ? 1 : 0;
+        lattice_ints_x<DIM, ORD, NS>(c, gs, gi);
+        S.goal_key_ok = pack_key_nohash<DIM, ORD, NS>(c, gi, S.gk0, S.gk1) ? 1 : 0;
       }
       if (st.control != c.control || st.enable_t != 0) S.status = MPLB_INTERNAL_BADCTRL;
       else {
@@ -901,9 +971,9 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
     __syncthreads();
     if (S.status < 0 && tid == 0) { /* gs:47-60: the start node is pushed and is necessarily the first pop (gs:64-68) */
       int ints[NS];
-      lattice_ints<DIM, ORD>(S.cur, ints);
+      lattice_ints_x<DIM, ORD, NS>(c, S.cur, ints);
       unsigned long long k0, k1;
-      if (!pack_key_nohash<DIM, ORD>(c, ints, k0, k1)) S.status = MPLB_PLAN_KEY_RANGE;
+      if (!pack_key_nohash<DIM, ORD, NS>(c, ints, k0, k1)) S.status = MPLB_PLAN_KEY_RANGE;
       else {
         NodeHot n0;
         n0.g = 0.0; n0.h = heuristic<DIM, ORD>(c, S, S.cur, k0, k1); n0.pg = 0.0; n0.heap_pos = 0; n0.action = -1;
@@ -1045,7 +1115,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
             if (lane == 0) { /* parity hash of the lattice ints (off the serial chain) */
               int ints[NS];
               unpack_ints<NS>(c, S.cur_k0, S.cur_k1, ints);
-              S.goal_hit = gh ? 1 : 0; S.cur_kh = khash_of_ints<NS>(ints);
+              S.goal_hit = gh ? 1 : 0; S.cur_kh = khash_of_ints<NS>(ints, (NS > DIM * ORD) ? c.nkey : NS);
             }
           }
           /* ---- B2: all collision samples of all controls, flat over 8-sample granules (warps 1..NW-2) */
@@ -1117,10 +1187,10 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
             continue;
           }
           double ecost = valid ? S.cost[i] : 0.0;
-          if (POT && c.pot && v == 3 && valid) { /* em:114-115: accumulate the sample terms in sample order, then eb:343-345 */
+          if (POT && (c.pot || c.use_yaw) && v == 3 && valid) { /* em:114-115,121-127: accumulate the sample terms in sample order, then eb:343-345 */
             double acc = 0.0;
             const int base_t = E.gbase[i] * 8, cn_t = E.cnt[i];
-            for (int q = 0; q < cn_t; q++) acc = dadd(acc, S.terms[base_t + q]);
+            for (int q = 0; q < cn_t; q++) { acc = dadd(acc, S.terms[base_t + q]); acc = dadd(acc, S.yterms[base_t + q]); }
             ecost = dadd(acc, S.cost[i]);
           }
           const double tentative = dadd(cg, ecost); /* gs:107 */
@@ -1274,6 +1344,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
                 for (int q = 0; q < 13; q++) row[q] = 0.0;
                 for (int d = 0; d < ORD; d++)
                   for (int ax = 0; ax < DIM; ax++) row[d * 3 + ax] = ps[d * DIM + ax];
+                if (NS > NP && c.use_yaw) row[12] = ps[NP];
               }
             }
             cnode = p;

@@ -17,6 +17,8 @@ from . import _lib
 from ._lib import MplbError, PARAM, check, lib, ptr  # noqa: F401
 from .maps import ACC, JRK, SNP, VEL  # noqa: F401
 
+VELxYAW, ACCxYAW, JRKxYAW, SNPxYAW = VEL | 16, ACC | 16, JRK | 16, SNP | 16  # control.h:15-18
+
 PLAN_OK, PLAN_START_NOT_FREE, PLAN_MAX_EXPAND, PLAN_QUEUE_EMPTY, PLAN_TRACEBACK_FAILED, PLAN_START_IS_GOAL = range(6)
 
 
@@ -60,8 +62,10 @@ class Primitive:
 
     def __init__(self, dim, control, state13, u, t):
         self.dim, self.control, self.t_ = dim, control, float(t)
-        order = {VEL: 1, ACC: 2, JRK: 3, SNP: 4}[control]
+        order = {VEL: 1, ACC: 2, JRK: 3, SNP: 4}[control & 15]
         self.coeffs = np.zeros((dim, 6))
+        # pr_yaw_ = Primitive1D(p.yaw, u(Dim)) for the *xYAW controls (primitive.h:236-253)
+        self.yaw_coeff = np.array([0, 0, 0, 0, u[dim], state13[12]], dtype=np.float64) if control & 16 else None
         for k in range(dim):
             p, v, a, j = state13[k], state13[3 + k], state13[6 + k], state13[9 + k]
             row = {1: (0, 0, 0, 0, u[k], p), 2: (0, 0, 0, u[k], v, p), 3: (0, 0, u[k], a, v, p),
@@ -80,6 +84,13 @@ class Primitive:
             out.vel[k] = c[0] / 24 * t ** 4 + c[1] / 6 * t ** 3 + c[2] / 2 * t * t + c[3] * t + c[4]
             out.acc[k] = c[0] / 6 * t ** 3 + c[1] / 2 * t * t + c[2] * t + c[3]
             out.jrk[k] = c[0] / 2 * t * t + c[1] * t + c[2]
+        if self.yaw_coeff is not None:  # primitive.h:328 + math.h:15-19
+            yaw = self.yaw_coeff[4] * t + self.yaw_coeff[5]
+            while yaw > np.pi:
+                yaw -= 2.0 * np.pi
+            while yaw < -np.pi:
+                yaw += 2.0 * np.pi
+            out.yaw = yaw
         return out
 
 
@@ -234,6 +245,7 @@ class MapPlanner:
     def setAmax(self, a): self._set("a_max", a)
     def setJmax(self, j): self._set("j_max", j)
     def setYawmax(self, y): self._set("yaw_max", y)
+    def setWyaw(self, w): self._set("wyaw", w)  # planner_base.h:221
     def setTmax(self, t): self._set("t_max", t)
     def setW(self, w): self._set("w", w)
     def setEpsilon(self, e): self._set("epsilon", e)

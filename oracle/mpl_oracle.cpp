@@ -124,6 +124,110 @@ std::vector<double> solve4(double a, double b, double c, double d, double e) {
   return ts;
 }
 
+
+/* ------------------------------------------------------------------ correctly rounded sin/cos for the yaw branch
+ * The reference calls libm cos/sin (pr:520, em:125) whose last bit is not specified (glibc 2.39 differs from the
+ * correctly rounded value on about 0.14 % of arguments, always by one ulp).  To give the yaw branch a reproducible
+ * definition the oracle can evaluate both: trig_mode 0 = libm (the reference as built on this machine),
+ * trig_mode 1 = correctly rounded via double-double arithmetic (what the CUDA path implements).  Constants from
+ * tools/gen_trig_tables.py.  Accuracy about 2^-100 relative, i.e. the rounding is correct unless the true value lies
+ * within 2^-100 of a rounding boundary. */
+namespace crtrig {
+static const double PIO2_1 = 0x1.921fb54442d18p+0, PIO2_2 = 0x1.1a62633145c07p-54, PIO2_3 = -0x1.f1976b7ed8fbcp-110;
+static const double TWO_OVER_PI = 0x1.45f306dc9c883p-1;
+/* 1/n! as double-double (hi, lo), n = 2..31 */
+static const double INV_FACT[30][2] = {
+  {0x1.0000000000000p-1, 0x0.0p+0}, /* 1/2! */
+  {0x1.5555555555555p-3, 0x1.5555555555555p-57}, /* 1/3! */
+  {0x1.5555555555555p-5, 0x1.5555555555555p-59}, /* 1/4! */
+  {0x1.1111111111111p-7, 0x1.1111111111111p-63}, /* 1/5! */
+  {0x1.6c16c16c16c17p-10, -0x1.f49f49f49f49fp-65}, /* 1/6! */
+  {0x1.a01a01a01a01ap-13, 0x1.a01a01a01a01ap-73}, /* 1/7! */
+  {0x1.a01a01a01a01ap-16, 0x1.a01a01a01a01ap-76}, /* 1/8! */
+  {0x1.71de3a556c734p-19, -0x1.c154f8ddc6c00p-73}, /* 1/9! */
+  {0x1.27e4fb7789f5cp-22, 0x1.cbbc05b4fa99ap-76}, /* 1/10! */
+  {0x1.ae64567f544e4p-26, -0x1.c062e06d1f209p-80}, /* 1/11! */
+  {0x1.1eed8eff8d898p-29, -0x1.2aec959e14c06p-83}, /* 1/12! */
+  {0x1.6124613a86d09p-33, 0x1.f28e0cc748ebep-87}, /* 1/13! */
+  {0x1.93974a8c07c9dp-37, 0x1.05d6f8a2efd1fp-92}, /* 1/14! */
+  {0x1.ae7f3e733b81fp-41, 0x1.1d8656b0ee8cbp-97}, /* 1/15! */
+  {0x1.ae7f3e733b81fp-45, 0x1.1d8656b0ee8cbp-101}, /* 1/16! */
+  {0x1.952c77030ad4ap-49, 0x1.ac981465ddc6cp-103}, /* 1/17! */
+  {0x1.6827863b97d97p-53, 0x1.eec01221a8b0bp-107}, /* 1/18! */
+  {0x1.2f49b46814157p-57, 0x1.2650f61dbdcb4p-112}, /* 1/19! */
+  {0x1.e542ba4020225p-62, 0x1.ea72b4afe3c2fp-120}, /* 1/20! */
+  {0x1.71b8ef6dcf572p-66, -0x1.d043ae40c4647p-120}, /* 1/21! */
+  {0x1.0ce396db7f853p-70, -0x1.aebcdbd20331cp-124}, /* 1/22! */
+  {0x1.761b41316381ap-75, -0x1.3423c7d91404fp-130}, /* 1/23! */
+  {0x1.f2cf01972f578p-80, -0x1.9ada5fcc1ab14p-135}, /* 1/24! */
+  {0x1.3f3ccdd165fa9p-84, -0x1.58ddadf344487p-139}, /* 1/25! */
+  {0x1.88e85fc6a4e5ap-89, -0x1.71c37ebd16540p-143}, /* 1/26! */
+  {0x1.d1ab1c2dccea3p-94, 0x1.054d0c78aea14p-149}, /* 1/27! */
+  {0x1.0a18a2635085dp-98, 0x1.b9e2e28e1aa54p-153}, /* 1/28! */
+  {0x1.259f98b4358adp-103, 0x1.eaf8c39dd9bc5p-157}, /* 1/29! */
+  {0x1.3932c5047d60ep-108, 0x1.832b7b530a627p-162}, /* 1/30! */
+  {0x1.434d2e783f5bcp-113, 0x1.0b87b91be9affp-167}, /* 1/31! */
+};
+
+struct DD { double hi, lo; };
+inline DD two_sum(double a, double b) { double s = a + b, bb = s - a; return {s, (a - (s - bb)) + (b - bb)}; }
+inline DD quick_two_sum(double a, double b) { double s = a + b; return {s, b - (s - a)}; }
+inline DD two_prod(double a, double b) { double p = a * b; return {p, std::fma(a, b, -p)}; }
+inline DD dd_add(DD x, DD y) {
+  DD s = two_sum(x.hi, y.hi), t = two_sum(x.lo, y.lo);
+  s.lo += t.hi;
+  s = quick_two_sum(s.hi, s.lo);
+  s.lo += t.lo;
+  return quick_two_sum(s.hi, s.lo);
+}
+inline DD dd_mul(DD x, DD y) {
+  DD p = two_prod(x.hi, y.hi);
+  p.lo += x.hi * y.lo + x.lo * y.hi;
+  return quick_two_sum(p.hi, p.lo);
+}
+inline DD dd_neg(DD x) { return {-x.hi, -x.lo}; }
+
+/* sin and cos of x for |x| < 2^20, each rounded to nearest. */
+void sincos_cr(double x, double *sn, double *cs) {
+  double kd = std::nearbyint(x * TWO_OVER_PI);
+  long k = (long)kd;
+  /* r = x - k*pi/2 with pi/2 = P1 + P2 + P3 (161 bits) */
+  DD a = two_prod(kd, PIO2_1), b = two_prod(kd, PIO2_2), c = two_prod(kd, PIO2_3);
+  DD r = two_sum(x, -a.hi);
+  r = dd_add(r, {-a.lo, 0.0});
+  r = dd_add(r, dd_neg(b));
+  r = dd_add(r, dd_neg(c));
+  DD r2 = dd_mul(r, r);
+  /* sin r = r (1 - r2/3! + r2^2/5! - ...), cos r = 1 - r2/2! + r2^2/4! - ...  (Horner in r2, |r| <= pi/4) */
+  DD ps = {INV_FACT[29][0], INV_FACT[29][1]}; /* 1/31! */
+  for (int n = 29; n >= 3; n -= 2) {
+    ps = dd_mul(ps, r2);
+    DD cf = {INV_FACT[n - 2][0], INV_FACT[n - 2][1]};
+    ps = dd_add(cf, dd_neg(ps));
+  }
+  ps = dd_mul(ps, r2);
+  ps = dd_add({1.0, 0.0}, dd_neg(ps));
+  DD s = dd_mul(ps, r);
+  DD pc = {INV_FACT[28][0], INV_FACT[28][1]}; /* 1/30! */
+  for (int n = 28; n >= 2; n -= 2) {
+    pc = dd_mul(pc, r2);
+    DD cf = {INV_FACT[n - 2][0], INV_FACT[n - 2][1]};
+    pc = dd_add(cf, dd_neg(pc));
+  }
+  pc = dd_mul(pc, r2);
+  DD cq = dd_add({1.0, 0.0}, dd_neg(pc));
+  DD so, co;
+  switch ((int)(((k % 4) + 4) % 4)) {
+    case 0: so = s; co = cq; break;
+    case 1: so = cq; co = dd_neg(s); break;
+    case 2: so = dd_neg(s); co = dd_neg(cq); break;
+    default: so = dd_neg(cq); co = s; break;
+  }
+  *sn = so.hi + so.lo;
+  *cs = co.hi + co.lo;
+}
+}  // namespace crtrig
+
 /* ------------------------------------------------------------------ Primitive1D, pr:21-198 */
 struct Prim1D {
   double c[6] = {0, 0, 0, 0, 0, 0};
@@ -190,10 +294,12 @@ struct Prim {
   double T = 0;
   int control = 0;
   Prim1D ax[3];
+  Prim1D yawp;  // pr_yaw_, pr:430 (Primitive1D(p.yaw, u(Dim)), pr:36,242-253)
 
   Prim() {}
   Prim(const WP &p, const double *u, double t, int dim_) : dim(dim_), T(t), control(p.control) {  // pr:220-256
     int cc = control & 15;
+    if (control & USE_YAW) { yawp.c[4] = u[dim_]; yawp.c[5] = p.yaw; }
     for (int i = 0; i < dim; i++) {
       double *c = ax[i].c;
       if (cc == C_SNP) { c[1] = u[i]; c[2] = p.jrk[i]; c[3] = p.acc[i]; c[4] = p.vel[i]; c[5] = p.pos[i]; }       // pr:50-52
@@ -202,7 +308,12 @@ struct Prim {
       else if (cc == C_VEL) { c[4] = u[i]; c[5] = p.pos[i]; }                                                     // pr:36
     }
   }
-  WP evaluate(double t) const {  // pr:321-331 (yaw controls are out of scope: use_yaw never set here)
+  static double normalize_angle(double angle) {  // math.h:15-19
+    while (angle > M_PI) angle -= 2.0 * M_PI;
+    while (angle < -M_PI) angle += 2.0 * M_PI;
+    return angle;
+  }
+  WP evaluate(double t) const {  // pr:321-331
     WP p;
     p.control = control;
     for (int k = 0; k < dim; k++) {
@@ -210,6 +321,7 @@ struct Prim {
       p.vel[k] = ax[k].v(t);
       p.acc[k] = ax[k].a(t);
       p.jrk[k] = ax[k].j(t);
+      if (control & USE_YAW) p.yaw = normalize_angle(yawp.p(t));
     }
     return p;
   }
@@ -251,8 +363,43 @@ bool validate_xxx(const Prim &pr, double max, int which) {  // pr:483-496
   return true;
 }
 
-bool validate_primitive(const Prim &pr, double mv, double ma, double mj) {  // pr:449-475 (non-yaw branches)
+/* cos/sin as the reference calls them (libm), or correctly rounded (see crtrig above) */
+void trig(int mode, double x, double *sn, double *cs) {
+  if (mode == 0) { *sn = std::sin(x); *cs = std::cos(x); }
+  else crtrig::sincos_cr(x, sn, cs);
+}
+
+/* v.normalized().dot(Vec2f(cos(yaw), sin(yaw))) with Eigen's normalized() = v / sqrt(squaredNorm) (pr:520, em:125) */
+double heading_dot(const double *vel, double yaw, int trig_mode) {
+  double z = vel[0] * vel[0] + vel[1] * vel[1];
+  double nx = vel[0], ny = vel[1];
+  if (z > 0) { double q = std::sqrt(z); nx = vel[0] / q; ny = vel[1] / q; }
+  double sn, cs;
+  trig(trig_mode, yaw, &sn, &cs);
+  return nx * cs + ny * sn;
+}
+
+bool validate_yaw(const Prim &pr, double my, int trig_mode) {  // pr:503-525
+  if (my <= 0) return true;
+  WP ws[2] = {pr.evaluate(0), pr.evaluate(pr.T)};
+  double sm, cm;
+  trig(trig_mode, my, &sm, &cm);
+  for (const WP &w : ws) {
+    if (w.vel[0] != 0 || w.vel[1] != 0) {
+      double d = heading_dot(w.vel, w.yaw, trig_mode);
+      if (d < cm) return false;
+    }
+  }
+  return true;
+}
+
+bool validate_primitive(const Prim &pr, double mv, double ma, double mj, double myaw = 0, int trig_mode = 0) {  // pr:449-475
   int cc = pr.control;
+  if (cc & USE_YAW) {  // pr:462-472: validate_yaw first, then the bounds of the base control
+    if (!validate_yaw(pr, myaw, trig_mode)) return false;
+    cc &= 15;
+    if (cc == C_VEL) return true;
+  }
   if (cc == C_ACC) return validate_xxx(pr, mv, C_VEL);
   else if (cc == C_JRK) return validate_xxx(pr, mv, C_VEL) && validate_xxx(pr, ma, C_ACC);
   else if (cc == C_SNP) return validate_xxx(pr, mv, C_VEL) && validate_xxx(pr, ma, C_ACC) && validate_xxx(pr, mj, C_JRK);
@@ -420,6 +567,8 @@ struct Planner {
   double w = 10.0, tol_pos = 0.5, tol_vel = -1.0, tol_acc = -1.0;
   double v_max = -1.0, a_max = -1.0, j_max = -1.0, yaw_max = -1.0, dt = 1.0;
   double eps = 1.0;
+  double wyaw = 1.0, tol_yaw = -1.0;  // eb:372,380
+  int trig_mode = 0;                  // 0 = libm cos/sin (the reference), 1 = correctly rounded (see crtrig)
   int max_num = -1;
   std::vector<std::vector<double>> U;
   WP goal;
@@ -457,6 +606,7 @@ struct Planner {
       for (int i = 0; i < dim; i++) m = std::max(m, std::abs(s.acc[i] - goal.acc[i]));
       goaled = m <= tol_acc;
     }
+    if (goaled && tol_yaw >= 0) goaled = std::abs(s.yaw - goal.yaw) <= tol_yaw;  // em:36-37
     if (goaled && map->ray_hits_occupied(s.pos, goal.pos)) return false;
     return goaled;
   }
@@ -470,7 +620,7 @@ struct Planner {
     return w * m;
   }
 
-  /* em:90-132 (no yaw) */
+  /* em:90-132 */
   double traverse(const Prim &pr, orc_prim_trace *tr, int64_t *n_samples) const {
     double max_v = 0;
     for (int i = 0; i < dim; i++)
@@ -506,6 +656,13 @@ struct Planner {
         if (tr) { tr->n_tested = tested; tr->block_idx = idx; }
         *n_samples += tested;
         return kInf;
+      }
+      if (wyaw > 0 && (pt.control & USE_YAW)) {  // em:121-128
+        double nrm = std::sqrt(pt.vel[0] * pt.vel[0] + pt.vel[1] * pt.vel[1]);
+        if (nrm > 1e-5) {
+          double v_value = 1 - heading_dot(pt.vel, pt.yaw, trig_mode);
+          c += wyaw * v_value * dts;
+        }
       }
     }
     if (tr) tr->n_tested = tested;
@@ -618,7 +775,7 @@ struct Planner {
         tr->key[15] = tk.n;
       }
       if (tk == ck) { if (tr) tr->verdict = 0; continue; }
-      if (!validate_primitive(pr, v_max, a_max, j_max)) { if (tr) tr->verdict = 1; continue; }
+      if (!validate_primitive(pr, v_max, a_max, j_max, yaw_max, trig_mode)) { if (tr) tr->verdict = 1; continue; }
       tn.t = curr.t + dt;
       succ.push_back(tn);
       bool same = true;
@@ -785,6 +942,7 @@ int orc_planner_set_param(void *pp, const char *key, double v) {
   else if (k == "tol_pos") p->tol_pos = v; else if (k == "tol_vel") p->tol_vel = v; else if (k == "tol_acc") p->tol_acc = v;
   else if (k == "potential_weight") p->potential_weight = v; else if (k == "gradient_weight") p->gradient_weight = v;
   else if (k == "pow") p->pow_ = v;
+  else if (k == "wyaw") p->wyaw = v; else if (k == "tol_yaw") p->tol_yaw = v; else if (k == "trig_mode") p->trig_mode = (int)v;
   else return -1;
   return 0;
 }
@@ -814,6 +972,9 @@ int64_t orc_planner_get_search_region(void *pp, uint8_t *out, int64_t cap) {
   return n;
 }
 void orc_planner_update_potential_map(void *pp, const double *pos) { ((Planner *)pp)->update_potential_map(pos); }
+void orc_sincos_cr(const double *x, int n, double *s, double *c) {
+  for (int i = 0; i < n; i++) crtrig::sincos_cr(x[i], &s[i], &c[i]);
+}
 int64_t orc_map_get_data(void *map, int8_t *out, int64_t cap) {
   Map *m = (Map *)map;
   int64_t n = (int64_t)m->data.size();
@@ -891,6 +1052,7 @@ int orc_plan_batch(void *pp, const orc_waypoint *starts, const orc_waypoint *goa
     local.max_num = base->max_num; local.U = base->U;
     local.potential_map = base->potential_map; local.search_region = base->search_region;
     local.potential_weight = base->potential_weight; local.gradient_weight = base->gradient_weight;
+    local.wyaw = base->wyaw; local.tol_yaw = base->tol_yaw; local.trig_mode = base->trig_mode;
     for (int i = tid; i < n; i += nthreads) {
       local.plan(from_c(starts[i]), from_c(goals[i]));
       results[i] = local.last;

@@ -77,7 +77,7 @@ void *orc_planner_create(int dim);
 void orc_planner_destroy(void *p);
 void orc_planner_set_map(void *p, void *map);
 /* keys: "v_max" "a_max" "j_max" "yaw_max" "dt" "w" "epsilon" "max_num" "tol_pos" "tol_vel" "tol_acc"
- *       "potential_weight" "gradient_weight" "pow" */
+ *       "potential_weight" "gradient_weight" "pow" "wyaw" "tol_yaw" "trig_mode" (0 = libm cos/sin, 1 = correctly rounded) */
 int orc_planner_set_param(void *p, const char *key, double v);
 void orc_planner_set_controls(void *p, const double *U, int n, int udim);
 
@@ -88,6 +88,8 @@ void orc_planner_clear_shaping(void *p);
 int64_t orc_planner_get_search_region(void *p, uint8_t *out, int64_t cap);
 void orc_planner_update_potential_map(void *p, const double *pos);                 /* map_planner.cpp:286-391 (rewrites the map) */
 int64_t orc_map_get_data(void *map, int8_t *out, int64_t cap);
+/* correctly rounded sin/cos (the yaw branch's reproducible definition of pr:520 / em:125), |x| < 2^20 */
+void orc_sincos_cr(const double *x, int n, double *s, double *c);
 int orc_plan(void *p, const orc_waypoint *start, const orc_waypoint *goal, orc_result *out);
 /* getters for the last orc_plan on this planner */
 int orc_get_actions(void *p, int32_t *actions, int cap);                 /* returns n_seg */

@@ -8,7 +8,7 @@ from mpl_ros_b200 import maps
 RESULT_FIELDS = ("status", "n_seg", "cost", "pops", "n_nodes", "n_open", "n_closed", "n_prims", "n_samples", "n_valid",
                  "pop_hash", "closed_hash")
 PARAM_SETTERS = dict(v_max="setVmax", a_max="setAmax", j_max="setJmax", dt="setDt", w="setW", epsilon="setEpsilon",
-                     max_num="setMaxNum")
+                     max_num="setMaxNum", yaw_max="setYawmax", wyaw="setWyaw")
 
 
 def make_pair(m, dim, params, U):
@@ -39,7 +39,7 @@ def make_pair(m, dim, params, U):
     return pl, op
 
 
-def waypoint_pair(pos, control, vel=None, acc=None):
+def waypoint_pair(pos, control, vel=None, acc=None, yaw=None):
     a, b = mp.waypoints_array(len(np.atleast_2d(pos))), oracle.make_waypoints(len(np.atleast_2d(pos)))
     for w in (a, b):
         p = np.atleast_2d(np.asarray(pos, dtype=np.float64))
@@ -50,6 +50,8 @@ def waypoint_pair(pos, control, vel=None, acc=None):
         if acc is not None:
             v = np.atleast_2d(np.asarray(acc, dtype=np.float64))
             w["acc"][:, :v.shape[1]] = v
+        if yaw is not None:
+            w["yaw"] = yaw
         w["control"] = control
     return a, b
 
