@@ -114,7 +114,7 @@ class Primitive {
     for (int i = 0; i < Dim; i++) {
       double *c = c_[i];
       for (int k = 0; k < 6; k++) c[k] = 0;
-      switch (control_) { /* primitive.h:35-52 */
+      switch ((int)control_ & 15) { /* primitive.h:35-52; the *xYAW variants share the base rows (primitive.h:236-253) */
         case Control::VEL: c[4] = u[i]; c[5] = p.pos(i); break;
         case Control::ACC: c[3] = u[i]; c[4] = p.vel(i); c[5] = p.pos(i); break;
         case Control::JRK: c[2] = u[i]; c[3] = p.acc(i); c[4] = p.vel(i); c[5] = p.pos(i); break;
@@ -122,10 +122,13 @@ class Primitive {
         default: break;
       }
     }
+    for (int k = 0; k < 6; k++) cyaw_[k] = 0;
+    if (((int)control_ & 16) && (int)u.size() > Dim) { cyaw_[4] = u[Dim]; cyaw_[5] = p.yaw; } /* pr_yaw_ = Primitive1D(p.yaw, u(Dim)) */
   }
   decimal_t t() const { return t_; }
   Control::Control control() const { return control_; }
   const double *coeff(int k) const { return c_[k]; } /* float64[6] row of planning_ros_msgs/Primitive (cx, cy, cz) */
+  const double *coeff_yaw() const { return cyaw_; }  /* the cyaw row (primitive.h:346-347) */
   Waypoint<Dim> evaluate(decimal_t t) const { /* primitive.h:128-145,321-331 */
     Waypoint<Dim> p(control_);
     for (int k = 0; k < Dim; k++) {
@@ -136,6 +139,12 @@ class Primitive {
       p.acc(k) = c[0] / 6 * t3 + c[1] / 2 * t * t + c[2] * t + c[3];
       p.jrk(k) = c[0] / 2 * t * t + c[1] * t + c[2];
     }
+    if (p.use_yaw) { /* primitive.h:328 with normalize_angle (math.h:15-19) */
+      decimal_t a = cyaw_[4] * t + cyaw_[5];
+      while (a > M_PI) a -= 2.0 * M_PI;
+      while (a < -M_PI) a += 2.0 * M_PI;
+      p.yaw = a;
+    }
     return p;
   }
   decimal_t J(const Control::Control &control) const { /* primitive.h:92-122,403-407 for c0 = 0 rows */
@@ -143,14 +152,15 @@ class Primitive {
     for (int k = 0; k < Dim; k++) {
       const double *c = c_[k];
       const double t = t_;
-      if (control == Control::VEL)
+      const int base = (int)control & 15; /* primitive.h:94-117: the yaw variants share the branch */
+      if (base == Control::VEL)
         j += (c[1] * c[1] / 252) * std::pow(t, 7) + (c[1] * c[2] / 36) * std::pow(t, 6) + (c[2] * c[2] / 20 + c[1] * c[3] / 15) * std::pow(t, 5) +
              (c[2] * c[3] / 4 + c[1] * c[4] / 12) * std::pow(t, 4) + (c[3] * c[3] / 3 + c[2] * c[4] / 3) * t * t * t + c[3] * c[4] * t * t + c[4] * c[4] * t;
-      else if (control == Control::ACC)
+      else if (base == Control::ACC)
         j += (c[1] * c[1] / 20) * std::pow(t, 5) + (c[1] * c[2] / 4) * std::pow(t, 4) + (c[2] * c[2] / 3 + c[1] * c[3] / 3) * t * t * t + c[2] * c[3] * t * t + c[3] * c[3] * t;
-      else if (control == Control::JRK)
+      else if (base == Control::JRK)
         j += (c[1] * c[1]) / 3 * t * t * t + c[1] * c[2] * t * t + c[2] * c[2] * t;
-      else if (control == Control::SNP)
+      else if (base == Control::SNP)
         j += c[1] * c[1] * t;
     }
     return j;
@@ -160,6 +170,7 @@ class Primitive {
   decimal_t t_{0};
   Control::Control control_{Control::NONE};
   double c_[Dim][6];
+  double cyaw_[6];
 };
 typedef Primitive<2> Primitive2D;
 typedef Primitive<3> Primitive3D;
@@ -282,7 +293,8 @@ class MapPlanner {
   void setVmax(decimal_t v) { set(MPLB_V_MAX, v); }
   void setAmax(decimal_t a) { set(MPLB_A_MAX, a); }
   void setJmax(decimal_t j) { set(MPLB_J_MAX, j); }
-  void setYawmax(decimal_t yaw) { set(MPLB_YAW_MAX, yaw); }
+  void setYawmax(decimal_t yaw) { set(MPLB_YAW_MAX, yaw); }   /* planner_base.h:197 */
+  void setWyaw(decimal_t w) { set(MPLB_WYAW, w); }             /* planner_base.h:221 */
   void setTmax(decimal_t t) { set(MPLB_T_MAX, t); }
   void setDt(decimal_t dt) { dt_ = dt; set(MPLB_DT, dt); }
   void setW(decimal_t w) { set(MPLB_W, w); }
@@ -293,9 +305,10 @@ class MapPlanner {
   }
   void setU(const vec_E<VecDf> &U) { /* planner_base.h:246 */
     U_ = U;
+    const int udim = (!U.empty() && (int)U[0].size() > Dim) ? Dim + 1 : Dim; /* Dim + 1: last entry is the yaw rate (primitive.h:217) */
     std::vector<double> flat;
-    for (const auto &u : U) for (int k = 0; k < Dim; k++) flat.push_back(u[k]);
-    if (h_ && mplb_planner_set_controls(h_, flat.data(), (int)U.size(), Dim) != MPLB_OK) report();
+    for (const auto &u : U) for (int k = 0; k < udim; k++) flat.push_back(u[k]);
+    if (h_ && mplb_planner_set_controls(h_, flat.data(), (int)U.size(), udim) != MPLB_OK) report();
   }
 
   /* planner_base.h:275-325 */
@@ -315,6 +328,7 @@ class MapPlanner {
       for (int i = 0; i < last_.n_seg; i++) {
         Waypoint<Dim> w(control_);
         for (int k = 0; k < Dim; k++) { w.pos(k) = st[i * 13 + k]; w.vel(k) = st[i * 13 + 3 + k]; w.acc(k) = st[i * 13 + 6 + k]; w.jrk(k) = st[i * 13 + 9 + k]; }
+        w.yaw = st[i * 13 + 12];
         prs.push_back(Primitive<Dim>(w, U_[acts[i]], dt_));
       }
       traj_ = Trajectory<Dim>(prs);

@@ -34,7 +34,7 @@ def _write_corridor(tmp_path):
     return p
 
 
-@pytest.mark.parametrize("name", ["test_planner_2d", "test_distance_map_planner_2d"])
+@pytest.mark.parametrize("name", ["test_planner_2d", "test_distance_map_planner_2d", "test_planner_2d_with_yaw"])
 def test_cpp_shim_compiles_and_links(tmp_path, name):
     assert os.path.exists(_build(tmp_path, name))
 
@@ -68,3 +68,13 @@ def test_cpp_planner_2d_known_answer(tmp_path):
     assert "Total time T: 35.000000" in out, out                 # MPL/README.md:201
     assert "J(VEL) = 36.750000, J(ACC) = 1.500000" in out, out   # MPL/README.md:202
     assert "cost: 351.500000" in out and "expanded: 615" in out and "waypoints: 36" in out, out
+
+
+@pytest.mark.gpu
+def test_cpp_planner_2d_with_yaw(tmp_path):
+    """tests/cpp/test_planner_2d_with_yaw.cpp (the reference's test_planner_2d_with_yaw.cpp flow) against the oracle's
+    answer for the same flow (tests/test_oracle_yaw.py pins it on the CPU in both trig definitions)."""
+    exe = _build(tmp_path, "test_planner_2d_with_yaw")
+    out = subprocess.check_output([exe, _write_corridor(tmp_path)]).decode()
+    assert "MPL Planner expanded states: 1342" in out, out
+    assert "yaw: cost 352.4275550989 pops 1342 segs 35 first yaw 1.570796" in out, out
