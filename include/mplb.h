@@ -184,6 +184,22 @@ int mplb_plan_batch(mplb_planner *p, const mplb_waypoint *starts, const mplb_way
 int mplb_plan_batch_device(mplb_planner *p, const void *d_starts, const void *d_goals, int n, void *d_results,
                            void *d_actions, void *d_seg_states, int max_seg, void *stream);
 
+/* ---- wire output: toTrajectoryROSMsg (planning_ros_utils/include/planning_ros_utils/
+ * primitive_ros_utils.h:11-33,36-55,78-113) followed by the ROS 1 serialisation of planning_ros_msgs/Trajectory
+ * (std_msgs/Header header; Primitive[] primitives {float64[] cx, cy, cz, cyaw; float64 t}; LambdaSeg[] lambda = empty),
+ * for every plan of a batch, written by the GPU.  Inputs are the outputs of mplb_plan_batch(_device) with the same
+ * max_seg (results, actions and seg_states are all required).  Plan i's message goes to out + i*stride and its byte
+ * length to len[i]; failed plans give a message with zero primitives (the reference's empty traj_); len[i] = 0 marks a
+ * plan whose trajectory was truncated (n_seg > max_seg) or does not fit in `stride`.  z is the height written into cz
+ * for 2D planners (primitive_ros_utils.h:12,18); header fields as in map_planner_node.cpp:55-57,207. */
+size_t mplb_trajectory_msg_size(int n_seg, const char *frame_id); /* bytes of one serialised message */
+int mplb_serialize_trajectories_device(mplb_planner *p, const void *d_results, const void *d_actions, const void *d_seg_states,
+                                       int n, int max_seg, double z, uint32_t seq, uint32_t stamp_sec, uint32_t stamp_nsec,
+                                       const char *frame_id, void *d_out, size_t stride, void *d_len, void *stream);
+int mplb_serialize_trajectories(mplb_planner *p, const mplb_result *results, const int32_t *actions, const double *seg_states,
+                                int n, int max_seg, double z, uint32_t seq, uint32_t stamp_sec, uint32_t stamp_nsec,
+                                const char *frame_id, uint8_t *out, size_t stride, uint32_t *len);
+
 /* Result getters of the retained single plan (two-call pattern: pass cap = 0 to get the size). */
 int mplb_get_actions(mplb_planner *p, int32_t *actions, int cap);      /* returns n_seg; recoverTraj graph_search.h:369-455 */
 int mplb_get_seg_states(mplb_planner *p, double *states13, int cap);   /* returns n_seg */

@@ -56,6 +56,11 @@ SYMBOLS = {
     "mplb_expand": (_I, [_VP, _VP, _I, _VP]),
     "mplb_last_batch_stats": (_I, [_VP, _VP, _VP, _VP]),
     "mplb_sincos_cr": (_I, [_VP, _I, _VP, _VP]),
+    "mplb_trajectory_msg_size": (C.c_size_t, [_I, C.c_char_p]),
+    "mplb_serialize_trajectories_device": (_I, [_VP, _VP, _VP, _VP, _I, _I, _D, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
+                                                _VP, C.c_size_t, _VP, _VP]),
+    "mplb_serialize_trajectories": (_I, [_VP, _VP, _VP, _VP, _I, _I, _D, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
+                                         _VP, C.c_size_t, _VP]),
 }
 
 PARAM = dict(v_max=0, a_max=1, j_max=2, yaw_max=3, dt=4, w=5, epsilon=6, max_num=7, tol_pos=8, tol_vel=9,

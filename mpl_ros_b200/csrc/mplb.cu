@@ -210,6 +210,78 @@ __global__ void k_fill_int(int *a, int v, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = v;
 }
 
+/* ---- planning_ros_msgs/Trajectory, ROS 1 wire format.  One warp per (plan, primitive): lane l writes bytes l, l+32, ...
+ * of the 216-byte Primitive record (4 x {uint32 6, float64[6]} + float64 t), so stores of a warp are contiguous. */
+struct MsgArgs {
+  const mplb_result *results;
+  const int *actions;
+  const double *segs;
+  int n, max_seg, dim, ord, use_yaw;
+  const double *U, *Uyaw;
+  double dt, z;
+  unsigned seq, sec, nsec, frame_len;
+  unsigned char frame[64];
+  unsigned char *out;
+  size_t stride;
+  unsigned *len;
+};
+__device__ __forceinline__ unsigned char byte_of(double v, int b) { return (unsigned char)((unsigned long long)__double_as_longlong(v) >> (8 * b)); }
+__device__ __forceinline__ unsigned char byte_of(unsigned v, int b) { return (unsigned char)(v >> (8 * b)); }
+__global__ void k_serialize_traj(const __grid_constant__ MsgArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const long long total = (long long)a.n * (a.max_seg + 1); /* slot 0 of every plan: header, counts, length */
+  for (long long w = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); w < total; w += (long long)gridDim.x * wpb) {
+    const int plan = (int)(w / (a.max_seg + 1)), k = (int)(w % (a.max_seg + 1)) - 1;
+    const mplb_result r = a.results[plan];
+    const int n_seg = (r.status == MPLB_PLAN_OK) ? r.n_seg : 0;
+    const size_t head = 16 + (size_t)a.frame_len + 4; /* seq, stamp.sec, stamp.nsec, frame_id length + bytes, primitive count */
+    const size_t need = head + (size_t)n_seg * 216 + 4;
+    const bool fits = n_seg <= a.max_seg && need <= a.stride;
+    unsigned char *o = a.out + (size_t)plan * a.stride;
+    if (k < 0) {
+      if (lane == 0) a.len[plan] = fits ? (unsigned)need : 0u;
+      if (!fits) continue;
+      for (int b = lane; b < (int)head; b += 32) {
+        unsigned char v;
+        if (b < 4) v = byte_of(a.seq, b);
+        else if (b < 8) v = byte_of(a.sec, b - 4);
+        else if (b < 12) v = byte_of(a.nsec, b - 8);
+        else if (b < 16) v = byte_of(a.frame_len, b - 12);
+        else if (b < 16 + (int)a.frame_len) v = a.frame[b - 16];
+        else v = byte_of((unsigned)n_seg, b - 16 - (int)a.frame_len);
+        o[b] = v;
+      }
+      if (lane < 4) o[need - 4 + lane] = 0; /* LambdaSeg[] lambda: empty */
+      continue;
+    }
+    if (!fits || k >= n_seg) continue;
+    const double *row = a.segs + ((size_t)plan * a.max_seg + k) * 13;
+    const int act = a.actions[(size_t)plan * a.max_seg + k];
+    unsigned char *po = o + head + (size_t)k * 216;
+    for (int b = lane; b < 216; b += 32) {
+      unsigned char v;
+      if (b >= 208) v = byte_of(a.dt, b - 208);
+      else {
+        const int arr = b / 52, off = b % 52; /* arr: 0 cx, 1 cy, 2 cz, 3 cyaw */
+        if (off < 4) v = byte_of(6u, off);
+        else {
+          const int ci = (off - 4) >> 3, bb = (off - 4) & 7; /* coefficient index 0..5, highest order first (pr:35-52) */
+          double c = 0.0;
+          if (arr < a.dim) {
+            const int d = 5 - ci; /* derivative held by this coefficient */
+            if (d < a.ord) c = row[d * 3 + arr];
+            else if (d == a.ord) c = a.U[act * 3 + arr];
+          } else if (arr == 2) c = (ci == 5) ? a.z : 0.0; /* 2D: cz = (0,0,0,0,0,z) */
+          else if (arr == 3 && a.use_yaw) c = (ci == 5) ? row[12] : (ci == 4 ? a.Uyaw[act] : 0.0);
+          v = byte_of(c, bb);
+        }
+      }
+      po[b] = v;
+    }
+  }
+}
+
 __global__ void k_sincos_cr(const double *x, int n, double *s, double *c) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) trig::sincos_cr(x[i], &s[i], &c[i]);
@@ -1313,6 +1385,63 @@ int mplb_debug_phase_cycles(mplb_planner *p, long long *out, int n) {
   return MPLB_OK;
 }
 #endif
+
+size_t mplb_trajectory_msg_size(int n_seg, const char *frame_id) {
+  return 16 + (frame_id ? std::strlen(frame_id) : 0) + 4 + (size_t)(n_seg > 0 ? n_seg : 0) * 216 + 4;
+}
+
+int mplb_serialize_trajectories_device(mplb_planner *p, const void *d_results, const void *d_actions, const void *d_seg_states,
+                                       int n, int max_seg, double z, uint32_t seq, uint32_t stamp_sec, uint32_t stamp_nsec,
+                                       const char *frame_id, void *d_out, size_t stride, void *d_len, void *stream) {
+  if (!p || !d_results || !d_actions || !d_seg_states || !d_out || !d_len) return fail(MPLB_ERR_ARG, "null argument");
+  if (n <= 0) return MPLB_OK;
+  if (max_seg <= 0) return fail(MPLB_ERR_ARG, "max_seg must be > 0");
+  if (p->dirty || !p->map) return fail(MPLB_ERR_STATE, "no batch has been planned with the current configuration");
+  const size_t fl = frame_id ? std::strlen(frame_id) : 0;
+  if (fl > 64) return fail(MPLB_ERR_ARG, "frame_id longer than 64 bytes");
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  const DevCfg &c = p->cfg;
+  MsgArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.results = (const mplb_result *)d_results; a.actions = (const int *)d_actions; a.segs = (const double *)d_seg_states;
+  a.n = n; a.max_seg = max_seg; a.dim = c.dim; a.ord = c.ord; a.use_yaw = c.use_yaw; a.U = c.U; a.Uyaw = c.Uyaw;
+  a.dt = c.dt; a.z = z; a.seq = seq; a.sec = stamp_sec; a.nsec = stamp_nsec; a.frame_len = (unsigned)fl;
+  if (fl) std::memcpy(a.frame, frame_id, fl);
+  a.out = (unsigned char *)d_out; a.stride = stride; a.len = (unsigned *)d_len;
+  const long long warps = (long long)n * (max_seg + 1);
+  const int blocks = (int)std::min<long long>((warps + 7) / 8, 148 * 8);
+  k_serialize_traj<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return MPLB_OK;
+}
+
+int mplb_serialize_trajectories(mplb_planner *p, const mplb_result *results, const int32_t *actions, const double *seg_states,
+                                int n, int max_seg, double z, uint32_t seq, uint32_t stamp_sec, uint32_t stamp_nsec,
+                                const char *frame_id, uint8_t *out, size_t stride, uint32_t *len) {
+  if (!p || !results || !actions || !seg_states || !out || !len) return fail(MPLB_ERR_ARG, "null argument");
+  if (n <= 0) return MPLB_OK;
+  if (max_seg <= 0) return fail(MPLB_ERR_ARG, "max_seg must be > 0");
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  unsigned char *d = nullptr;
+  const size_t b_res = align_up((size_t)n * sizeof(mplb_result), 256), b_act = align_up((size_t)n * max_seg * sizeof(int), 256),
+               b_seg = align_up((size_t)n * max_seg * 13 * sizeof(double), 256), b_len = align_up((size_t)n * sizeof(unsigned), 256),
+               b_out = (size_t)n * stride;
+  CUDA_TRY(cudaMalloc((void **)&d, b_res + b_act + b_seg + b_len + b_out));
+  cudaError_t e = cudaMemcpy(d, results, (size_t)n * sizeof(mplb_result), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d + b_res, actions, (size_t)n * max_seg * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d + b_res + b_act, seg_states, (size_t)n * max_seg * 13 * sizeof(double), cudaMemcpyHostToDevice);
+  int rc = MPLB_OK;
+  if (e == cudaSuccess)
+    rc = mplb_serialize_trajectories_device(p, d, d + b_res, d + b_res + b_act, n, max_seg, z, seq, stamp_sec, stamp_nsec, frame_id,
+                                            d + b_res + b_act + b_seg + b_len, stride, d + b_res + b_act + b_seg, nullptr);
+  if (e == cudaSuccess && rc == MPLB_OK) e = cudaMemcpy(len, d + b_res + b_act + b_seg, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && rc == MPLB_OK) e = cudaMemcpy(out, d + b_res + b_act + b_seg + b_len, b_out, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(MPLB_ERR_CUDA, std::string("mplb_serialize_trajectories: ") + cudaGetErrorString(e));
+  return rc;
+}
 
 int mplb_sincos_cr(const double *x, int n, double *s, double *c) {
   if (n <= 0) return MPLB_OK;

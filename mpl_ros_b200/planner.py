@@ -431,6 +431,22 @@ class MapPlanner:
         check(lib().mplb_plan_batch_device(self._h, vp(d_starts), vp(d_goals), n, vp(d_results), vp(d_actions), vp(d_segs),
                                            max_seg, vp(stream)))
 
+    def serialize_trajectories(self, results, actions, seg_states, z=0.0, frame_id="map", seq=0, stamp=(0, 0)):
+        """toTrajectoryROSMsg + ROS 1 serialisation of planning_ros_msgs/Trajectory for every plan of a batch
+        (primitive_ros_utils.h:62-113, map_planner_node.cpp:55-57,206-208), written by the GPU.  Returns a list of
+        `bytes`, one message per plan (None for a plan whose trajectory was truncated by max_seg)."""
+        n, max_seg = int(actions.shape[0]), int(actions.shape[1])
+        results = np.ascontiguousarray(results)
+        actions = np.ascontiguousarray(actions, dtype=np.int32)
+        seg_states = np.ascontiguousarray(seg_states, dtype=np.float64)
+        fid = frame_id.encode()
+        stride = int(lib().mplb_trajectory_msg_size(max_seg, fid))
+        out = np.zeros((n, stride), dtype=np.uint8)
+        ln = np.zeros(n, dtype=np.uint32)
+        check(lib().mplb_serialize_trajectories(self._h, ptr(results), ptr(actions), ptr(seg_states), n, max_seg, float(z),
+                                                int(seq), int(stamp[0]), int(stamp[1]), fid, ptr(out), stride, ptr(ln)))
+        return [out[i, :ln[i]].tobytes() if ln[i] else None for i in range(n)]
+
     def last_batch_stats(self):
         ms, l, t = C.c_double(), C.c_int32(), C.c_int32()
         check(lib().mplb_last_batch_stats(self._h, C.byref(ms), C.byref(l), C.byref(t)))
