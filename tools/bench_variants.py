@@ -22,7 +22,7 @@ def run(name, pl, op, sg, gg, so, go, n_cpu, reps=3):
     ms = []
     for _ in range(reps):
         rg, ag, _ = pl.plan_batch(sg, gg, max_seg=64)
-        ms.append(pl.last_batch_stats()[0])
+        ms.append(pl.last_batch_stats()["kernel_ms"])
     prims = int(rg["n_prims"].sum())
     t0 = time.time()
     ro, ao = op.plan_batch(so[:n_cpu], go[:n_cpu], nthreads=min(os.cpu_count() or 1, 64), max_seg=64)
