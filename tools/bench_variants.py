@@ -36,8 +36,30 @@ def run(name, pl, op, sg, gg, so, go, n_cpu, reps=3):
     return rg, ag
 
 
+def single_plan_latency():
+    """The reference's own use: ONE plan per call (map_planner_node).  Wall time of plan() through the public API
+    (host buffers, result copied back) next to the oracle on one core."""
+    from helpers import load_config
+    for name in ("corridor", "skir"):
+        m, dim, params, U, start, goal = load_config(name)
+        pl, op = make_pair(m, dim, params, U)
+        sg, so = waypoint_pair(start, mp.ACC)
+        gg, go = waypoint_pair(goal, mp.ACC)
+        pl.plan(sg, gg)
+        tg, tc = [], []
+        for _ in range(20):
+            t0 = time.perf_counter(); pl.plan(sg, gg); tg.append(time.perf_counter() - t0)
+        for _ in range(5):
+            t0 = time.perf_counter(); ro = op.plan(so, go); tc.append(time.perf_counter() - t0)
+        rg = pl.result()
+        print(json.dumps({"variant": "single_plan_latency_" + name, "pops": int(rg["pops"]), "gpu_ms": 1e3 * float(np.median(tg)),
+                          "gpu_kernel_ms": pl.last_batch_stats()["kernel_ms"], "cpu_oracle_ms": 1e3 * float(np.median(tc)),
+                          "same": bool(rg["pop_hash"] == ro["pop_hash"])}))
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+    single_plan_latency()
     m = maps.levine256()
     S, G = maps.sample_queries(m, n, seed=0)
     params = dict(v_max=2.0, a_max=1.0, dt=1.0, tol_pos=0.5)
