@@ -84,8 +84,9 @@ __host__ __device__ inline DD dd_mul(DD x, DD y) {
 }
 __host__ __device__ inline DD dd_neg(DD x) { return {-x.hi, -x.lo}; }
 
-/* sin(x) and cos(x), each rounded to nearest, |x| < 2^20.  Kept out of line on the device: about 1.5k instructions. */
-__host__ __device__ __noinline__ inline void sincos_cr(double x, double *sn, double *cs) {
+/* Reference-quality path: everything in double-double, ~2^-100 accurate.  About 1.5k instructions; taken only when the
+ * quick path below cannot decide the rounding (about one call in 16 000). */
+__host__ __device__ __noinline__ inline void sincos_cr_slow(double x, double *sn, double *cs) {
   const double INV_FACT[30][2] = MPLB_INV_FACT_INIT; /* folded into immediates by the unrolled loops */
   const double kd = rint(t_mul(x, TWO_OVER_PI));
   const int k = (int)kd;
@@ -121,6 +122,70 @@ __host__ __device__ __noinline__ inline void sincos_cr(double x, double *sn, dou
   }
   *sn = t_add(so.hi, so.lo);
   *cs = t_add(co.hi, co.lo);
+}
+
+/* sin(x) and cos(x), each rounded to nearest, |x| < 2^20 (Ziv's two-step scheme).
+ * Quick path: the same double-double argument reduction, the leading terms of the series in double-double
+ * (sin: r, r^3/3!, r^5/5!, r^7/7!; cos: 1, r^2/2!, ..., r^8/8!) and the remaining tail (below 2^-21 of the result) in
+ * plain double, for a total error under 2^-70 of the result.  The rounding of hi + lo is accepted when it is the same
+ * for lo +- 2^-68 |hi|; otherwise the slow path decides.  Both paths return the correctly rounded value, so which one
+ * ran is unobservable. */
+__host__ __device__ __noinline__ inline void sincos_cr(double x, double *sn, double *cs) {
+  const double F[30][2] = MPLB_INV_FACT_INIT; /* only constant indices are used: folded into immediates */
+  const double kd = rint(t_mul(x, TWO_OVER_PI));
+  const int k = (int)kd;
+  DD a = two_prod(kd, PIO2_1), b = two_prod(kd, PIO2_2), c = two_prod(kd, PIO2_3);
+  DD r = two_sum(x, -a.hi);
+  r = dd_add(r, DD{-a.lo, 0.0});
+  r = dd_add(r, dd_neg(b));
+  r = dd_add(r, dd_neg(c));
+  const DD r2 = dd_mul(r, r);
+  const double z = r2.hi;
+  const double z2 = t_mul(z, z);
+  /* sin */
+  const DD r3 = dd_mul(r2, r), r5 = dd_mul(r3, r2), r7 = dd_mul(r5, r2);
+  double ps = F[19][0];                                   /* 1/21! */
+  ps = t_sub(F[17][0], t_mul(z, ps));                      /* 1/19! */
+  ps = t_sub(F[15][0], t_mul(z, ps));
+  ps = t_sub(F[13][0], t_mul(z, ps));
+  ps = t_sub(F[11][0], t_mul(z, ps));
+  ps = t_sub(F[9][0], t_mul(z, ps));
+  ps = t_sub(F[7][0], t_mul(z, ps));                       /* 1/9! */
+  const double tail_s = t_mul(t_mul(r.hi, t_mul(z2, z2)), ps);
+  DD s = dd_add(dd_mul(r5, DD{F[3][0], F[3][1]}), dd_neg(dd_mul(r7, DD{F[5][0], F[5][1]})));
+  s = dd_add(s, DD{tail_s, 0.0});
+  s = dd_add(dd_neg(dd_mul(r3, DD{F[1][0], F[1][1]})), s);
+  s = dd_add(r, s);
+  /* cos */
+  const DD r4 = dd_mul(r2, r2), r6 = dd_mul(r4, r2), r8 = dd_mul(r4, r4);
+  double pc = F[20][0];                                   /* 1/22! */
+  pc = t_sub(F[18][0], t_mul(z, pc));
+  pc = t_sub(F[16][0], t_mul(z, pc));
+  pc = t_sub(F[14][0], t_mul(z, pc));
+  pc = t_sub(F[12][0], t_mul(z, pc));
+  pc = t_sub(F[10][0], t_mul(z, pc));
+  pc = t_sub(F[8][0], t_mul(z, pc));                       /* 1/10! */
+  const double tail_c = -t_mul(t_mul(t_mul(z2, z2), z), pc);
+  DD cq = dd_add(dd_neg(dd_mul(r6, DD{F[4][0], F[4][1]})), dd_mul(r8, DD{F[6][0], F[6][1]}));
+  cq = dd_add(cq, DD{tail_c, 0.0});
+  cq = dd_add(dd_mul(r4, DD{F[2][0], F[2][1]}), cq);
+  cq = dd_add(DD{-t_mul(r2.hi, 0.5), -t_mul(r2.lo, 0.5)}, cq);
+  cq = dd_add(DD{1.0, 0.0}, cq);
+  DD so, co;
+  switch (((k % 4) + 4) % 4) {
+    case 0: so = s; co = cq; break;
+    case 1: so = cq; co = dd_neg(s); break;
+    case 2: so = dd_neg(s); co = dd_neg(cq); break;
+    default: so = dd_neg(cq); co = s; break;
+  }
+  const double es = t_mul(fabs(so.hi), 0x1p-68), ec = t_mul(fabs(co.hi), 0x1p-68);
+  const double s1 = t_add(so.hi, t_add(so.lo, es)), s2 = t_add(so.hi, t_sub(so.lo, es));
+  const double c1 = t_add(co.hi, t_add(co.lo, ec)), c2 = t_add(co.hi, t_sub(co.lo, ec));
+  if (s1 == s2 && c1 == c2) { *sn = s1; *cs = c1; return; }
+#if defined(MPLB_TRIG_STATS) && !defined(__CUDA_ARCH__)
+  mplb_trig_slow_calls++;
+#endif
+  sincos_cr_slow(x, sn, cs);
 }
 
 }  // namespace trig

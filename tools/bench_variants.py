@@ -59,41 +59,44 @@ def single_plan_latency():
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-    single_plan_latency()
+    only = sys.argv[2] if len(sys.argv) > 2 else "all"  # "all" | "yaw"
+    if only == "all":
+        single_plan_latency()
     m = maps.levine256()
     S, G = maps.sample_queries(m, n, seed=0)
     params = dict(v_max=2.0, a_max=1.0, dt=1.0, tol_pos=0.5)
 
-    # 8f.1: potential map (radius 0.4 m / 0.2 m, whole map) + search region = everything but a thin slab
-    U = maps.make_U(1.0, 1, 3)
-    pl, op = make_pair(m, 3, params, U)
-    for o, f in ((pl, "setPotentialRadius"),):
-        getattr(o, f)([0.4, 0.4, 0.2])
-    op.set_vec("potential_radius", [0.4, 0.4, 0.2])
-    pl.setPotentialWeight(0.1)
-    op.set_param("potential_weight", 0.1)
-    t0 = time.time()
-    pl.updatePotentialMap(S[0])
-    t_gpu_pot = time.time() - t0
-    t0 = time.time()
-    op.update_potential_map(np.asarray(S[0], dtype=np.float64))
-    t_cpu_pot = time.time() - t0
-    mu, om = pl._keep
-    ncell = int(np.prod(np.asarray(m.dim, dtype=np.int64)))
-    same_map = bool(np.array_equal(mu.getMap(), om.get_data(ncell)))
-    print(json.dumps({"variant": "update_potential_map", "cells": ncell, "gpu_s": t_gpu_pot, "cpu_s": t_cpu_pot,
-                      "identical": same_map}))
-    sg, so = waypoint_pair(S, mp.ACC)
-    gg, go = waypoint_pair(G, mp.ACC)
-    rg, ag = run("shaped_potential_levine256_U27", pl, op, sg, gg, so, go, n_cpu=min(n, 128))
+    if only == "all":
+        # 8f.1: potential map (radius 0.4 m / 0.2 m, whole map) + search region = everything but a thin slab
+        U = maps.make_U(1.0, 1, 3)
+        pl, op = make_pair(m, 3, params, U)
+        for o, f in ((pl, "setPotentialRadius"),):
+            getattr(o, f)([0.4, 0.4, 0.2])
+        op.set_vec("potential_radius", [0.4, 0.4, 0.2])
+        pl.setPotentialWeight(0.1)
+        op.set_param("potential_weight", 0.1)
+        t0 = time.time()
+        pl.updatePotentialMap(S[0])
+        t_gpu_pot = time.time() - t0
+        t0 = time.time()
+        op.update_potential_map(np.asarray(S[0], dtype=np.float64))
+        t_cpu_pot = time.time() - t0
+        mu, om = pl._keep
+        ncell = int(np.prod(np.asarray(m.dim, dtype=np.int64)))
+        same_map = bool(np.array_equal(mu.getMap(), om.get_data(ncell)))
+        print(json.dumps({"variant": "update_potential_map", "cells": ncell, "gpu_s": t_gpu_pot, "cpu_s": t_cpu_pot,
+                          "identical": same_map}))
+        sg, so = waypoint_pair(S, mp.ACC)
+        gg, go = waypoint_pair(G, mp.ACC)
+        rg, ag = run("shaped_potential_levine256_U27", pl, op, sg, gg, so, go, n_cpu=min(n, 128))
 
-    # 8f.4: serialisation of that batch's trajectories
-    rg, ag, segs = pl.plan_batch(sg, gg, max_seg=64, want_states=True)
-    t0 = time.time()
-    msgs = pl.serialize_trajectories(rg, ag, segs)
-    t_ser = time.time() - t0
-    nbytes = sum(len(x) for x in msgs if x)
-    print(json.dumps({"variant": "serialize_trajectories_host_api", "plans": n, "bytes": nbytes, "seconds": t_ser}))
+        # 8f.4: serialisation of that batch's trajectories
+        rg, ag, segs = pl.plan_batch(sg, gg, max_seg=64, want_states=True)
+        t0 = time.time()
+        msgs = pl.serialize_trajectories(rg, ag, segs)
+        t_ser = time.time() - t0
+        nbytes = sum(len(x) for x in msgs if x)
+        print(json.dumps({"variant": "serialize_trajectories_host_api", "plans": n, "bytes": nbytes, "seconds": t_ser}))
 
     # 8f.2: yaw controls (planar controls x 3 yaw rates = 27 rows)
     Uy = np.array([[dx, dy, 0.0, dyaw] for dx in (-1.0, 0.0, 1.0) for dy in (-1.0, 0.0, 1.0) for dyaw in (-0.5, 0.0, 0.5)])
