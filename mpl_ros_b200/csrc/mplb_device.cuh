@@ -30,7 +30,7 @@ __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a,
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 
 /* Rounding without the XU pipe.  On B200 every FP64 conversion / rounding instruction (F2I, I2F, FRND, MUFU.RCP64H)
- * issues to the XU pipe, which the first profile of this kernel showed 65 % busy; adding and subtracting
+ * issues to the low-rate XU pipe and has a long latency on the serial chain of a pop; adding and subtracting
  * 1.5 * 2^52 rounds to nearest-even on the FP64 pipe instead and leaves the integer in the low mantissa word.
  * Valid for |x| < 2^31; used only inside filters that defer to the exact formula near ties. */
 #define MPLB_MAGIC 6755399441055744.0
@@ -68,7 +68,7 @@ struct DevCfg {
   int koff[13]; /* 12 polynomial fields + yaw (wp:114-117) */
   unsigned char kshift[13], kbits[13], kword[13];
   int key_wide; /* 1 when word 1 of the key needs more than 32 bits (table slots then also compare the row header) */
-  /* filtered (FP32) collision sampling: see sample_blocked_fast */
+  /* filtered collision sampling (FP64 Horner in cell units with a guard band): see sample_blocked_filtered */
   double inv_res;   /* 1/res, used only inside filters whose doubtful cases fall back to the exact division */
   int use_fast;     /* tables fit in shared memory and every dynamic bound is known */
   int tt_total;     /* number of entries of ttab */

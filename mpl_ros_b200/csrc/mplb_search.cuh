@@ -14,17 +14,23 @@
  * dependent FP64 op 8.3 cycles, __ddiv_rn 125, LDS 34, SHFL 26, HBM round trip ~1000) and throughput comes from
  * running several hundred plans at once.  One pop is organised so that almost nothing sits on the serial chain:
  *
- *   warp 0  (search)  B1: one lane per control — exact FP64 end state, validation, lattice key, sample count;
- *                     issues the hash-table probe of every candidate successor (ONE HBM round trip: the table slot
- *                     carries the node's g and best-predecessor g), then helps sampling; after the barrier it
- *                     relaxes all successors lane-parallel and performs the heap pushes in control order with a
- *                     warp-cooperative sift-up on the SHARED-MEMORY heap, then takes the next node off the root.
- *   warps 1-2 (sample) per-pop FP32 sampling coefficients, goal test + parity hash of the current node, then every
- *                     collision sample of every control (flat list of 8-sample granules) through a FILTERED path:
- *                     FP32 evaluation with a proven error bound decides the voxel whenever the sample is not within
- *                     delta of a voxel boundary, otherwise the exact FP64 formula of the reference is evaluated.
- *   warp 3  (heap)    finishes the previous pop's sift-down and prefetches the new root's state row while the
- *                     other warps expand the current node.
+ *   warp 0  (search)  B1 when it was not prepared one pop ahead: one lane per control — exact FP64 end state,
+ *                     validation, lattice key, sample count; issues the hash-table probe of every candidate successor
+ *                     (ONE HBM round trip: the table slot carries the node's g and best-predecessor g) and computes h
+ *                     while they fly; after the barrier it relaxes all successors lane-parallel and performs the heap
+ *                     pushes in control order with a warp-cooperative sift-up on the SHARED-MEMORY heap, then takes
+ *                     the next node off the root.
+ *   warps 1-6 (sample) every collision sample of every control (flat list of 8-sample granules) through a FILTERED
+ *                     path: an FP64 Horner evaluation in cell units decides the voxel whenever the sample is not
+ *                     within a proven guard band of a voxel boundary, otherwise the exact FP64 formula of the
+ *                     reference is evaluated; warp 1 also runs the goal test and the parity hash of the current node.
+ *   warp 7  (heap)    finishes the previous pop's sift-down, prefetches the new root's state row, and runs B1 for
+ *                     that node (the predicted next pop) into the second expansion record while the other warps
+ *                     expand the current node.
+ *
+ * A second set of instantiations (POT = true, |U| <= 32) adds the cost-shaping branches of env_map (search region,
+ * potential map, env_map.h:104-118) and the yaw controls (primitive.h:236-253,503-525, env_map.h:121-128); the plain
+ * instantiations carry none of that code.
  *
  * Exactness: every value that is stored or compared (states, costs, g, h, f, keys, voxel indices) is identical to the
  * reference's double arithmetic; filters only skip work when the exact result is provably the same.  Rare hazards
