@@ -2,7 +2,9 @@
 """bench.py — primitive expansions/s of the batched lattice planner (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            this repo's CUDA path (one process per GPU)
-  python bench.py --impl reference --gpus N --steps K ...   the reference CPU algorithm (oracle port) on host cores
+  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU implementation on host cores: its own
+                                                            sources (oracle/_ref, stand-in Eigen/Boost headers) when
+                                                            that binary is present, else the oracle port
 
 Workload (BASELINE.json configs[1], SURVEY.md §8d "C2"): levine-256 (levine.bag upsampled 2x, cropped and placed
 in a 256^3 int8 grid), |U| = 27 acceleration controls u in {-1,0,1}^3, dt = 1, v_max = 2, a_max = 1, w = 10,
@@ -15,7 +17,9 @@ primitive expansion = one (popped state, u) pair entering env_map.h:155.
             H2D of starts/goals and D2H of results + action rows inside the timed region.
 `roofline`: ALGORITHMIC bytes per primitive expansion (SURVEY.md §8d formula, recomputed from the kernel's own
             counters) x expansions per launch / launch duration, against MEASURED_PEAKS.json hbm_gbs.
-`cpu_baseline`: the oracle (CPU restatement of the reference path) on this box's host cores, bounded sample.
+`cpu_baseline`: the reference's CPU path on this box's host cores, bounded sample: oracle/_ref ("reference": the reference's
+            own planner sources compiled against the stand-in headers of oracle/shim/) when present, else the oracle
+            port ("port"); the port is always run as well because it doubles as the in-bench parity check.
 """
 import argparse
 import json
@@ -112,16 +116,22 @@ class ClockSampler:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
-def run_reference(args):
-    """The reference's own CPU algorithm for the path (oracle port; the reference cannot be compiled here, see
-    DESIGN.md), all host threads, a bounded sample of the same workload per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def cpu_planner(m, U, prefer_reference=True):
+    """(planner, kind): the reference's own sources (oracle/_ref) when that library is present, else the oracle port.
+    Both expose plan_batch(starts, goals, nthreads) -> results with n_prims per plan."""
     import oracle
-    from mpl_ros_b200 import maps
-    m = maps.levine256()
-    U = maps.make_U(1.0, 1, 3)
+    if prefer_reference:
+        from oracle import ref
+        if ref.available():
+            rm = ref.RefMap(m.origin, m.dim, m.data, m.res)
+            rm.free_unknown()
+            rp = ref.RefPlanner(3)
+            rp.set_map(rm)
+            for k, v in PLAN_PARAMS.items():
+                rp.set_param(k, v)
+            rp.set_controls(U)
+            rp._keep = rm
+            return rp, "reference"
     om = oracle.OracleMap(m.origin, m.dim, m.data, m.res)
     om.free_unknown()
     op = oracle.OraclePlanner(3)
@@ -129,6 +139,28 @@ def run_reference(args):
     for k, v in PLAN_PARAMS.items():
         op.set_param(k, v)
     op.set_controls(U)
+    op._keep = om
+
+    class _Port:
+        def plan_batch(self, s, g, nthreads=1):
+            return op.plan_batch(s, g, nthreads=nthreads)[0]
+    return _Port(), "port"
+
+
+KIND_NOTE = {"reference": "the reference's own planner sources (oracle/_ref: stand-in Eigen/Boost headers, see oracle/shim)",
+             "port": "oracle port (oracle/_ref absent)"}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path, all host threads, a bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from mpl_ros_b200 import maps
+    m = maps.levine256()
+    U = maps.make_U(1.0, 1, 3)
+    op, kind = cpu_planner(m, U)
     s, g = make_queries(m, 0)
     cores = os.cpu_count() or 1
     sample = args.cpu_sample
@@ -140,7 +172,7 @@ def run_reference(args):
     t0 = time.perf_counter()
     prims = 0
     for _ in range(args.steps):
-        res, _ = op.plan_batch(so, go, nthreads=cores)
+        res = op.plan_batch(so, go, nthreads=cores)
         prims += int(res["n_prims"].sum())
     dt = time.perf_counter() - t0
     v = prims / dt
@@ -148,7 +180,7 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "step": "first %d of the 1024 queries per step (bounded sample)" % sample},
-            "cpu_baseline": {"value": v, "unit": "prim_exp/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": v, "unit": "prim_exp/s", "cores": cores, "kind": kind, "what": KIND_NOTE[kind],
                              "sample": "first %d queries of the rank-0 batch, %d steps, std::thread striping" % (sample, args.steps)},
             "e2e": {"value": v, "unit": "prim_exp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -342,10 +374,23 @@ def main():
         for f in ("status", "pops", "n_nodes", "pop_hash", "cost"):  # the sample doubles as an in-bench parity check
             a, b = ro[f], res[f][:n_s]
             assert np.array_equal(a, b) or f == "cost" and np.array_equal(a[np.isfinite(a)], b[np.isfinite(b)]), f
-        line["cpu_baseline"] = {"value": float(ro["n_prims"].sum()) / dt_all, "unit": "prim_exp/s", "cores": cores,
-                                "kind": "port", "single_core_value": float(r1["n_prims"].sum()) / dt_1,
-                                "sample": "first %d of the 1024 rank-0 queries, one std::thread per core; GPU results for the "
-                                          "same queries checked equal" % n_s}
+        port_v = float(ro["n_prims"].sum()) / dt_all
+        cb = {"value": port_v, "unit": "prim_exp/s", "cores": cores, "kind": "port",
+              "single_core_value": float(r1["n_prims"].sum()) / dt_1,
+              "sample": "first %d of the 1024 rank-0 queries, one std::thread per core; GPU results for the same queries "
+                        "checked equal against the oracle port" % n_s}
+        rp, kind = cpu_planner(m, U)
+        if kind == "reference":  # the reference's own sources: time them on the same sample and check them too
+            t0 = time.perf_counter()
+            rr = rp.plan_batch(so, go, nthreads=cores)
+            dt_ref = time.perf_counter() - t0
+            for f in ("pops", "n_nodes", "pop_hash", "cost"):
+                a, b = rr[f], res[f][:n_s]
+                assert np.array_equal(a, b) or f == "cost" and np.array_equal(a[np.isfinite(a)], b[np.isfinite(b)]), ("reference", f)
+            cb.update({"value": float(rr["n_prims"].sum()) / dt_ref, "kind": "reference", "what": KIND_NOTE["reference"],
+                       "port_value": port_v})
+            cb["sample"] += " and against the reference's own sources"
+        line["cpu_baseline"] = cb
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

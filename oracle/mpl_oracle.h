@@ -7,15 +7,16 @@
  * check and time the reference algorithm.  Nothing under mpl_ros_b200/ may include, link or
  * call it.
  *
- * Parity pin: MPL/README.md:200-202 (closed set 615, T = 35, J(VEL) = 36.75, J(ACC) = 1.5 on
- * MPL/data/corridor.yaml with MPL/test/test_planner_2d.cpp:29-62 parameters) — checked by
- * tests/test_oracle_kat.py.  Everything else (3D, |U| = 27, JRK, the search-region / potential-map branch of
- * env_map.h:104-118 with MapPlanner::setSearchRegion / updatePotentialMap / iterativePlan, and the yaw controls) is
- * pinned only through this restatement: "parity unpinned by the reference's own tests" for those configs — the
- * reference's tests for them (test_distance_map_planner_2d*.cpp, test_planner_2d_with_yaw.cpp) draw pictures and
- * publish no numbers.  For the yaw branch the reference's cos/sin come from an unpinned libm: trig_mode 0 calls this
- * machine's libm, trig_mode 1 evaluates them correctly rounded (the definition the CUDA path uses); both are checked
- * in tests/test_oracle_yaw.py.
+ * Parity pins: (1) MPL/README.md:200-202 (closed set 615, T = 35, J(VEL) = 36.75, J(ACC) = 1.5 on
+ * MPL/data/corridor.yaml with MPL/test/test_planner_2d.cpp:29-62 parameters), tests/test_oracle_kat.py — the only numbers
+ * the reference publishes.  (2) The reference's OWN planner sources compiled here against stand-in Eigen/Boost headers
+ * (oracle/shim/, oracle/ref_harness.cpp -> oracle/_ref/libmplref.so): tests/test_oracle_vs_reference.py compares this
+ * restatement with them exactly on 3D, |U| = 27, JRK, yaw controls, the search-region / potential-map branch and
+ * iterativePlan.  Where that library cannot be built (no /root/reference) those configurations are "parity unpinned by
+ * the reference's own tests" (test_distance_map_planner_2d*.cpp and test_planner_2d_with_yaw.cpp draw pictures and
+ * publish no numbers).  For the yaw branch the reference's cos/sin come from an unpinned libm: trig_mode 0 calls this
+ * machine's libm (what pin 2 exercises), trig_mode 1 evaluates them correctly rounded (the definition the CUDA path
+ * uses); tests/test_oracle_yaw.py relates the two.
  *
  * Third-party pieces that are NOT under /root/reference and are restated from their published
  * behaviour: Boost.Heap d_ary_heap<arity 2, mutable> (sift rules, see heap section of the .cpp),

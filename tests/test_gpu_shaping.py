@@ -2,8 +2,8 @@
 map_planner.cpp:20-114,286-434) against the oracle, bit-exact.
 
 The reference publishes no numbers for this branch (test_distance_map_planner_2d.cpp only draws a picture), so the
-oracle side is "parity unpinned by the reference's own tests" here; the plain-map first plan of the same flow is the
-README known answer.
+oracle side is pinned by the reference's own sources run on the CPU (tests/test_oracle_vs_reference.py); the plain-map
+first plan of the same flow is the README known answer.
 """
 import numpy as np
 import pytest

@@ -4,7 +4,8 @@ env_map.h:121-128) against the oracle.
 Tolerance policy: the reference evaluates cos/sin with an unpinned libm; the product defines the branch with the
 correctly rounded functions, and the oracle is run in the same definition (trig_mode 1), so every comparison here is
 still bit-exact.  tests/test_oracle_yaw.py (CPU) bounds the distance between that definition and libm.
-The reference publishes no numbers for its yaw tests (they draw pictures): parity unpinned by the reference.
+The reference publishes no numbers for its yaw tests (they draw pictures); the oracle's yaw branch (libm definition) is
+pinned by the reference's own sources in tests/test_oracle_vs_reference.py.
 """
 import ctypes as C
 import math

@@ -1,7 +1,8 @@
 """CPU checks of the oracle's cost-shaping branch: search region + potential map.
 
 The reference publishes no numbers for this branch, so these are structural properties plus a regression pin of the
-oracle's own answer for MPL/test/test_distance_map_planner_2d.cpp's flow ("parity unpinned by the reference" here).
+oracle's own answer for MPL/test/test_distance_map_planner_2d.cpp's flow (tests/test_oracle_vs_reference.py checks the
+same flow against the reference's own sources where they can be compiled).
 """
 import numpy as np
 
