@@ -157,6 +157,30 @@ def test_jrk_control_2d():
     assert np.array_equal(pl.getActions(), op.actions(ro["n_seg"]))
 
 
+def test_snp_control_2d():
+    """Snap control (Control::SNP, order 4: primitive.h:48-52, validate_primitive with v/a/j bounds): the ORD = 4
+    kernel instantiations, with and without a jerk bound (the latter takes the per-control exact sampling path)."""
+    m, dim, params, U, start, goal = load_config("corridor")
+    for prm, u, vel in ((dict(v_max=1.0, a_max=1.0, j_max=1.0, dt=1.0, tol_pos=0.5, max_num=1500), U, None),
+                        (dict(v_max=1.5, a_max=1.0, j_max=2.0, dt=0.5, tol_pos=0.5, max_num=800), maps.make_U(1.0, 1, 2) * 0.5, [0.5, 0.0]),
+                        (dict(v_max=1.0, a_max=1.0, dt=1.0, tol_pos=0.5, max_num=600), U, None)):
+        pl, op = make_pair(m, dim, prm, u)
+        sg, so = waypoint_pair(start, mp.SNP, vel=vel)
+        gg, go = waypoint_pair(goal, mp.SNP)
+        pl.plan(sg, gg)
+        ro = op.plan(so, go)
+        assert_results_equal(pl.result(), ro, ("SNP", prm))
+        gn = pl.getNodes()
+        assert np.array_equal(gn["key"][pl.getPopLog()], op.pop_keys(ro["pops"]))
+        on, gk = _nodes_by_key(op.nodes(ro["n_nodes"])), _nodes_by_key(gn)
+        assert set(on) == set(gk)
+        for k, a in gk.items():
+            assert np.array_equal(a["state"][:12], on[k]["state"][:12]) and a["g"] == on[k]["g"], k
+        if ro["status"] == 0:
+            assert np.array_equal(pl.getActions(), op.actions(ro["n_seg"]))
+            assert np.array_equal(pl.getSegStates()[:, :12], op.seg_states(ro["n_seg"])[:, :12])
+
+
 def test_map_ops():
     m = maps.load_fixture("simple")
     data = m.data.copy()

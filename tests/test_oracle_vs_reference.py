@@ -154,6 +154,21 @@ def test_jrk_epsilon_startvel_maxnum():
     assert op.plan(_wp(goal, 3), _wp(goal, 3))["status"] == rp.plan(_wp(goal, 3), _wp(goal, 3))["status"] == 5
 
 
+def test_snp_2d_and_jrk_125_controls_3d():
+    """Snap control (order 4) on the corridor, and BASELINE configs[4]'s shape at test size (3D jerk control, |U| = 125)."""
+    m, dim, params, U, start, goal = load_config("corridor")
+    op, rp = _pair(m, dim, dict(v_max=1.0, a_max=1.0, j_max=1.0, dt=1.0, tol_pos=0.5, max_num=1500), U)
+    _compare(op, rp, _wp(start, 15), _wp(goal, 15), dim, 15, U, "SNP 2D")
+    Uh = maps.make_U(1.0, 1, 2) * 0.5
+    op, rp = _pair(m, dim, dict(v_max=1.5, a_max=1.0, j_max=2.0, dt=0.5, tol_pos=0.5, max_num=800), Uh)
+    _compare(op, rp, _wp(start, 15, vel=[0.5, 0.0]), _wp(goal, 15), dim, 15, Uh, "SNP 2D dt 0.5")
+    m = maps.load_fixture("skir")
+    U5 = maps.make_U(2.0, 2, 3)
+    assert U5.shape[0] == 125
+    op, rp = _pair(m, 3, dict(v_max=3.0, a_max=2.0, dt=0.5, max_num=400, tol_pos=0.5), U5)
+    _compare(op, rp, _wp([5.5, 5.5, 0.5], 7), _wp([1.5, 1.5, 5.5], 7), 3, 7, U5, "JRK 125", nodes=False)
+
+
 @pytest.mark.parametrize("yaw_max,wyaw", [(0.7, 1.0), (-1.0, 1.0), (1.2, 2.5)])
 def test_yaw_controls_libm_definition(yaw_max, wyaw):
     """MPL/test/test_planner_2d_with_yaw.cpp; the oracle in trig_mode 0 calls the same libm as the reference code does."""
