@@ -89,6 +89,30 @@ class ShardedBatchPlanner:
         self.planner = self.make_planner(o, d, r, grid)
         return o, d, r
 
+    def set_cost_shaping(self, potential=None, region=None, src=0):
+        """Install a potential map (int8 per cell, env_map::set_potential_map) and / or a search-region mask (one byte
+        per cell, env_base::set_search_region) on every rank's planner: rank `src` supplies them (e.g. the map its own
+        planner rewrote with updatePotentialMap), the others receive them with one broadcast each.  None on `src`
+        clears that piece everywhere."""
+        rank = dist.get_rank()
+        flags = torch.zeros(2, dtype=torch.int64, device=self.device)
+        if rank == src:
+            flags[0] = 0 if potential is None else int(np.asarray(potential).size)
+            flags[1] = 0 if region is None else int(np.asarray(region).size)
+        dist.broadcast(flags, src)
+        n_pot, n_reg = (int(x) for x in flags.cpu().numpy())
+        for n, arr, dtype, setter in ((n_pot, potential, np.int8, "setPotentialMap"), (n_reg, region, np.uint8, "setSearchRegionMask")):
+            if n == 0:
+                getattr(self.planner, setter)(None)
+                continue
+            tdt = torch.int8 if dtype == np.int8 else torch.uint8
+            if rank == src:
+                t = torch.as_tensor(np.ascontiguousarray(arr, dtype=dtype).reshape(-1)).to(self.device)
+            else:
+                t = torch.empty(n, dtype=tdt, device=self.device)
+            dist.broadcast(t, src)
+            getattr(self.planner, setter)(t.cpu().numpy())
+
     def plan_batch(self, starts, goals, max_seg=64, dst=0):
         """starts/goals: full arrays on every rank (host, WAYPOINT_DTYPE). Each rank plans its stripe."""
         rank, world = dist.get_rank(), dist.get_world_size()

@@ -49,6 +49,8 @@ def lib():
         L.orc_planner_set_vec.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.orc_planner_set_search_region.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.orc_planner_clear_shaping.argtypes = [C.c_void_p]
+        L.orc_planner_set_potential_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.orc_planner_set_search_region_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_planner_get_search_region.restype = C.c_int64
         L.orc_planner_get_search_region.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_planner_update_potential_map.argtypes = [C.c_void_p, C.c_void_p]
@@ -147,6 +149,20 @@ class OraclePlanner:
     def update_potential_map(self, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64)
         lib().orc_planner_update_potential_map(self.h, _ptr(pos))
+
+    def set_potential_map(self, pot):
+        if pot is None:
+            lib().orc_planner_set_potential_map(self.h, None, 0)
+            return
+        pot = np.ascontiguousarray(pot, dtype=np.int8).ravel()
+        lib().orc_planner_set_potential_map(self.h, _ptr(pot), pot.size)
+
+    def set_search_region_mask(self, mask):
+        if mask is None:
+            lib().orc_planner_set_search_region_mask(self.h, None, 0)
+            return
+        mask = np.ascontiguousarray(mask, dtype=np.uint8).ravel()
+        lib().orc_planner_set_search_region_mask(self.h, _ptr(mask), mask.size)
 
     def clear_shaping(self):
         lib().orc_planner_clear_shaping(self.h)

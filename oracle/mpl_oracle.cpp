@@ -964,6 +964,15 @@ void orc_planner_set_search_region(void *pp, const double *path, int n, int dens
   for (int i = 0; i < n; i++) { pts[i] = {0, 0, 0}; for (int k = 0; k < p->dim; k++) pts[i][k] = path[(size_t)i * 3 + k]; }
   p->set_search_region_path(pts, dense != 0);
 }
+void orc_planner_set_potential_map(void *pp, const int8_t *pot, int64_t n) { /* env_map::set_potential_map, em:182 */
+  Planner *p = (Planner *)pp;
+  p->potential_map.assign(pot, pot + (pot ? n : 0));
+}
+void orc_planner_set_search_region_mask(void *pp, const uint8_t *mask, int64_t n) { /* env_base::set_search_region, eb:301-303 */
+  Planner *p = (Planner *)pp;
+  p->search_region.assign((size_t)(mask ? n : 0), false);
+  for (int64_t i = 0; mask && i < n; i++) p->search_region[i] = mask[i] != 0;
+}
 void orc_planner_clear_shaping(void *pp) { Planner *p = (Planner *)pp; p->search_region.clear(); p->potential_map.clear(); }
 int64_t orc_planner_get_search_region(void *pp, uint8_t *out, int64_t cap) {
   Planner *p = (Planner *)pp;

@@ -34,6 +34,30 @@ class _OracleStandIn:
         res, acts = self.op.plan_batch(starts, goals, nthreads=2, max_seg=max_seg)
         return res, acts, None
 
+    # the two cost-shaping setters of MapPlanner that ShardedBatchPlanner.set_cost_shaping drives
+    def setPotentialMap(self, pot):
+        self.op.set_potential_map(pot)
+
+    def setSearchRegionMask(self, mask):
+        self.op.set_search_region_mask(mask)
+
+
+def _shaping_inputs(m):
+    """A deterministic potential map (graded halo around obstacles along x) and a region mask (everything but a slab)."""
+    nd = np.asarray(m.dim)
+    grid = np.asarray(m.data, dtype=np.int8).reshape(tuple(nd[::-1]))
+    grid = np.where(grid < 0, 0, grid).astype(np.int8)  # like freeUnknown
+    pot = grid.copy()
+    occ = grid == 100
+    for shift, val in ((1, 60), (2, 30)):
+        for sgn in (-1, 1):
+            halo = np.roll(occ, sgn * shift, axis=2)
+            pot = np.where((pot < val) & halo & ~occ, val, pot).astype(np.int8)
+    mask = np.ones_like(grid, dtype=np.uint8)
+    mask[:, :, nd[0] // 2] = 0
+    mask[:, : nd[1] // 2, nd[0] // 2] = 1
+    return pot.ravel(), mask.ravel()
+
 
 def _worker(rank, world, port, n, out_path):
     sys.path.insert(0, ROOT)
@@ -55,10 +79,16 @@ def _worker(rank, world, port, n, out_path):
     s, g = mp.waypoints_array(n), mp.waypoints_array(n)
     s["pos"], g["pos"], s["control"], g["control"] = S, G, mp.ACC, mp.ACC
     res, acts = sp.plan_batch(s, g, max_seg=32)
+    # cost shaping: rank 0 supplies a potential map and a region mask, everyone installs them, then clears them again
+    pot, mask = _shaping_inputs(m)
+    sp.set_cost_shaping(pot, mask) if rank == 0 else sp.set_cost_shaping()
+    res2, acts2 = sp.plan_batch(s, g, max_seg=32)
+    sp.set_cost_shaping(None, None) if rank == 0 else sp.set_cost_shaping()
+    res3, _ = sp.plan_batch(s, g, max_seg=32)
     if rank == 0:
-        np.savez(out_path, res=res.view(np.uint8), acts=acts)
+        np.savez(out_path, res=res.view(np.uint8), acts=acts, res2=res2.view(np.uint8), acts2=acts2, res3=res3.view(np.uint8))
     else:
-        assert res is None
+        assert res is None and res2 is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,6 +110,15 @@ def test_sharded_batch_gloo(tmp_path):
     got = z["res"].view(_lib.RESULT_DTYPE).reshape(-1)
     assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
     assert np.array_equal(z["acts"], want_acts)
+    # shaped batch: same as a single process with the same potential map and mask installed; cleared = plain again
+    pot, mask = _shaping_inputs(m)
+    ref.setPotentialMap(pot)
+    ref.setSearchRegionMask(mask)
+    want2, want_acts2, _ = ref.plan_batch(s, g, max_seg=32)
+    assert np.array_equal(z["res2"].view(_lib.RESULT_DTYPE).reshape(-1).view(np.uint8), want2.view(np.uint8))
+    assert np.array_equal(z["acts2"], want_acts2)
+    assert not np.array_equal(want2["cost"], want["cost"])  # the shaping changed something
+    assert np.array_equal(z["res3"], z["res"])
 
 
 def test_shard_indices_cover_everything():
