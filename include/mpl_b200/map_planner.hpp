@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <limits>
 #include <memory>
 #include <vector>
@@ -262,6 +263,45 @@ class MapUtil {
     for (int i = 0; i < Dim; i++) p(i) = (pn(i) + 0.5) * res_ + origin_d_(i);
     return p;
   }
+  bool isOutside(const Veci<Dim> &pn) { /* map_util.h:51-55 */
+    for (int i = 0; i < Dim; i++) if (pn(i) < 0 || pn(i) >= dim_(i)) return true;
+    return false;
+  }
+  vec_Vecf<Dim> getCloud() { /* map_util.h:137-162: centres of the occupied cells, x outermost */
+    vec_Vecf<Dim> cloud;
+    const Tmap m = getMap();
+    const int nz = Dim == 3 ? dim_(Dim - 1) : 1;
+    Veci<Dim> n;
+    for (int x = 0; x < dim_(0); x++)
+      for (int y = 0; y < dim_(1); y++)
+        for (int z = 0; z < nz; z++) {
+          n(0) = x; n(1) = y;
+          if (Dim == 3) n(Dim - 1) = z;
+          if (m[(size_t)x + (size_t)dim_(0) * y + (size_t)dim_(0) * dim_(1) * z] == 100) cloud.push_back(intToFloat(n));
+        }
+    return cloud;
+  }
+  vec_Veci<Dim> rayTrace(const Vecf<Dim> &pt1, const Vecf<Dim> &pt2) { /* map_util.h:117-134 */
+    vec_Veci<Dim> pns;
+    decimal_t q = 0;
+    Vecf<Dim> diff;
+    for (int i = 0; i < Dim; i++) { diff(i) = pt2(i) - pt1(i); q = std::max(q, std::abs(diff(i) / res_)); }
+    const int max_diff = (int)(q / 0.8);
+    const decimal_t s = 1.0 / max_diff;
+    Veci<Dim> prev;
+    for (int i = 0; i < Dim; i++) prev(i) = -1;
+    for (int n = 1; n < max_diff; n++) {
+      Vecf<Dim> pt;
+      for (int i = 0; i < Dim; i++) pt(i) = pt1(i) + diff(i) * s * n;
+      const Veci<Dim> pn = floatToInt(pt);
+      if (isOutside(pn)) break;
+      bool same = true;
+      for (int i = 0; i < Dim; i++) same = same && pn(i) == prev(i);
+      if (!same) pns.push_back(pn);
+      prev = pn;
+    }
+    return pns;
+  }
   mplb_map *handle() const { return h_; }
 
  private:
@@ -300,6 +340,10 @@ class MapPlanner {
   void setW(decimal_t w) { set(MPLB_W, w); }
   void setEpsilon(decimal_t eps) { set(MPLB_EPSILON, eps); }
   void setMaxNum(int num) { set(MPLB_MAX_NUM, num); }
+  void setHeurIgnoreDynamics(bool ignore) { /* planner_base.h:233: only the default (true) is on this path */
+    if (!ignore) std::printf("[MapPlanner] heur_ignore_dynamics = false is not supported (env_base.h:67-211 needs a polynomial root finder)\n");
+  }
+  void reset() { traj_ = Trajectory<Dim>(); initialized_ = false; last_ = mplb_result{}; } /* planner_base.h:164-167 */
   void setTol(decimal_t tol_pos, decimal_t tol_vel = -1, decimal_t tol_acc = -1) { /* planner_base.h:255-265 */
     set(MPLB_TOL_POS, tol_pos); set(MPLB_TOL_VEL, tol_vel); set(MPLB_TOL_ACC, tol_acc);
   }
@@ -356,6 +400,41 @@ class MapPlanner {
     for (int i = 0; i < n; i++) ps.push_back(pos_of(nodes[ids[i]]));
     return ps;
   }
+  /* planner_base.h:143-145 (env_map.h:166): finite-cost primitives of every expanded node, in expansion order, rebuilt
+   * by running get_succ (mplb_expand) over the popped states; plain-map plans only. */
+  vec_E<Primitive<Dim>> getExpandedEdges() const {
+    vec_E<Primitive<Dim>> prs;
+    if (!h_ || last_.pops <= 0 || U_.empty()) return prs;
+    std::vector<mplb_node> nodes = fetch_nodes();
+    std::vector<int32_t> ids(last_.pops);
+    const int n = mplb_get_pop_log(h_, ids.data(), (int)ids.size());
+    if (n <= 0) return prs;
+    std::vector<mplb_waypoint> st(n);
+    for (int i = 0; i < n; i++) {
+      const mplb_node &nd = nodes[ids[i]];
+      mplb_waypoint &w = st[i];
+      std::memset(&w, 0, sizeof(w));
+      for (int k = 0; k < 3; k++) { w.pos[k] = nd.state[k]; w.vel[k] = nd.state[3 + k]; w.acc[k] = nd.state[6 + k]; w.jrk[k] = nd.state[9 + k]; }
+      w.yaw = nd.state[12];
+      w.control = (int)control_;
+    }
+    std::vector<mplb_prim_trace> rows((size_t)n * U_.size());
+    if (mplb_expand(h_, st.data(), n, rows.data()) != MPLB_OK) { report(); return prs; }
+    for (int i = 0; i < n; i++)
+      for (size_t a = 0; a < U_.size(); a++) {
+        const mplb_prim_trace &r = rows[(size_t)i * U_.size() + a];
+        if (r.verdict < 3 || std::isinf(r.cost)) continue;
+        Waypoint<Dim> w(control_);
+        for (int k = 0; k < Dim; k++) { w.pos(k) = st[i].pos[k]; w.vel(k) = st[i].vel[k]; w.acc(k) = st[i].acc[k]; w.jrk(k) = st[i].jrk[k]; }
+        w.yaw = st[i].yaw;
+        prs.push_back(Primitive<Dim>(w, U_[a], dt_));
+      }
+    return prs;
+  }
+  /* planner_base.h:30-74: in A* a predecessor record is appended exactly when an expanded node yields a finite-cost
+   * successor (graph_search.h:81,100-102), so both are the set of getExpandedEdges (the reference lists them in hash-map order) */
+  vec_E<Primitive<Dim>> getValidPrimitives() const { return getExpandedEdges(); }
+  vec_E<Primitive<Dim>> getAllPrimitives() const { return getExpandedEdges(); }
   const mplb_result &result() const { return last_; }
   mplb_planner *handle() const { return h_; }
 

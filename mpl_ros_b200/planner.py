@@ -178,6 +178,13 @@ class MapUtil:
     def getOrigin(self):
         return self._info()[1]
 
+    def getCloud(self):  # map_util.h:137-161: centres of the occupied cells
+        nd = self.getDim()
+        grid = self.getMap().reshape(tuple(int(x) for x in nd[::-1]))
+        idx = np.argwhere(grid == 100)[:, ::-1]  # (x, y[, z])
+        idx = idx[np.lexsort(idx[:, ::-1].T)]    # the reference walks x outermost
+        return (idx + 0.5) * self.getRes() + self.getOrigin()
+
     def getMap(self):  # map_util.h:25
         nd = self.getDim()
         out = np.zeros(int(np.prod(nd.astype(np.int64))), dtype=np.int8)
@@ -250,6 +257,11 @@ class MapPlanner:
     def setW(self, w): self._set("w", w)
     def setEpsilon(self, e): self._set("epsilon", e)
     def setMaxNum(self, n): self._set("max_num", n)
+
+    def setHeurIgnoreDynamics(self, ignore):  # planner_base.h:233 — only the default (True) is on this path
+        if not ignore:
+            raise MplbError("heur_ignore_dynamics = false needs the reference's polynomial root finder (env_base.h:67-211); "
+                            "not part of this path")
     def setMemFraction(self, f): self._set("mem_fraction", f)
     def setMaxSlots(self, n): self._set("max_slots", n)
 
@@ -415,6 +427,35 @@ class MapPlanner:
 
     def getExpandedNodes(self):  # planner_base.h:140 (expanded_nodes_, pop order)
         return self.getNodes()["state"][self.getPopLog()][:, :self.dim]
+
+    def getExpandedEdges(self):
+        """planner_base.h:143-145 (env_map.h:166): the finite-cost primitives of every expanded node, in expansion order.
+        Rebuilt by running get_succ (mplb_expand) over the popped states; plain-map plans only."""
+        nodes = self.getNodes()
+        st = nodes["state"][self.getPopLog()]
+        w = waypoints_array(len(st))
+        w["pos"], w["vel"], w["acc"], w["jrk"] = st[:, 0:3], st[:, 3:6], st[:, 6:9], st[:, 9:12]
+        w["control"] = self._control
+        rows = self.expand(w)
+        prs = []
+        for i in range(len(st)):
+            for a in np.flatnonzero(np.isfinite(rows[i]["cost"]) & (rows[i]["verdict"] >= 3)):
+                prs.append(Primitive(self.dim, self._control, st[i], self.U_[a], self.dt_))
+        return prs
+
+    def getValidPrimitives(self):
+        """planner_base.h:30-51: the finite-cost predecessor edges of every node.  In A* a predecessor record is appended
+        exactly when an expanded node yields a finite-cost successor (graph_search.h:81,100-102), so this is the same
+        set of primitives as getExpandedEdges (the reference returns it in hash-map order)."""
+        return self.getExpandedEdges()
+
+    def getAllPrimitives(self):  # planner_base.h:54-74: A* never records an infinite-cost predecessor, same set again
+        return self.getExpandedEdges()
+
+    def reset(self):  # planner_base.h:164-167
+        self._initialized = False
+        self._last = None
+        self.traj_cost_ = None
 
     # ---- batch (north-star extension; every entry behaves like plan())
     def plan_batch(self, starts, goals, max_seg=0, want_states=False):

@@ -53,5 +53,9 @@ int main(int argc, char **argv) {
   std::printf("Total J:  J(VEL) = %f, J(ACC) = %f\n", traj.J(Control::VEL), traj.J(Control::ACC));
   std::printf("cost: %f open: %zu expanded: %zu waypoints: %zu\n", planner->getTrajCost(), planner->getOpenSet().size(),
               planner->getExpandedNodes().size(), traj.getWaypoints().size());
+  std::printf("edges: %zu valid: %zu cloud: %zu ray: %zu\n", planner->getExpandedEdges().size(), planner->getValidPrimitives().size(),
+              map_util->getCloud().size(), map_util->rayTrace(start.pos, goal.pos).size());
+  planner->reset();
+  std::printf("initialized after reset: %d\n", planner->initialized() ? 1 : 0);
   return 0;
 }

@@ -68,6 +68,10 @@ def test_cpp_planner_2d_known_answer(tmp_path):
     assert "Total time T: 35.000000" in out, out                 # MPL/README.md:201
     assert "J(VEL) = 36.750000, J(ACC) = 1.500000" in out, out   # MPL/README.md:202
     assert "cost: 351.500000" in out and "expanded: 615" in out and "waypoints: 36" in out, out
+    # getExpandedEdges / getValidPrimitives = the 2539 finite-cost primitives the survey measured; getCloud = occupied cells
+    n_occ = int((m.data == 100).sum())
+    assert "edges: 2539 valid: 2539 cloud: %d ray:" % n_occ in out, out
+    assert "initialized after reset: 0" in out, out
 
 
 @pytest.mark.gpu

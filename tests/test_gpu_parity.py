@@ -57,6 +57,13 @@ def test_single_plan_parity(name):
     traj = pl.getTraj()
     assert traj.getTotalTime() == ro["n_seg"] * params["dt"]
     assert len(traj.getWaypoints()) == ro["n_seg"] + 1
+    # debug getters rebuilt from the pop log: finite-cost primitives of all expanded nodes (planner_base.h:30-74,143-145)
+    edges = pl.getExpandedEdges()
+    assert len(edges) == ro["n_valid"] == len(pl.getValidPrimitives())
+    mu = pl._keep[0]
+    assert len(mu.getCloud()) == int((mu.getMap() == 100).sum())
+    pl.reset()
+    assert not pl.initialized()
 
 
 @pytest.mark.parametrize("name", ["corridor", "simple", "skir"])
