@@ -169,6 +169,20 @@ def test_snp_2d_and_jrk_125_controls_3d():
     _compare(op, rp, _wp([5.5, 5.5, 0.5], 7), _wp([1.5, 1.5, 5.5], 7), 3, 7, U5, "JRK 125", nodes=False)
 
 
+def test_goal_tolerances_and_weights():
+    """Goal region with velocity / acceleration tolerances (env_map.h:25-45), other w / epsilon / dt values."""
+    m, dim, params, U, start, goal = load_config("corridor")
+    for prm, ctl in ((dict(params, tol_vel=0.3), 3), (dict(params, tol_vel=0.0, max_num=4000), 3),
+                     (dict(v_max=1.0, a_max=1.0, j_max=2.0, dt=1.0, tol_pos=0.5, tol_vel=0.5, tol_acc=0.5, max_num=2500), 7),
+                     (dict(params, w=3.0), 3), (dict(params, w=25.0, epsilon=0.5), 3), (dict(params, dt=0.5, max_num=5000), 3),
+                     (dict(params, epsilon=0.0, max_num=3000), 3)):
+        op, rp = _pair(m, dim, prm, U)
+        ro, rr = op.plan(_wp(start, ctl), _wp(goal, ctl)), rp.plan(_wp(start, ctl), _wp(goal, ctl))
+        assert _same_status(int(ro["status"]), int(rr["status"])), prm
+        for f in ("cost", "pops", "n_nodes", "n_open", "n_closed", "n_prims", "n_valid", "pop_hash", "closed_hash"):
+            assert ro[f] == rr[f] or (f == "cost" and np.isinf(ro[f]) and np.isinf(rr[f])), (prm, f, ro[f], rr[f])
+
+
 @pytest.mark.parametrize("yaw_max,wyaw", [(0.7, 1.0), (-1.0, 1.0), (1.2, 2.5)])
 def test_yaw_controls_libm_definition(yaw_max, wyaw):
     """MPL/test/test_planner_2d_with_yaw.cpp; the oracle in trig_mode 0 calls the same libm as the reference code does."""
