@@ -49,6 +49,7 @@ def lib():
         L.orc_planner_set_vec.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.orc_planner_set_search_region.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.orc_planner_clear_shaping.argtypes = [C.c_void_p]
+        L.orc_planner_set_prior_trajectory.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_planner_set_potential_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_planner_set_search_region_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_planner_get_search_region.restype = C.c_int64
@@ -163,6 +164,9 @@ class OraclePlanner:
             return
         mask = np.ascontiguousarray(mask, dtype=np.uint8).ravel()
         lib().orc_planner_set_search_region_mask(self.h, _ptr(mask), mask.size)
+
+    def set_prior_trajectory(self, src):
+        lib().orc_planner_set_prior_trajectory(self.h, src.h if src is not None else None)
 
     def clear_shaping(self):
         lib().orc_planner_clear_shaping(self.h)

@@ -575,6 +575,8 @@ struct Planner {
   // cost shaping (em:104-118, eb:395-396; MapPlanner members map_planner.h:104-118)
   std::vector<int8_t> potential_map;
   std::vector<bool> search_region;
+  std::vector<std::pair<WP, double>> prior;  // eb:397 prior_traj_
+  WP prior_goal;                             // em:224: goal_node_ = traj.evaluate(total_time)
   double potential_weight = 0.1, gradient_weight = 0.0;  // em:294-296
   double search_radius[3] = {0, 0, 0}, potential_radius[3] = {0, 0, 0}, potential_map_range[3] = {0, 0, 0};
   double pow_ = 1.0;
@@ -611,13 +613,57 @@ struct Planner {
     return goaled;
   }
 
-  /* eb:46-64, heur_ignore_dynamics_ = true (default eb:368), no prior trajectory */
-  double get_heur(const WP &s, const Key &skey) const {
-    if (make_key(goal, dim) == skey) return 0;
+  /* eb:56-64, heur_ignore_dynamics_ = true (default eb:368) */
+  double cal_heur(const WP &s, const WP &target) const {
     double m = 0;
-    for (int i = 0; i < dim; i++) m = std::max(m, std::abs(s.pos[i] - goal.pos[i]));
+    for (int i = 0; i < dim; i++) m = std::max(m, std::abs(s.pos[i] - target.pos[i]));
     if (v_max > 0) return w * m / v_max;
     return w * m;
+  }
+  /* eb:46-53: with a prior trajectory the heuristic is the distance to the prior's waypoint at the state's own time plus
+   * the prior's remaining time cost */
+  double get_heur(const WP &s, const Key &skey) const {
+    if (make_key(goal, dim) == skey) return 0;
+    size_t id = (size_t)(s.t / dt);
+    if (!prior.empty() && id < prior.size()) return cal_heur(s, prior[id].first) + prior[id].second;
+    return cal_heur(s, goal);
+  }
+  /* PlannerBase::setPriorTrajectory -> env_base::set_prior_trajectory (pb:249-252, eb:249-256) from the trajectory of
+   * `src`'s last plan; Trajectory::evaluate (trajectory.h:66-86) without a time-scaling lambda */
+  void set_prior_from(const Planner &src) {
+    prior.clear();
+    const int n = (int)src.traj_actions.size();
+    std::vector<Prim> segs;
+    std::vector<double> taus(1, 0.0);
+    for (int i = 0; i < n; i++) {
+      segs.emplace_back(src.nodes[src.traj_nodes[i]].coord, src.U[src.traj_actions[i]].data(), src.dt, src.dim);
+      taus.push_back(segs.back().T + taus.back());  // trajectory.h:52-57
+    }
+    const double total = taus.back();
+    auto evaluate = [&](double time) {  // trajectory.h:66-86
+      double tau = time;
+      if (tau < 0) tau = 0;
+      if (tau > total) tau = total;
+      WP p;
+      for (size_t id = 0; id < segs.size(); id++) {
+        if ((tau >= taus[id] && tau < taus[id + 1]) || id == segs.size() - 1) {
+          tau -= taus[id];
+          p.control = segs[id].control;
+          for (int j = 0; j < dim; j++) {
+            p.pos[j] = segs[id].ax[j].p(tau); p.vel[j] = segs[id].ax[j].v(tau);
+            p.acc[j] = segs[id].ax[j].a(tau); p.jrk[j] = segs[id].ax[j].j(tau);
+            p.yaw = Prim::normalize_angle(segs[id].yawp.p(tau));
+          }
+          break;
+        }
+      }
+      return p;
+    };
+    /* em:187-225 without a potential map: costs[id] = w t, total_cost = traverse_trajectory (0 on a free path) + w total,
+     * prior cost = total_cost - costs[id]; then the prior's end point becomes the goal */
+    const double total_cost = 0.0 + w * total;
+    for (double t = 0; t < total; t += dt) prior.push_back(std::make_pair(evaluate(t), total_cost - w * t));
+    prior_goal = evaluate(total);
   }
 
   /* em:90-132 */
@@ -797,7 +843,8 @@ struct Planner {
     int pn[3] = {0, 0, 0};
     map->float_to_int(start.pos, pn);
     if (!map->is_free(pn)) { last.status = 1; return 1; }
-    goal = goal_;  // eb:295-298
+    if (prior.empty()) goal = goal_;  // eb:295-298: with a prior trajectory the requested goal is ignored ...
+    else goal = prior_goal;          // ... and the goal stays the prior's end point (em:224)
     // gs:44
     if (is_goal(start)) { last.status = 5; last.cost = 0; return 5; }
     // gs:47-60
@@ -973,6 +1020,10 @@ void orc_planner_set_search_region_mask(void *pp, const uint8_t *mask, int64_t n
   p->search_region.assign((size_t)(mask ? n : 0), false);
   for (int64_t i = 0; mask && i < n; i++) p->search_region[i] = mask[i] != 0;
 }
+void orc_planner_set_prior_trajectory(void *pp, void *src) { /* src = planner whose last plan supplies the trajectory; NULL clears */
+  Planner *p = (Planner *)pp;
+  if (src) p->set_prior_from(*(Planner *)src); else p->prior.clear();
+}
 void orc_planner_clear_shaping(void *pp) { Planner *p = (Planner *)pp; p->search_region.clear(); p->potential_map.clear(); }
 int64_t orc_planner_get_search_region(void *pp, uint8_t *out, int64_t cap) {
   Planner *p = (Planner *)pp;
@@ -1062,6 +1113,7 @@ int orc_plan_batch(void *pp, const orc_waypoint *starts, const orc_waypoint *goa
     local.potential_map = base->potential_map; local.search_region = base->search_region;
     local.potential_weight = base->potential_weight; local.gradient_weight = base->gradient_weight;
     local.wyaw = base->wyaw; local.tol_yaw = base->tol_yaw; local.trig_mode = base->trig_mode;
+    local.prior = base->prior; local.prior_goal = base->prior_goal;
     for (int i = tid; i < n; i += nthreads) {
       local.plan(from_c(starts[i]), from_c(goals[i]));
       results[i] = local.last;

@@ -92,6 +92,9 @@ void orc_planner_set_vec(void *p, const char *key, const double *v);
 void orc_planner_set_search_region(void *p, const double *path, int n, int dense); /* map_planner.cpp:46-95; n rows of 3 doubles */
 void orc_planner_set_potential_map(void *p, const int8_t *pot, int64_t n);          /* env_map.h:182; n = 0 clears */
 void orc_planner_set_search_region_mask(void *p, const uint8_t *mask, int64_t n);   /* env_base.h:301-303; n = 0 clears */
+/* PlannerBase::setPriorTrajectory (planner_base.h:249-252, env_base.h:46-53,249-256): the trajectory of `src`'s last plan
+ * becomes the prior of `p` (NULL clears).  Oracle-only so far: the CUDA path does not implement prior trajectories. */
+void orc_planner_set_prior_trajectory(void *p, void *src);
 void orc_planner_clear_shaping(void *p);
 int64_t orc_planner_get_search_region(void *p, uint8_t *out, int64_t cap);
 void orc_planner_update_potential_map(void *p, const double *pos);                 /* map_planner.cpp:286-391 (rewrites the map) */

@@ -57,6 +57,7 @@ def lib():
         L.ref_planner_update_potential_map.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_iterative_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_planner_set_prior_trajectory.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_get_traj_coeffs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ref_get_pop_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ref_get_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -139,6 +140,9 @@ class RefPlanner:
         res = np.zeros(1, dtype=RESULT_DTYPE)
         lib().ref_iterative_plan(self.h, raw_planner.h, _ptr(start), _ptr(goal), int(max_num), _ptr(res))
         return res[0]
+
+    def set_prior_trajectory(self, src):
+        lib().ref_planner_set_prior_trajectory(self.h, src.h)
 
     def traj_coeffs(self, n_seg):
         out = np.zeros((max(n_seg, 1), 4, 6), dtype=np.float64)

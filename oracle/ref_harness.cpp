@@ -84,6 +84,7 @@ struct IPlanner {
   virtual int get_traj_coeffs(double *out, int cap_seg) = 0;
   virtual int get_pop_keys(int32_t *keys16, int cap) = 0;
   virtual int get_nodes(orc_node *nodes, int cap) = 0;
+  virtual void set_prior(IPlanner *raw) = 0;
   virtual IPlanner *clone_config() = 0;
 };
 
@@ -221,6 +222,7 @@ struct PlannerT : public IPlanner {
     fill_result(ok, true, out);
     return last.status;
   }
+  void set_prior(IPlanner *raw) override { pl->setPriorTrajectory(static_cast<PlannerT<Dim> *>(raw)->pl->traj()); } /* planner_base.h:249-252 */
   int get_traj_coeffs(double *out, int cap_seg) override { /* rows cx, cy, cz, cyaw of toPrimitiveROSMsg, 6 doubles each */
     if (!have_traj) return 0;
     const auto &segs = pl->traj().segs;
@@ -361,6 +363,10 @@ int ref_plan(void *p, const orc_waypoint *s, const orc_waypoint *g, orc_result *
 int ref_iterative_plan(void *p, void *p_raw, const orc_waypoint *s, const orc_waypoint *g, int max_num, orc_result *out) {
   QuietStdout q;
   return ((RefPlanner *)p)->p->iterative_plan(*s, *g, ((RefPlanner *)p_raw)->p, max_num, out);
+}
+void ref_planner_set_prior_trajectory(void *p, void *p_raw) {
+  QuietStdout q; /* env_map.h:209,217 print every prior cost unconditionally */
+  ((RefPlanner *)p)->p->set_prior(((RefPlanner *)p_raw)->p);
 }
 int ref_get_traj_coeffs(void *p, double *out, int cap_seg) { return ((RefPlanner *)p)->p->get_traj_coeffs(out, cap_seg); }
 int ref_get_pop_keys(void *p, int32_t *keys16, int cap) { return ((RefPlanner *)p)->p->get_pop_keys(keys16, cap); }

@@ -243,6 +243,31 @@ def test_distance_map_flow(grad_w):
     assert rit["status"] == 0 and rit["cost"] == roi["cost"] and rit["n_seg"] == roi["n_seg"] and rit["pop_hash"] == roi["pop_hash"]
 
 
+def test_prior_trajectory_heuristic():
+    """MPL/test/test_planner_2d_with_prior_traj.cpp:29-105: a VEL-control plan becomes the prior trajectory of a second
+    planner whose heuristic then follows it (env_base.h:46-53,249-256).  Oracle-only groundwork: the CUDA path does not
+    implement prior trajectories yet."""
+    m, dim, params, _, start, goal = load_config("corridor")
+    U1 = maps.make_U(1.0, 1, 2)
+    op1, rp1 = _pair(m, dim, dict(v_max=1.0, a_max=1.0, dt=1.0), U1)
+    ro1, rr1 = _compare(op1, rp1, _wp(start, 1), _wp(goal, 1), dim, 1, U1, "VEL prior")
+    assert ro1["status"] == 0
+    U2 = maps.make_U(1.0, 1, 2) * 0.5
+    for ctl, prm in ((7, dict(epsilon=1.0, v_max=1.0, a_max=1.0, dt=1.0, w=10.0, tol_pos=0.5, max_num=20000)),
+                     (3, dict(epsilon=1.0, v_max=1.0, a_max=1.0, dt=1.0, w=10.0, tol_pos=0.5))):
+        op2, rp2 = _pair(m, dim, prm, U2)
+        op2.set_prior_trajectory(op1)
+        rp2.set_prior_trajectory(rp1)
+        ro2, rr2 = op2.plan(_wp(start, ctl), _wp(goal, ctl)), rp2.plan(_wp(start, ctl), _wp(goal, ctl))
+        assert _same_status(int(ro2["status"]), int(rr2["status"])), ctl
+        for f in ("cost", "pops", "n_nodes", "n_open", "n_closed", "n_prims", "n_valid", "pop_hash", "closed_hash"):
+            assert ro2[f] == rr2[f] or (f == "cost" and np.isinf(ro2[f]) and np.isinf(rr2[f])), (ctl, f, ro2[f], rr2[f])
+        assert np.array_equal(op2.pop_keys(ro2["pops"]), rp2.pop_keys(rr2["pops"]))
+        # the prior changes the search: a plain planner with the same parameters expands a different set
+        op3, _ = _pair(m, dim, prm, U2)
+        assert op3.plan(_wp(start, ctl), _wp(goal, ctl))["pop_hash"] != ro2["pop_hash"]
+
+
 def test_potential_map_3d_local_range():
     m, dim, params, U, start, goal = load_config("skir")
     op, rp = _pair(m, dim, dict(params, potential_weight=0.2, gradient_weight=0.1), U)
