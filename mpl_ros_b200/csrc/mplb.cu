@@ -950,6 +950,7 @@ void mplb_planner_destroy(mplb_planner *p) {
   p->d_U.release(); p->d_ttab.release(); p->d_toff.release(); p->d_tcnt.release(); p->arena.release();
   p->d_ctrl.release(); p->d_work.release(); p->d_over.release(); p->d_slot.release(); p->d_starts.release();
   p->d_goals.release(); p->d_results.release(); p->d_actions.release(); p->d_segs.release();
+  p->d_keys.release(); p->d_phase.release(); p->d_pot.release(); p->d_region.release(); p->d_Uyaw.release();
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   delete p;
