@@ -42,6 +42,7 @@ def lib():
         L.ref_map_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.ref_map_destroy.argtypes = [C.c_void_p]
         L.ref_map_free_unknown.argtypes = [C.c_void_p]
+        L.ref_map_dilate.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ref_map_get_data.restype = C.c_int64
         L.ref_map_get_data.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.ref_planner_create.restype = C.c_void_p
@@ -76,6 +77,10 @@ class RefMap:
 
     def free_unknown(self):
         lib().ref_map_free_unknown(self.h)
+
+    def dilate(self, ns):
+        ns = np.ascontiguousarray(ns, dtype=np.int32)
+        lib().ref_map_dilate(self.h, _ptr(ns), ns.shape[0])
 
     def get_data(self):
         out = np.zeros(self.ncell, dtype=np.int8)

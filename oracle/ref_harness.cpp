@@ -327,6 +327,18 @@ void *ref_map_create(int dim, const int32_t *nd, const double *origin, double re
 }
 void ref_map_destroy(void *map) { delete (MapAny *)map; }
 void ref_map_free_unknown(void *map) { MapAny *m = (MapAny *)map; if (m->dim == 2) m->m2.mu->freeUnknown(); else m->m3.mu->freeUnknown(); }
+void ref_map_dilate(void *map, const int32_t *ns, int n) { /* MapUtil::dilate, map_util.h:221-257; ns = n rows of Dim ints */
+  MapAny *m = (MapAny *)map;
+  if (m->dim == 2) {
+    vec_Vec2i v;
+    for (int i = 0; i < n; i++) v.push_back(Vec2i(ns[i * 2], ns[i * 2 + 1]));
+    m->m2.mu->dilate(v);
+  } else {
+    vec_Vec3i v;
+    for (int i = 0; i < n; i++) v.push_back(Vec3i(ns[i * 3], ns[i * 3 + 1], ns[i * 3 + 2]));
+    m->m3.mu->dilate(v);
+  }
+}
 int64_t ref_map_get_data(void *map, int8_t *out, int64_t cap) {
   MapAny *m = (MapAny *)map;
   const auto v = m->dim == 2 ? m->m2.mu->getMap() : m->m3.mu->getMap();

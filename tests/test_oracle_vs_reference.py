@@ -277,3 +277,26 @@ def test_potential_map_3d_local_range():
         p.update_potential_map(np.asarray(start, dtype=np.float64))
     assert np.array_equal(op._keep.get_data(int(np.prod(m.dim))), rp._keep.get_data())
     _compare(op, rp, _wp(start, 3), _wp(goal, 3), dim, 3, U, "potential 3d")
+
+
+def test_map_ops_against_reference_sources():
+    """MapUtil::freeUnknown / dilate (map_util.h:221-276) of the reference's code against the numpy formulation that
+    tests/test_gpu_parity.py::test_map_ops holds the GPU map kernels to."""
+    m = maps.load_fixture("simple")
+    data = m.data.copy()
+    data[::7] = -1
+    rm = ref.RefMap(m.origin, m.dim, data, m.res)
+    assert np.array_equal(rm.get_data(), data)
+    rm.free_unknown()
+    want = np.where(data == -1, 0, data)
+    assert np.array_equal(rm.get_data(), want)
+    ns = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0]], dtype=np.int32)
+    rm.dilate(ns)
+    g = want.reshape(tuple(int(x) for x in m.dim[::-1]))
+    out = g.copy()
+    occ = g == 100
+    out[:, :, 1:][occ[:, :, :-1]] = 100
+    out[:, :, :-1][occ[:, :, 1:]] = 100
+    out[:, 1:, :][occ[:, :-1, :]] = 100
+    out[:, :-1, :][occ[:, 1:, :]] = 100
+    assert np.array_equal(rm.get_data(), out.reshape(-1))
