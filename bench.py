@@ -5,23 +5,32 @@
   python bench.py --impl reference --gpus N --steps K ...   the reference's CPU implementation on host cores: its own
                                                             sources (oracle/_ref, stand-in Eigen/Boost headers) when
                                                             that binary is present, else the oracle port
+  --workload c2 (default) | c5        --queries Q (default 65536)
 
-Workload (BASELINE.json configs[1], SURVEY.md §8d "C2"): levine-256 (levine.bag upsampled 2x, cropped and placed
-in a 256^3 int8 grid), |U| = 27 acceleration controls u in {-1,0,1}^3, dt = 1, v_max = 2, a_max = 1, w = 10,
-eps = 1, tol_pos = 0.5, 1024 (start, goal) pairs per GPU drawn with RandomState(rank) from free voxel centres,
-unreachable pairs kept.  A "step" is one pass of the whole batch through the planner.  Unit of work: one
-primitive expansion = one (popped state, u) pair entering env_map.h:155.
+Workloads (mpl_ros_b200/workloads.py):
+  c2  BASELINE configs[1] scaled to the north-star batch: levine-256 (levine.bag upsampled 2x, cropped, placed in a 256^3
+      int8 grid), |U| = 27 acceleration controls, dt = 1, v_max = 2, a_max = 1, tol_pos = 0.5; ONE list of 65 536
+      (start, goal) pairs, RandomState(0), unreachable pairs kept.  The list is sharded over the N ranks (query i ->
+      rank i mod N: strong scaling).  The literal configs[1] batch (the first 1024 queries of the list, one GPU) is
+      measured in the same run and reported under config.batch1024.
+  c5  BASELINE configs[4]: synthetic 1024^3 box map, |U| = 125 jerk controls, dt = 0.5, v_max = 3, a_max = 2,
+      max_num = 50 000, 65 536 pairs RandomState(2) with L-inf distance in [3 m, 30 m].
+A "step" is one pass of the whole list through the planner: every rank plans its stripe, rank 0 gathers the result
+records and action rows (the one data-path collective).  Unit of work: one primitive expansion = one (popped state, u)
+pair entering env_map.h:155.
 
-`value`   : device-resident inputs/outputs (mplb_plan_batch_device), CUDA events on the launch stream.
-`e2e`     : the public host-buffer call (MapPlanner.plan_batch -> mplb_plan_batch) with pinned host inputs,
-            H2D of starts/goals and D2H of results + action rows inside the timed region.
+`value`   : device-resident stripes (ShardedBatchPlanner.plan_stripe_device -> mplb_plan_batch_device + gather), CUDA
+            events on the launch stream, max over ranks.
+`e2e`     : the public host-buffer call (ShardedBatchPlanner.plan_batch -> MapPlanner.plan_batch -> mplb_plan_batch) with
+            pinned host inputs: H2D of the stripe's starts/goals, D2H of results + action rows and the gather inside the
+            timed region.
 `roofline`: ALGORITHMIC bytes per primitive expansion (SURVEY.md §8d formula, recomputed from the kernel's own
             counters) x expansions per launch / launch duration, against MEASURED_PEAKS.json hbm_gbs.
-`cpu_baseline`: the reference's CPU path on this box's host cores, bounded sample: oracle/_ref ("reference": the reference's
-            own planner sources compiled against the stand-in headers of oracle/shim/) when present, else the oracle
-            port ("port"); the port is always run as well because it doubles as the in-bench parity check.
+`cpu_baseline`: the reference's CPU path on this box's host cores, bounded sample (dynamic work queue over the sample,
+            longest plans first, threads pinned): oracle/_ref ("reference") when present, else the oracle port ("port").
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -34,10 +43,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BATCH = 1024
 MAX_SEG = 64
-WORKLOAD = "levine256_U27_acc_batch1024"
-PLAN_PARAMS = dict(v_max=2.0, a_max=1.0, dt=1.0, tol_pos=0.5)
 
 
 def load_peaks():
@@ -47,21 +53,59 @@ def load_peaks():
     return 6650.0, "fallback"
 
 
-def make_queries(m, rank, n=BATCH):
-    from mpl_ros_b200 import maps
-    import mpl_ros_b200 as mp
-    S, G = maps.sample_queries(m, n, seed=rank)
-    s, g = mp.waypoints_array(n), mp.waypoints_array(n)
-    s["pos"], g["pos"], s["control"], g["control"] = S, G, mp.ACC, mp.ACC
-    return s, g
+def workload(name):
+    from mpl_ros_b200 import workloads as W
+    if name == "c2":
+        return dict(spec=W.C2, tag="levine256_U27_acc", make_map=W.c2_map, make_queries=W.c2_queries,
+                    map_note="levine-256 (256^3 int8, 16 MiB; kernel reads 2 MiB of occupancy bit-bricks)",
+                    b_state=56.0, b_succ=72.0, kernel="astar_batch_kernel<3,2,1,0>", cpu_sample=1024, cpu_threads=None,
+                    mem_fraction=None)
+    return dict(spec=W.C5, tag="boxes1024_U125_jrk", make_map=W.c5_map, make_queries=W.c5_queries,
+                map_note="synthetic boxes 1024^3 int8 (1 GiB; kernel reads 128 MiB of occupancy bit-bricks)",
+                b_state=80.0, b_succ=96.0, kernel="astar_batch_kernel<3,3,4,0>", cpu_sample=16, cpu_threads=16,
+                mem_fraction=0.85)
 
 
-def b_alg(res, nU):
-    """B_alg = B_state/|U| + S_mean*1 + p_valid*(B_succ + B_probe), C2 sizes."""
+def src_sha():
+    """Hash of the kernel sources: profiles/traffic.json entries are only trusted for the code they were captured on."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "mpl_ros_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def b_alg(res, nU, wl):
+    """B_alg = B_state/|U| + S_mean*1 + p_valid*(B_succ + B_probe)."""
     prims = float(res["n_prims"].sum())
     s_mean = float(res["n_samples"].sum()) / prims
     p_valid = float(res["n_valid"].sum()) / prims
-    return 56.0 / nU + s_mean + p_valid * (72.0 + 16.0), s_mean, p_valid
+    return wl["b_state"] / nU + s_mean + p_valid * (wl["b_succ"] + 16.0), s_mean, p_valid
+
+
+def lpt_order(m, S, G):
+    """Longest-plans-first processing order for the CPU queue (scheduling only): queries whose goal lies in another
+    free-space component exhaust the start's component, then larger L-inf distance first — the same hint the GPU path
+    computes with its own label kernels."""
+    try:
+        from scipy import ndimage
+    except Exception:
+        return None
+    nd = tuple(int(x) for x in m.dim[::-1])
+    if int(np.prod(nd)) > (1 << 26):
+        return None
+    lab, _ = ndimage.label(m.data.reshape(nd) != 100)
+    size = np.bincount(lab.ravel())
+
+    def cell(P):
+        c = np.floor((P - m.origin) / m.res).astype(np.int64)
+        c = np.clip(c, 0, m.dim.astype(np.int64) - 1)
+        return lab[c[:, 2], c[:, 1], c[:, 0]] if m.ndim == 3 else lab[c[:, 1], c[:, 0]]
+    ls, lg = cell(S), cell(G)
+    dist = np.abs(S - G).max(axis=1)
+    key = np.where((ls != lg) & (ls > 0), 1e9 + size[ls], dist)
+    return np.argsort(-key, kind="stable").astype(np.int32)
 
 
 class ClockSampler:
@@ -116,39 +160,62 @@ class ClockSampler:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
-def cpu_planner(m, U, prefer_reference=True):
-    """(planner, kind): the reference's own sources (oracle/_ref) when that library is present, else the oracle port.
-    Both expose plan_batch(starts, goals, nthreads) -> results with n_prims per plan."""
+KIND_NOTE = {"reference": "the reference's own planner sources (oracle/_ref: stand-in Eigen/Boost headers, see oracle/shim)",
+             "port": "oracle port (oracle/_ref absent)"}
+
+
+def cpu_planners(m, U, wl):
+    """{'port': planner, 'reference': planner or absent}; both expose plan_batch(s, g, nthreads, order, pin, want_busy)."""
     import oracle
-    if prefer_reference:
+    params = wl["spec"]["params"]
+    out = {}
+    om = oracle.OracleMap(m.origin, m.dim, m.data, m.res)
+    om.free_unknown()
+    op = oracle.OraclePlanner(3)
+    op.set_map(om)
+    for k, v in params.items():
+        op.set_param(k, v)
+    op.set_controls(U)
+    op._keep = om
+
+    class _Port:
+        def plan_batch(self, s, g, **kw):
+            r = op.plan_batch(s, g, want_busy=True, **kw)
+            return r[0], r[2]
+    out["port"] = _Port()
+    try:
         from oracle import ref
         if ref.available():
             rm = ref.RefMap(m.origin, m.dim, m.data, m.res)
             rm.free_unknown()
             rp = ref.RefPlanner(3)
             rp.set_map(rm)
-            for k, v in PLAN_PARAMS.items():
+            for k, v in params.items():
                 rp.set_param(k, v)
             rp.set_controls(U)
             rp._keep = rm
-            return rp, "reference"
-    om = oracle.OracleMap(m.origin, m.dim, m.data, m.res)
-    om.free_unknown()
-    op = oracle.OraclePlanner(3)
-    op.set_map(om)
-    for k, v in PLAN_PARAMS.items():
-        op.set_param(k, v)
-    op.set_controls(U)
-    op._keep = om
 
-    class _Port:
-        def plan_batch(self, s, g, nthreads=1):
-            return op.plan_batch(s, g, nthreads=nthreads)[0]
-    return _Port(), "port"
+            class _Ref:
+                def plan_batch(self, s, g, **kw):
+                    return rp.plan_batch(s, g, want_busy=True, **kw)
+            out["reference"] = _Ref()
+    except Exception as e:  # a broken checker build must not take the bench line down: the port always exists
+        out["reference_error"] = repr(e)[:200]
+    return out
 
 
-KIND_NOTE = {"reference": "the reference's own planner sources (oracle/_ref: stand-in Eigen/Boost headers, see oracle/shim)",
-             "port": "oracle port (oracle/_ref absent)"}
+def cpu_sample_queries(S, G, control, n):
+    import oracle
+    so, go = oracle.make_waypoints(n), oracle.make_waypoints(n)
+    so["pos"], go["pos"], so["control"], go["control"] = S[:n], G[:n], control, control
+    return so, go
+
+
+def time_cpu(pl, so, go, threads, order):
+    t0 = time.perf_counter()
+    res, busy = pl.plan_batch(so, go, nthreads=threads, order=order, pin=True)
+    dt = time.perf_counter() - t0
+    return res, dt, float(busy.sum() / (dt * threads))
 
 
 def run_reference(args):
@@ -156,35 +223,40 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
-    from mpl_ros_b200 import maps
-    m = maps.levine256()
-    U = maps.make_U(1.0, 1, 3)
-    try:
-        op, kind = cpu_planner(m, U)
-    except Exception:  # checker build unusable on this box: the oracle port always exists
-        op, kind = cpu_planner(m, U, prefer_reference=False)
-    s, g = make_queries(m, 0)
+    wl = workload(args.workload)
+    from mpl_ros_b200 import workloads as W
+    m = wl["make_map"]()
+    U = W.controls(wl["spec"])
+    n_s = args.cpu_sample or wl["cpu_sample"]
+    S, G = wl["make_queries"](m, n_s)
+    pls = cpu_planners(m, U, wl)
+    kind = "reference" if "reference" in pls else "port"
+    pl = pls[kind]
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample
-    so, go = oracle.make_waypoints(sample), oracle.make_waypoints(sample)
-    for f in ("pos", "control"):
-        so[f], go[f] = s[f][:sample], g[f][:sample]
+    threads = min(cores, wl["cpu_threads"] or cores, n_s)
+    so, go = cpu_sample_queries(S, G, wl["spec"]["control"], n_s)
+    order = lpt_order(m, S, G)
     for _ in range(args.warmup):
-        op.plan_batch(so[:8], go[:8], nthreads=cores)
+        pl.plan_batch(so[:min(threads, n_s)], go[:min(threads, n_s)], nthreads=threads, pin=True)
     t0 = time.perf_counter()
-    prims = 0
+    prims, util, ms_all = 0, [], []
     for _ in range(args.steps):
-        res = op.plan_batch(so, go, nthreads=cores)
+        res, dt, u = time_cpu(pl, so, go, threads, order)
         prims += int(res["n_prims"].sum())
+        util.append(u)
+        ms_all.append(res["device_ms"])
     dt = time.perf_counter() - t0
     v = prims / dt
+    ms_all = np.concatenate(ms_all)
+    sample = "first %d of the %d queries per step (bounded sample), atomic work queue, longest plans first, threads pinned" % (
+        n_s, wl["spec"]["n_queries"])
     line = {"impl": "reference", "metric": "primitive_expansions_per_sec", "value": v, "unit": "prim_exp/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "step": "first %d of the 1024 queries per step (bounded sample)" % sample},
-            "cpu_baseline": {"value": v, "unit": "prim_exp/s", "cores": cores, "kind": kind, "what": KIND_NOTE[kind],
-                             "sample": "first %d queries of the rank-0 batch, %d steps, std::thread striping" % (sample, args.steps)},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s_batch%d" % (wl["tag"], wl["spec"]["n_queries"]), "step": sample,
+                       "ms_per_plan_p50": float(np.percentile(ms_all, 50)), "ms_per_plan_p95": float(np.percentile(ms_all, 95))},
+            "cpu_baseline": {"value": v, "unit": "prim_exp/s", "cores": threads, "kind": kind, "what": KIND_NOTE[kind],
+                             "sample": sample, "thread_utilisation": float(np.mean(util))},
             "e2e": {"value": v, "unit": "prim_exp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -195,8 +267,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mplb", choices=["mplb", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=256, help="queries in the CPU-baseline sample")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
+    ap.add_argument("--queries", type=int, default=0, help="length of the global query list (default: the workload's 65536)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU-baseline sample (default per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch1024", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -205,8 +280,11 @@ def main():
 
     import torch
     import mpl_ros_b200 as mp
-    from mpl_ros_b200 import _lib, maps
+    from mpl_ros_b200 import _lib, workloads as W
+    from mpl_ros_b200 import dist as mdist
 
+    wl = workload(args.workload)
+    spec = wl["spec"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -216,47 +294,57 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("MPLB_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # stdout carries the one JSON line: NCCL's own log (NCCL_DEBUG as the caller set it) goes to a file unless the
+        # caller already chose one
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl.bench.%h.%p.log")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- map: rank 0 builds it, one NCCL broadcast puts it in every GPU's HBM
-    U = maps.make_U(1.0, 1, 3)
-    m = maps.levine256() if rank == 0 or world == 1 else None
-    mu = mp.VoxelMapUtil()
-    if world > 1:
-        from mpl_ros_b200 import dist as mdist
-        o, d, r, grid = mdist.broadcast_map(m.origin if m else None, m.dim if m else None, m.res if m else None,
-                                            m.data if m else None, dev)
-        mu.setMapFromDevice(o, d, grid.data_ptr(), r)
-        if m is None:
-            m = maps.GridMap(o, d, r, grid.cpu().numpy())
-    else:
-        mu.setMap(m.origin, m.dim, m.data, m.res)
-    mu.freeUnknown()
-    pl = mp.VoxelMapPlanner(False)
-    pl.setMapUtil(mu)
-    pl.setVmax(PLAN_PARAMS["v_max"]); pl.setAmax(PLAN_PARAMS["a_max"]); pl.setDt(PLAN_PARAMS["dt"])
-    pl.setU(U); pl.setTol(PLAN_PARAMS["tol_pos"])
+    # ---- map and the ONE query list: rank 0 builds both; one NCCL broadcast of the grid puts the map in every GPU's
+    # HBM, one broadcast hands every rank the list it takes its stripe from
+    U = W.controls(spec)
+    nq = args.queries or spec["n_queries"]
+    m = wl["make_map"]() if rank == 0 else None
 
-    s, g = make_queries(m, rank)
-    hs = torch.from_numpy(s.view(np.uint8).reshape(BATCH, -1)).pin_memory()
-    hg = torch.from_numpy(g.view(np.uint8).reshape(BATCH, -1)).pin_memory()
+    def make_planner(o, d, r, grid):
+        mu = mp.VoxelMapUtil()
+        mu.setMapFromDevice(o, d, grid.data_ptr(), r)
+        mu.freeUnknown()
+        pl = mp.VoxelMapPlanner(False)
+        pl.setMapUtil(mu)
+        p = spec["params"]
+        pl.setVmax(p["v_max"]); pl.setAmax(p["a_max"]); pl.setDt(p["dt"]); pl.setU(U); pl.setTol(p["tol_pos"])
+        if "max_num" in p:
+            pl.setMaxNum(p["max_num"])
+        if wl["mem_fraction"]:
+            pl.setMemFraction(wl["mem_fraction"])
+        pl._keep = mu
+        return pl
+
+    sp = mdist.ShardedBatchPlanner(make_planner, dev)
+    if m is not None:
+        sp.set_map(m.origin, m.dim, m.res, m.data)
+    else:
+        sp.set_map()
+    pl = sp.planner
+    s_all, g_all = mp.waypoints_array(nq), mp.waypoints_array(nq)
+    if rank == 0:
+        S, G = wl["make_queries"](m, nq)
+        W.fill(s_all, g_all, S, G, spec["control"])
+    s_all, g_all = sp.broadcast_queries(s_all, g_all)
+    idx = mdist.shard_indices(nq, rank, world)
+    n_loc = len(idx)
+    hs = torch.from_numpy(np.ascontiguousarray(s_all[idx]).view(np.uint8).reshape(n_loc, -1)).pin_memory()
+    hg = torch.from_numpy(np.ascontiguousarray(g_all[idx]).view(np.uint8).reshape(n_loc, -1)).pin_memory()
     ds, dg = hs.to(dev), hg.to(dev)
-    dres = torch.zeros(BATCH, _lib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    dact = torch.zeros(BATCH, MAX_SEG, dtype=torch.int32, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
-
-    gres = [torch.empty_like(dres) for _ in range(world)] if (world > 1 and rank == 0) else None
-    gact = [torch.empty_like(dact) for _ in range(world)] if (world > 1 and rank == 0) else None
+    bufs = sp.make_device_buffers(nq, MAX_SEG)
 
     def step_device():
-        pl.plan_batch_device(ds.data_ptr(), dg.data_ptr(), BATCH, dres.data_ptr(), dact.data_ptr(), 0, MAX_SEG,
-                             stream.cuda_stream)
-        if dist is not None:  # the one data-path collective per batch: gather result records + action rows on rank 0
-            dist.gather(dres, gres, dst=0)
-            dist.gather(dact, gact, dst=0)
+        return sp.plan_stripe_device(ds, dg, n_loc, bufs, MAX_SEG, stream)
 
     def barrier():
         if dist is not None:
@@ -282,120 +370,156 @@ def main():
     t_wall1 = time.time()
     clk = clocks.stop(t_wall0, t_wall1)
     launches = int(_lib.lib().mplb_launch_count() - launches0)
-    ms_steps = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(ms_steps))
-    res = dres.cpu().numpy().view(_lib.RESULT_DTYPE).reshape(-1)
-    prims = int(res["n_prims"].sum())
-    pops = int(res["pops"].sum())
+    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    res_loc = bufs["res"].cpu().numpy().view(_lib.RESULT_DTYPE).reshape(-1)[:n_loc]
+    res_all, _ = sp.unstripe(bufs, nq, MAX_SEG) if rank == 0 else (None, None)
 
-    # ---- e2e through the public host-buffer API (pinned inputs, H2D + D2H inside the timed region)
-    s_pin, g_pin = hs.numpy().view(_lib.WAYPOINT_DTYPE).reshape(-1), hg.numpy().view(_lib.WAYPOINT_DTYPE).reshape(-1)
-    pl.plan_batch(s_pin, g_pin, max_seg=MAX_SEG)
+    # ---- e2e through the public host-buffer API (pinned inputs, H2D + D2H + gather inside the timed region)
+    s_pin = hs.numpy().view(_lib.WAYPOINT_DTYPE).reshape(-1)
+    g_pin = hg.numpy().view(_lib.WAYPOINT_DTYPE).reshape(-1)
+    sp.plan_batch_local(s_pin, g_pin, nq, MAX_SEG)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        res_h, acts_h, _ = pl.plan_batch(s_pin, g_pin, max_seg=MAX_SEG)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_steps = max(2, min(args.steps, int(30e3 * args.steps / max(total_ms, 1.0))))
     flush_ms = 0.0
     tf0, tf1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tf0.record(); flush.zero_(); tf1.record(); torch.cuda.synchronize()
     flush_ms = tf0.elapsed_time(tf1)
-    e2e_ms -= flush_ms * args.steps
-    assert np.array_equal(res_h.view(np.uint8), res.view(np.uint8)), "host-API results differ from device-API results"
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        res_h, acts_h = sp.plan_batch_local(s_pin, g_pin, nq, MAX_SEG)
+    barrier()
+    e2e_ms = ((time.perf_counter() - t0) * 1e3 - flush_ms * e2e_steps) / e2e_steps
+    if rank == 0:
+        for f in ("status", "pops", "n_nodes", "pop_hash", "closed_hash", "n_seg"):
+            assert np.array_equal(res_h[f], res_all[f]), "host-API results differ from device-API results: " + f
 
-    # ---- multi-GPU: max over ranks of the timed region, whole-job units; one gather of result records
-    tot = np.array([total_ms, e2e_ms, float(prims), float(pops), float(np.mean(kernel_ms))])
+    # ---- multi-GPU: max over ranks of the timed region
+    tot = np.array([total_ms, e2e_ms, float(np.mean(kernel_ms))])
     if dist is not None:
         t = torch.tensor(tot, dtype=torch.float64, device=dev)
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, e2e_ms, kms = float(tmax[0]), float(tmax[1]), float(tmax[4])
-        prims_all, pops_all = float(tsum[2]), float(tsum[3])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms, kms_max = (float(x) for x in t.cpu().numpy())
     else:
-        prims_all, pops_all, kms = float(prims), float(pops), float(np.mean(kernel_ms))
+        kms_max = float(np.mean(kernel_ms))
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    value = prims_all * args.steps / (total_ms * 1e-3)
-    e2e_v = prims_all * args.steps / (e2e_ms * 1e-3)
+    prims_all, pops_all = float(res_all["n_prims"].sum()), float(res_all["pops"].sum())
+    ms_step = total_ms / args.steps
+    value = prims_all / (ms_step * 1e-3)
+    e2e_v = prims_all / (e2e_ms * 1e-3)
     peak, peak_kind = load_peaks()
-    balg, s_mean, p_valid = b_alg(res, U.shape[0])
-    ach = prims * balg / (kms * 1e-3) / 1e9
-    traffic = None
+    balg, s_mean, p_valid = b_alg(res_loc, U.shape[0], wl)
+    kms = float(np.mean(kernel_ms))
+    ach = float(res_loc["n_prims"].sum()) * balg / (kms * 1e-3) / 1e9
+    traffic, traffic_note = None, "no ncu capture recorded for this workload"
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
-        traffic = json.load(open(prof)).get("astar_batch_kernel_dram_bytes_per_launch")
+        ent = json.load(open(prof)).get(args.workload)
+        if ent and ent.get("src_sha") == src_sha() and ent.get("queries_per_launch") == n_loc:
+            traffic, traffic_note = ent["dram_bytes_per_launch"], "ncu --set full capture %s of this code and launch size" % ent.get("capture", "")
+        elif ent:
+            traffic_note = "stale: the recorded capture is of other kernel sources or another launch size"
 
-    ok = res["status"] == 0
+    dms = res_all["device_ms"]
+    # single-plan latency through the public API (what map_planner_node does): a few queries one at a time
+    lat = []
+    for i in range(min(8, nq)):
+        a, b = s_all[i:i + 1].copy(), g_all[i:i + 1].copy()
+        t0 = time.perf_counter()
+        pl.plan(a, b)
+        lat.append((time.perf_counter() - t0) * 1e3)
+
+    ok = res_all["status"] == 0
+    cfg = {"workload": "%s_batch%d" % (wl["tag"], nq), "map": wl["map_note"], "U": int(U.shape[0]), "global_batch": nq,
+           "parallelism": "one query list sharded over %d rank(s), query i -> rank i mod N; map broadcast + result gather" % world,
+           "l2": "flushed between timed iterations (512 MiB memset outside the event pairs)",
+           "plans_per_sec": nq / (ms_step * 1e-3),
+           "ms_per_plan_p50": float(np.percentile(dms, 50)), "ms_per_plan_p95": float(np.percentile(dms, 95)),
+           "ms_per_plan_max": float(dms.max()),
+           "ms_per_plan_note": "device time of each plan inside the batch (mplb_result.device_ms), all ranks",
+           "single_plan_api_ms_p50": float(np.median(lat)),
+           "node_expansions_per_sec": pops_all / (ms_step * 1e-3),
+           "success_rate": float(ok.mean()), "unreachable_rate": float((res_all["status"] == 3).mean()),
+           "max_expand_rate": float((res_all["status"] == 2).mean()),
+           "mean_samples_per_prim": s_mean, "p_valid": p_valid, "e2e_steps": e2e_steps}
     line = {
         "metric": "primitive_expansions_per_sec", "value": value, "unit": "prim_exp/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "map": "levine-256 (256^3 int8, 16 MiB; kernel reads 2 MiB of occupancy bit-bricks)",
-                   "U": 27, "batch_per_gpu": BATCH, "parallelism": "query-sharded dp%d" % world,
-                   "l2": "flushed between timed iterations (512 MiB memset outside the event pairs)",
-                   "plans_per_sec": BATCH * world * args.steps / (total_ms * 1e-3),
-                   "ms_per_plan_mean": total_ms / args.steps / BATCH,
-                   "node_expansions_per_sec": pops_all * args.steps / (total_ms * 1e-3),
-                   "success_rate": float(ok.mean()), "unreachable_rate": float((res["status"] == 3).mean()),
-                   "mean_samples_per_prim": s_mean, "p_valid": p_valid},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "e2e": {"value": e2e_v, "unit": "prim_exp/s",
-                "h2d_bytes_per_step": int(2 * BATCH * _lib.WAYPOINT_DTYPE.itemsize),
-                "d2h_bytes_per_step": int(BATCH * (_lib.RESULT_DTYPE.itemsize + 4 * MAX_SEG))},
+                "h2d_bytes_per_step": int(2 * nq * _lib.WAYPOINT_DTYPE.itemsize),
+                "d2h_bytes_per_step": int(nq * (_lib.RESULT_DTYPE.itemsize + 4 * MAX_SEG))},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                     "kernel": "astar_batch_kernel<3,2>", "alg_bytes_per_prim": balg, "peak_kind": peak_kind + " (burst copy)",
-                     "kernel_ms_per_launch": kms,
+                     "traffic_note": traffic_note, "kernel": wl["kernel"], "alg_bytes_per_prim": balg,
+                     "peak_kind": peak_kind + " (burst copy)", "kernel_ms_per_launch": kms,
+                     "kernel_ms_per_launch_max_over_ranks": kms_max,
                      "note": "latency/issue-bound search bookkeeping, not HBM-bound: see DESIGN.md roofline section"},
     }
+
+    # ---- the literal configs[1] batch: the first 1024 queries on one GPU (N = 1 only)
+    if world == 1 and not args.no_batch1024 and nq >= 1024 and args.workload == "c2":
+        nb = 1024
+        b = sp.make_device_buffers(nb, MAX_SEG)
+        d1s, d1g = ds[:nb].contiguous(), dg[:nb].contiguous()
+        for _ in range(3):
+            flush.zero_()
+            sp.plan_stripe_device(d1s, d1g, nb, b, MAX_SEG, stream)
+        torch.cuda.synchronize()
+        nst = min(args.steps, 10)
+        e1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nst)]
+        for k in range(nst):
+            flush.zero_()
+            e1[k][0].record(stream)
+            sp.plan_stripe_device(d1s, d1g, nb, b, MAX_SEG, stream)
+            e1[k][1].record(stream)
+        torch.cuda.synchronize()
+        ms1 = float(np.mean([x.elapsed_time(y) for x, y in e1]))
+        r1 = b["res"].cpu().numpy().view(_lib.RESULT_DTYPE).reshape(-1)[:nb]
+        cfg["batch1024"] = {"what": "BASELINE configs[1] as literally stated: the first 1024 queries of the list in one launch",
+                            "value": float(r1["n_prims"].sum()) / (ms1 * 1e-3), "unit": "prim_exp/s", "ms_per_step": ms1,
+                            "steps": nst, "ms_per_plan_p50": float(np.percentile(r1["device_ms"], 50)),
+                            "ms_per_plan_p95": float(np.percentile(r1["device_ms"], 95))}
+
     if not args.no_cpu_baseline:
-        import oracle
-        om = oracle.OracleMap(m.origin, m.dim, m.data, m.res)
-        om.free_unknown()
-        op = oracle.OraclePlanner(3)
-        op.set_map(om)
-        for k, v in PLAN_PARAMS.items():
-            op.set_param(k, v)
-        op.set_controls(U)
+        n_s = min(args.cpu_sample or wl["cpu_sample"], nq)
         cores = os.cpu_count() or 1
-        n_s = args.cpu_sample
-        so, go = oracle.make_waypoints(n_s), oracle.make_waypoints(n_s)
-        for f in ("pos", "control"):
-            so[f], go[f] = s[f][:n_s], g[f][:n_s]
-        t0 = time.perf_counter()
-        ro, _ = op.plan_batch(so, go, nthreads=cores)
-        dt_all = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        r1, _ = op.plan_batch(so[:8], go[:8], nthreads=1)
-        dt_1 = time.perf_counter() - t0
-        for f in ("status", "pops", "n_nodes", "pop_hash", "cost"):  # the sample doubles as an in-bench parity check
-            a, b = ro[f], res[f][:n_s]
-            assert np.array_equal(a, b) or f == "cost" and np.array_equal(a[np.isfinite(a)], b[np.isfinite(b)]), f
-        port_v = float(ro["n_prims"].sum()) / dt_all
-        cb = {"value": port_v, "unit": "prim_exp/s", "cores": cores, "kind": "port",
-              "single_core_value": float(r1["n_prims"].sum()) / dt_1,
-              "sample": "first %d of the 1024 rank-0 queries, one std::thread per core; GPU results for the same queries "
-                        "checked equal against the oracle port" % n_s}
-        try:
-            rp, kind = cpu_planner(m, U)
-        except Exception as e:  # a broken checker build must not take the bench line down: the port result stands
-            rp, kind = None, "port"
-            cb["reference_unavailable"] = repr(e)[:200]
-        if kind == "reference":  # the reference's own sources: time them on the same sample and check them too
-            t0 = time.perf_counter()
-            rr = rp.plan_batch(so, go, nthreads=cores)
-            dt_ref = time.perf_counter() - t0
-            for f in ("pops", "n_nodes", "pop_hash", "cost"):
-                a, b = rr[f], res[f][:n_s]
-                assert np.array_equal(a, b) or f == "cost" and np.array_equal(a[np.isfinite(a)], b[np.isfinite(b)]), ("reference", f)
+        threads = min(cores, wl["cpu_threads"] or cores, n_s)
+        Sq, Gq = s_all["pos"][:n_s], g_all["pos"][:n_s]
+        so, go = cpu_sample_queries(Sq, Gq, spec["control"], n_s)
+        order = lpt_order(m, Sq, Gq)
+        pls = cpu_planners(m, U, wl)
+        ro, dt_port, util_port = time_cpu(pls["port"], so, go, threads, order)
+        n1 = min(8, n_s)
+        r1c, dt_1, _ = time_cpu(pls["port"], so[:n1], go[:n1], 1, None)
+        for f in ("status", "pops", "n_nodes", "pop_hash", "closed_hash", "cost"):  # the sample doubles as an in-bench parity check
+            a, b2 = ro[f], res_all[f][:n_s]
+            assert np.array_equal(a, b2) or f == "cost" and np.array_equal(a[np.isfinite(a)], b2[np.isfinite(b2)]), f
+        port_v = float(ro["n_prims"].sum()) / dt_port
+        sample = ("first %d of the %d queries, atomic work queue (longest plans first), %d pinned threads; GPU results for "
+                  "the same queries checked equal against the oracle port" % (n_s, nq, threads))
+        cb = {"value": port_v, "unit": "prim_exp/s", "cores": threads, "host_cores": cores, "kind": "port",
+              "thread_utilisation": util_port, "single_core_value": float(r1c["n_prims"].sum()) / dt_1,
+              "ms_per_plan_p50": float(np.percentile(ro["device_ms"], 50)), "ms_per_plan_p95": float(np.percentile(ro["device_ms"], 95)),
+              "sample": sample}
+        if "reference_error" in pls:
+            cb["reference_unavailable"] = pls["reference_error"]
+        if "reference" in pls:  # the reference's own sources: time them on the same sample and check them too
+            rr, dt_ref, util_ref = time_cpu(pls["reference"], so, go, threads, order)
+            for f in ("pops", "n_nodes", "pop_hash", "closed_hash", "cost"):
+                a, b2 = rr[f], res_all[f][:n_s]
+                assert np.array_equal(a, b2) or f == "cost" and np.array_equal(a[np.isfinite(a)], b2[np.isfinite(b2)]), ("reference", f)
             cb.update({"value": float(rr["n_prims"].sum()) / dt_ref, "kind": "reference", "what": KIND_NOTE["reference"],
-                       "port_value": port_v})
+                       "thread_utilisation": util_ref, "port_value": port_v,
+                       "ms_per_plan_p50": float(np.percentile(rr["device_ms"], 50)),
+                       "ms_per_plan_p95": float(np.percentile(rr["device_ms"], 95))})
             cb["sample"] += " and against the reference's own sources"
         line["cpu_baseline"] = cb
     print(json.dumps(line))

@@ -359,7 +359,9 @@ class MapPlanner {
   bool plan(const Coord &start, const Coord &goal) {
     mplb_waypoint s = to_c(start), g = to_c(goal);
     control_ = start.control;
-    traj_ = Trajectory<Dim>();
+    /* traj_ is rewritten only where the reference writes it: recoverTraj's success or failure (graph_search.h:447-451);
+     * start-not-free (planner_base.h:283-287), start-is-goal (graph_search.h:44), MaxExpandStep and the empty queue
+     * (graph_search.h:149-161) leave the previous trajectory in place. */
     if (!h_ || mplb_plan(h_, &s, &g, &last_) != MPLB_OK) { report(); traj_cost_ = std::numeric_limits<decimal_t>::infinity(); return false; }
     initialized_ = true;
     traj_cost_ = last_.cost;
@@ -376,7 +378,7 @@ class MapPlanner {
         prs.push_back(Primitive<Dim>(w, U_[acts[i]], dt_));
       }
       traj_ = Trajectory<Dim>(prs);
-    }
+    } else if (last_.status == MPLB_PLAN_TRACEBACK_FAILED) traj_ = Trajectory<Dim>();
     return last_.status == MPLB_PLAN_OK || last_.status == MPLB_PLAN_START_IS_GOAL;
   }
 

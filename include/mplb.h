@@ -75,6 +75,8 @@ typedef struct mplb_result {
   int64_t n_valid;     /* finite-cost successors (graph_search.h:81 passes) */
   uint64_t pop_hash;   /* order-dependent hash of popped lattice keys (parity artefact) */
   uint64_t closed_hash;/* order-independent hash of closed lattice keys (parity artefact) */
+  double device_ms;    /* device time of this plan: from the moment a CTA picked it up to its result record (%globaltimer);
+                          the per-plan latency behind the p50/p95 figures of bench.py.  Not a reference quantity. */
 } mplb_result;
 
 /* One (state, u) row of env_map::get_succ, env_map.h:147-172 (parity artefact + micro-benchmark output). */

@@ -15,12 +15,12 @@ WAYPOINT_DTYPE = np.dtype([("pos", "f8", 3), ("vel", "f8", 3), ("acc", "f8", 3),
                            ("yaw", "f8"), ("t", "f8"), ("control", "i4"), ("enable_t", "i4")], align=True)
 RESULT_DTYPE = np.dtype([("status", "i4"), ("n_seg", "i4"), ("cost", "f8"), ("pops", "i4"), ("n_nodes", "i4"),
                          ("n_open", "i4"), ("n_closed", "i4"), ("n_prims", "i8"), ("n_samples", "i8"),
-                         ("n_valid", "i8"), ("pop_hash", "u8"), ("closed_hash", "u8")], align=True)
+                         ("n_valid", "i8"), ("pop_hash", "u8"), ("closed_hash", "u8"), ("device_ms", "f8")], align=True)
 TRACE_DTYPE = np.dtype([("verdict", "i4"), ("n", "i4"), ("n_tested", "i4"), ("block_idx", "i4"), ("cost", "f8"),
                         ("succ", "f8", 13), ("key", "i4", 16)], align=True)
 NODE_DTYPE = np.dtype([("state", "f8", 13), ("g", "f8"), ("h", "f8"), ("key", "i4", 16), ("opened", "i4"),
                        ("closed", "i4"), ("parent", "i4"), ("action", "i4")], align=True)
-assert WAYPOINT_DTYPE.itemsize == 120 and RESULT_DTYPE.itemsize == 72
+assert WAYPOINT_DTYPE.itemsize == 120 and RESULT_DTYPE.itemsize == 80
 
 # every symbol include/mplb.h declares: (restype, argtypes)
 _VP, _I, _D = C.c_void_p, C.c_int, C.c_double

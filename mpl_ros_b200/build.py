@@ -5,6 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "mplb.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "mplb_search.cuh"), os.path.join(HERE, "csrc", "mplb_device.cuh"),
+        os.path.join(HERE, "csrc", "mplb_trig.cuh"),
         os.path.join(HERE, "..", "include", "mplb.h")]
 OUT = os.path.join(HERE, "libmplb.so")
 

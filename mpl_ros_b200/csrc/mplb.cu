@@ -282,6 +282,12 @@ __global__ void k_serialize_traj(const __grid_constant__ MsgArgs a) {
   }
 }
 
+/* plans that fit no arena tier: their (internal overflow) status becomes MPLB_PLAN_NOMEM */
+__global__ void k_mark_status(mplb_result *results, const int *work, int n_work, int status) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_work) results[work ? work[i] : i].status = status;
+}
+
 __global__ void k_sincos_cr(const double *x, int n, double *s, double *c) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) trig::sincos_cr(x[i], &s[i], &c[i]);
@@ -381,11 +387,14 @@ struct Layout {
   int tsize_max;
 };
 
-Layout make_layout(int cap, int ns, int nU) {
+/* Large tiers (hundreds of MB per plan) trade probe length for room: load factor <= 1/2 instead of 1/4. */
+int load_inv_of(int cap) { return cap > 262144 ? 2 : MPLB_LOAD_INV; }
+
+Layout make_layout(int cap, int ns, int nU, bool want_poplog) {
   Layout L;
-  int ts = MPLB_TINIT;
-  while ((long long)ts < (long long)MPLB_LOAD_INV * (cap + nU)) ts <<= 1;
-  L.tsize_max = ts;
+  long long ts = MPLB_TINIT; /* 64-bit: the last tier would overflow an int (the caller stops tiering at 2^30 table slots) */
+  while (ts < (long long)load_inv_of(cap) * ((long long)cap + nU) && ts < (1ll << 30)) ts <<= 1;
+  L.tsize_max = (int)ts;
   size_t o = 0;
   L.row_bytes = (sizeof(RowHdr) + (size_t)ns * sizeof(double) + 15) & ~(size_t)15;
   o += align_up((size_t)cap * sizeof(NodeHot), 256);
@@ -396,7 +405,7 @@ Layout make_layout(int cap, int ns, int nU) {
   L.off_table = o;
   o += align_up((size_t)ts * sizeof(Slot), 256);
   L.off_poplog = o;
-  o += align_up((size_t)cap * sizeof(int), 256);
+  if (want_poplog) o += align_up((size_t)cap * sizeof(int), 256);
   L.stride = o;
   return L;
 }
@@ -677,13 +686,15 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
   int n_work = n;
   bool identity = true;
   int cap = 32768;
-  if (c.max_num > 0) { /* MaxExpandStep bounds the node count by max_num * |U|: start in the tier that is likely to fit */
-    long long est = (long long)c.max_num * c.nU + c.nU + 64;
-    while (cap < est && cap < 262144) cap *= 8;
+  /* MaxExpandStep bounds the node count by max_num * |U| (every pop creates at most |U| nodes): no tier needs more */
+  const long long cap_bound = c.max_num > 0 ? std::min<long long>((long long)c.max_num * c.nU + 2LL * c.nU + 64, 1ll << 30) : (1ll << 30);
+  if (c.max_num > 0) { /* start in the tier that is likely to fit */
+    while (cap < cap_bound && cap < 262144) cap *= 8;
   }
+  cap = (int)std::min<long long>(cap, std::max<long long>(cap_bound, 1024));
   p->last_launches = 0; p->last_tiers = 0;
   bool ev0_done = false;
-  if (n > resident / 2 && n <= 8192) { /* longest-first order (scheduling only): see k_plan_keys */
+  if (n > resident / 2 && n <= 65536) { /* longest-first order (scheduling only): see k_plan_keys */
     mplb_map *m = p->map;
     if (m->ncell <= (1ull << 26) && m->labels_version != m->version) {
       if (!m->d_labels && cudaMalloc((void **)&m->d_labels, m->ncell * sizeof(int)) != cudaSuccess) { cudaGetLastError(); m->d_labels = nullptr; }
@@ -724,18 +735,16 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
   }
   if (!ev0_done) CUDA_TRY(cudaEventRecord(p->ev0, s));
   while (n_work > 0) {
-    Layout L = make_layout(cap, c.ns, c.nU);
+    Layout L = make_layout(cap, c.ns, c.nU, retain);
     int slots = std::min(n_work, resident);
     if (p->max_slots > 0) slots = std::min(slots, p->max_slots);
     if ((size_t)slots * L.stride > budget) slots = (int)(budget / L.stride);
-    if (slots <= 0) { /* nothing larger fits: the remaining plans report NOMEM (their overflow status is rewritten) */
-      std::vector<int> ids(n_work);
-      CUDA_TRY(cudaMemcpyAsync(ids.data(), p->d_work.p, n_work * sizeof(int), cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(cudaStreamSynchronize(s));
-      for (int id : ids) {
-        int st = MPLB_PLAN_NOMEM;
-        CUDA_TRY(cudaMemcpyAsync(&d_results[id].status, &st, sizeof(int), cudaMemcpyHostToDevice, s));
-      }
+    if (slots <= 0 || (long long)load_inv_of(cap) * ((long long)cap + c.nU) > (1ll << 30)) {
+      /* nothing larger fits (or the table would pass 2^30 slots): the remaining plans report NOMEM.  In the first tier
+       * the work list may be the identity (no id array was written), later tiers carry the overflow list. */
+      k_mark_status<<<(n_work + 255) / 256, 256, 0, s>>>(d_results, identity ? nullptr : p->d_work.p, n_work, MPLB_PLAN_NOMEM);
+      g_launches++;
+      CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaStreamSynchronize(s));
       break;
     }
@@ -751,7 +760,7 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
     std::memset(&a, 0, sizeof(a));
     a.starts = d_starts; a.goals = d_goals; a.results = d_results; a.actions = d_actions; a.seg_states = d_segs;
     a.max_seg = max_seg; a.work = identity ? nullptr : p->d_work.p; a.n_work = n_work;
-    a.work_counter = p->d_ctrl.p; a.arena = p->arena.p; a.stride = L.stride; a.cap = cap; a.tsize_max = L.tsize_max;
+    a.work_counter = p->d_ctrl.p; a.arena = p->arena.p; a.stride = L.stride; a.cap = cap; a.tsize_max = L.tsize_max; a.load_inv = load_inv_of(cap);
     a.off_rows = L.off_rows; a.off_heap = L.off_heap; a.off_table = L.off_table; a.off_poplog = L.off_poplog;
     a.want_poplog = retain ? 1 : 0; a.slot_of_plan = retain ? p->d_slot.p : nullptr;
     a.overflow_count = p->d_ctrl.p + 1; a.overflow_list = p->d_over.p;
@@ -775,8 +784,8 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
     std::swap(p->d_work, p->d_over);
     n_work = n_over;
     identity = false;
-    if (cap > (1 << 27)) { cap = 1 << 30; continue; }
-    cap *= 8;
+    if (cap >= cap_bound || cap > (1 << 27)) { cap = 1 << 30; continue; } /* beyond every budget: the next pass reports NOMEM */
+    cap = (int)std::min<long long>((long long)cap * 8, cap_bound);
   }
   CUDA_TRY(cudaEventRecord(p->ev1, s));
   CUDA_TRY(cudaEventSynchronize(p->ev1));
@@ -1256,11 +1265,18 @@ int mplb_plan_batch(mplb_planner *p, const mplb_waypoint *starts, const mplb_way
 
 int mplb_plan(mplb_planner *p, const mplb_waypoint *start, const mplb_waypoint *goal, mplb_result *out) {
   if (!p || !start || !goal || !out) return fail(MPLB_ERR_ARG, "null argument");
-  const int max_seg = 4096;
+  int max_seg = 4096;
   p->ret_actions.assign(max_seg, -1);
   p->ret_segs.assign((size_t)max_seg * 13, 0.0);
   int rc = plan_batch_host(p, start, goal, 1, out, p->ret_actions.data(), p->ret_segs.data(), max_seg, true);
   if (rc != MPLB_OK) return rc;
+  if (out->status == MPLB_PLAN_OK && out->n_seg > max_seg) { /* longer than the retained rows: plan again with room (deterministic) */
+    max_seg = out->n_seg;
+    p->ret_actions.assign(max_seg, -1);
+    p->ret_segs.assign((size_t)max_seg * 13, 0.0);
+    rc = plan_batch_host(p, start, goal, 1, out, p->ret_actions.data(), p->ret_segs.data(), max_seg, true);
+    if (rc != MPLB_OK) return rc;
+  }
   p->ret_result = *out;
   p->ret_slot = 0;
   CUDA_TRY(cudaMemcpy(&p->ret_slot, p->d_slot.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1278,14 +1294,14 @@ int mplb_plan(mplb_planner *p, const mplb_waypoint *start, const mplb_waypoint *
 int mplb_get_actions(mplb_planner *p, int32_t *actions, int cap) {
   if (!p || !p->retained) return fail(MPLB_ERR_STATE, "no retained plan");
   int n = p->ret_result.n_seg;
-  for (int i = 0; i < n && i < cap && actions; i++) actions[i] = p->ret_actions[i];
+  for (int i = 0; i < n && i < cap && i < (int)p->ret_actions.size() && actions; i++) actions[i] = p->ret_actions[i];
   return n;
 }
 
 int mplb_get_seg_states(mplb_planner *p, double *states13, int cap) {
   if (!p || !p->retained) return fail(MPLB_ERR_STATE, "no retained plan");
   int n = p->ret_result.n_seg;
-  for (int i = 0; i < n && i < cap && states13; i++) std::memcpy(states13 + (size_t)i * 13, &p->ret_segs[(size_t)i * 13], 13 * sizeof(double));
+  for (int i = 0; i < n && i < cap && (size_t)(i + 1) * 13 <= p->ret_segs.size() && states13; i++) std::memcpy(states13 + (size_t)i * 13, &p->ret_segs[(size_t)i * 13], 13 * sizeof(double));
   return n;
 }
 

@@ -111,6 +111,12 @@ struct HeapEnt {
 };
 static_assert(sizeof(HeapEnt) == 24, "HeapEnt must be 24 bytes");
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 /* cmp(a,b) of compare_pair: true iff a is worse (lower priority) than b. */
 __device__ __forceinline__ bool heap_worse(double af, double ag, double bf, double bg) {
   return (af == bf) ? (ag > bg) : (af > bf);
@@ -129,6 +135,7 @@ struct BatchArgs {
   size_t stride;
   int cap;       /* nodes (and heap entries, pop-log entries) per slot */
   int tsize_max; /* table slots per slot arena (power of two) */
+  int load_inv;  /* table load factor bound 1/load_inv of this tier (MPLB_LOAD_INV in the small tiers, 2 in the large ones) */
   size_t off_rows, off_heap, off_table, off_poplog;
   int want_poplog;
   int *slot_of_plan;   /* optional: which slot ran plan i (retained single plan) */
@@ -217,6 +224,7 @@ struct PlanSmem {
   double pf_st[NS];
   int n_nodes, n_heap, tsize, pops, n_closed, status, plan_idx;
   long long n_samples, n_valid;
+  unsigned long long t_start; /* %globaltimer when this CTA picked the plan up */
   unsigned long long pop_hash, closed_hash;
 #ifdef MPLB_PHASE_TIMING
   unsigned long long dbg[8];
@@ -905,7 +913,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
 
   while (true) {
     __syncthreads();
-    if (tid == 0) S.plan_idx = atomicAdd(a.work_counter, 1);
+    if (tid == 0) { S.plan_idx = atomicAdd(a.work_counter, 1); S.t_start = global_timer_ns(); }
     __syncthreads();
     const int w = S.plan_idx;
     if (w >= a.n_work) break;
@@ -1015,19 +1023,19 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
         __syncthreads();
         break;
       }
-      if ((S.n_nodes + c.nU) * MPLB_LOAD_INV > S.tsize) { /* keep the load factor <= 1/MPLB_LOAD_INV: grow in place and re-insert every node */
-        int nt = S.tsize;
-        while ((S.n_nodes + c.nU) * MPLB_LOAD_INV > nt) nt <<= 1;
+      if ((long long)(S.n_nodes + c.nU) * a.load_inv > S.tsize) { /* keep the load factor <= 1/load_inv: grow in place and re-insert every node */
+        long long nt = S.tsize;
+        while ((long long)(S.n_nodes + c.nU) * a.load_inv > nt) nt <<= 1;
         __syncthreads();
         if (nt > a.tsize_max) { if (tid == 0) S.status = MPLB_INTERNAL_OVERFLOW; __syncthreads(); break; }
         unsigned long long *t64 = reinterpret_cast<unsigned long long *>(table);
-        for (int i = tid; i < 4 * nt; i += MPLB_NT) t64[i] = 0ull;
+        for (size_t i = tid; i < 4 * (size_t)nt; i += MPLB_NT) t64[i] = 0ull;
         __syncthreads();
         for (int i = tid; i < S.n_nodes; i += MPLB_NT) {
           RowHdr *rh = reinterpret_cast<RowHdr *>(rows + (size_t)i * ROWB);
-          rh->slot = table_insert_atomic(table, nt, rh->k0, rh->k1, i, hot[i].g, hot[i].pg);
+          rh->slot = table_insert_atomic(table, (int)nt, rh->k0, rh->k1, i, hot[i].g, hot[i].pg);
         }
-        if (tid == 0) S.tsize = nt;
+        if (tid == 0) S.tsize = (int)nt;
         __syncthreads();
       }
 
@@ -1041,9 +1049,11 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
           if (lane == 0) { E.pk0 = S.cur_k0; E.pk1 = S.cur_k1; }
           __syncwarp();
           b1_warp<DIM, ORD, NB>(c, S, E, lane, fast);
-          if (lane == 0) { E.node = S.cur_node; E.ready = 1; }
         }
         if (warp != NW - 1) asm volatile("bar.sync 1, %0;" ::"n"(MPLB_NT - 32) : "memory"); /* B1 outputs visible to the sampling warps */
+        /* E.node / E.ready are deliberately left alone: every warp evaluates `hit` from them right after the loop-end
+         * barrier, and a write here could reach a late warp before it has done so.  The record is rewritten by the
+         * heap warp before it is consulted again (the next pop uses the other record). */
       }
       MPLB_TICK(0);
       if (warp == NW - 1) {
@@ -1357,6 +1367,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
           }
         }
       }
+      r.device_ms = (double)(global_timer_ns() - S.t_start) * 1e-6;
       a.results[pid] = r;
       if (r.status == MPLB_INTERNAL_OVERFLOW) a.overflow_list[atomicAdd(a.overflow_count, 1)] = pid;
     }

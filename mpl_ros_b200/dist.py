@@ -1,17 +1,24 @@
 """Multi-GPU sharding of a query batch: one process per GPU, torch.distributed for the plumbing.
 
 The path shards by query (plans are independent and read-only on the map).  There are exactly
-two collectives: one broadcast of the voxel grid per map, and one gather of fixed-stride result records per
-batch.  No other data-path communication exists; within one plan there is nothing to shard.
+two collectives on the data path: one broadcast of the voxel grid per map, and one gather of fixed-stride result
+records per batch (plus, at set-up, one broadcast of the query list when only one rank holds it).  Within one plan
+there is nothing to shard.
 
 Works with backend "nccl" (GPU tensors, NVLink/NVSwitch) and "gloo" (CPU tensors; used by the CPU tests with a
-stand-in planner, since libmplb has no CPU path).
+stand-in planner, since libmplb has no CPU path), and without a process group at all (world size 1).
 """
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import _lib
+
+
+def _rank_world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
 
 
 def shard_indices(n, rank, world):
@@ -22,7 +29,11 @@ def shard_indices(n, rank, world):
 def broadcast_map(origin, dim, res, data, device, src=0):
     """Rank `src` supplies the map; every rank returns (origin, dim, res, grid tensor on `device`).
     One broadcast of a small header and one of the int8 grid."""
-    rank = dist.get_rank()
+    rank, world = _rank_world()
+    if world == 1:
+        dimv = np.asarray(dim, dtype=np.int32)
+        grid = torch.as_tensor(np.ascontiguousarray(data, dtype=np.int8).reshape(-1)).to(device)
+        return np.asarray(origin, dtype=np.float64).copy(), dimv, float(res), grid
     hdr = torch.zeros(8, dtype=torch.float64, device=device)
     if rank == src:
         nd = len(dim)
@@ -47,7 +58,10 @@ def gather_results(local_results, local_actions, n_total, max_seg, device, dst=0
     """Gather per-rank result records (and action rows) to rank `dst`, restoring global query order.
     local_results: numpy structured array (RESULT_DTYPE) for queries shard_indices(n_total, rank, world).
     Returns (results[n_total], actions[n_total, max_seg]) on dst, (None, None) elsewhere."""
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world = _rank_world()
+    if world == 1:
+        acts = np.ascontiguousarray(local_actions, dtype=np.int32) if max_seg else np.full((n_total, 0), -1, dtype=np.int32)
+        return local_results, acts
     per = (n_total + world - 1) // world
     rec = _lib.RESULT_DTYPE.itemsize
     row = rec + 4 * max_seg
@@ -94,12 +108,13 @@ class ShardedBatchPlanner:
         per cell, env_base::set_search_region) on every rank's planner: rank `src` supplies them (e.g. the map its own
         planner rewrote with updatePotentialMap), the others receive them with one broadcast each.  None on `src`
         clears that piece everywhere."""
-        rank = dist.get_rank()
+        rank, world = _rank_world()
         flags = torch.zeros(2, dtype=torch.int64, device=self.device)
         if rank == src:
             flags[0] = 0 if potential is None else int(np.asarray(potential).size)
             flags[1] = 0 if region is None else int(np.asarray(region).size)
-        dist.broadcast(flags, src)
+        if world > 1:
+            dist.broadcast(flags, src)
         n_pot, n_reg = (int(x) for x in flags.cpu().numpy())
         for n, arr, dtype, setter in ((n_pot, potential, np.int8, "setPotentialMap"), (n_reg, region, np.uint8, "setSearchRegionMask")):
             if n == 0:
@@ -110,12 +125,67 @@ class ShardedBatchPlanner:
                 t = torch.as_tensor(np.ascontiguousarray(arr, dtype=dtype).reshape(-1)).to(self.device)
             else:
                 t = torch.empty(n, dtype=tdt, device=self.device)
-            dist.broadcast(t, src)
+            if world > 1:
+                dist.broadcast(t, src)
             getattr(self.planner, setter)(t.cpu().numpy())
+
+    def broadcast_queries(self, starts, goals, src=0):
+        """Rank `src` holds the query list; every rank returns it (one broadcast of the two waypoint arrays)."""
+        rank, world = _rank_world()
+        if world == 1:
+            return starts, goals
+        n = len(starts)
+        host = np.concatenate([starts.view(np.uint8).reshape(n, -1), goals.view(np.uint8).reshape(n, -1)]) if rank == src else None
+        t = torch.as_tensor(host).to(self.device) if rank == src else torch.empty((2 * n, _lib.WAYPOINT_DTYPE.itemsize), dtype=torch.uint8,
+                                                                                 device=self.device)
+        dist.broadcast(t, src)
+        b = t.cpu().numpy()
+        return (np.ascontiguousarray(b[:n]).view(_lib.WAYPOINT_DTYPE).reshape(-1),
+                np.ascontiguousarray(b[n:]).view(_lib.WAYPOINT_DTYPE).reshape(-1))
+
+    # ---- device-resident stripes (inputs and outputs stay in HBM; the gather moves device buffers)
+    def make_device_buffers(self, n_total, max_seg, dst=0):
+        rank, world = _rank_world()
+        per = (n_total + world - 1) // world
+        b = {"res": torch.zeros(per, _lib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=self.device),
+             "act": torch.zeros(per, max(max_seg, 1), dtype=torch.int32, device=self.device), "gres": None, "gact": None}
+        if world > 1 and rank == dst:
+            b["gres"] = [torch.empty_like(b["res"]) for _ in range(world)]
+            b["gact"] = [torch.empty_like(b["act"]) for _ in range(world)]
+        return b
+
+    def plan_stripe_device(self, d_starts, d_goals, n_local, bufs, max_seg, stream=None, dst=0):
+        """This rank's stripe (device tensors of waypoint records) through mplb_plan_batch_device, then the one gather of
+        result records and action rows on `dst`."""
+        rank, world = _rank_world()
+        self.planner.plan_batch_device(d_starts.data_ptr(), d_goals.data_ptr(), n_local, bufs["res"].data_ptr(),
+                                       bufs["act"].data_ptr() if max_seg else 0, 0, max_seg,
+                                       stream.cuda_stream if stream is not None else 0)
+        if world > 1:
+            dist.gather(bufs["res"], bufs["gres"], dst=dst)
+            dist.gather(bufs["act"], bufs["gact"], dst=dst)
+
+    def unstripe(self, bufs, n_total, max_seg):
+        """On the gather destination: (results[n_total], actions[n_total, max_seg]) in global query order."""
+        rank, world = _rank_world()
+        results = np.zeros(n_total, dtype=_lib.RESULT_DTYPE)
+        actions = np.full((n_total, max_seg), -1, dtype=np.int32)
+        parts = zip(bufs["gres"], bufs["gact"]) if world > 1 else [(bufs["res"], bufs["act"])]
+        for r, (tr, ta) in enumerate(parts):
+            idx = shard_indices(n_total, r, world)
+            results[idx] = np.ascontiguousarray(tr.cpu().numpy()[:len(idx)]).view(_lib.RESULT_DTYPE).reshape(-1)
+            if max_seg:
+                actions[idx] = ta.cpu().numpy()[:len(idx), :max_seg]
+        return results, actions
+
+    def plan_batch_local(self, starts_local, goals_local, n_total, max_seg=64, dst=0):
+        """Host buffers holding only this rank's stripe (queries shard_indices(n_total, rank, world))."""
+        res, acts, _ = self.planner.plan_batch(starts_local, goals_local, max_seg=max_seg)
+        return gather_results(res, acts, n_total, max_seg, self.device, dst)
 
     def plan_batch(self, starts, goals, max_seg=64, dst=0):
         """starts/goals: full arrays on every rank (host, WAYPOINT_DTYPE). Each rank plans its stripe."""
-        rank, world = dist.get_rank(), dist.get_world_size()
+        rank, world = _rank_world()
         idx = shard_indices(len(starts), rank, world)
         res, acts, _ = self.planner.plan_batch(np.ascontiguousarray(starts[idx]), np.ascontiguousarray(goals[idx]),
                                                max_seg=max_seg)

@@ -130,3 +130,35 @@ def sample_queries(m, n, seed=0, min_dist=2.0, max_dist=None):
         starts[i], goals[i] = s, g
         i += 1
     return starts, goals
+
+
+def sample_queries_local(m, n, seed=2, min_dist=3.0, max_dist=30.0, chunk=1 << 16):
+    """n (start, goal) pairs for large maps: the start is a uniformly drawn free voxel centre, the
+    goal a free voxel centre drawn uniformly from the cells within `max_dist` (L-inf) of the start, re-drawn while the
+    L-inf distance is < min_dist.  Rejection sampling on cell coordinates with RandomState(seed), vectorised in chunks,
+    so that a 1024^3 grid needs neither an index of its free cells nor a Python loop per query.  Unreachable pairs are
+    kept."""
+    rs = np.random.RandomState(seed)
+    dim = m.dim.astype(np.int64)
+    nd = m.ndim
+    rad = int(np.floor(max_dist / m.res))
+    starts = np.zeros((0, nd), dtype=np.int64)
+    goals = np.zeros((0, nd), dtype=np.int64)
+
+    def lin(c):
+        idx = c[:, 0] + dim[0] * c[:, 1]
+        if nd == 3:
+            idx = idx + dim[0] * dim[1] * c[:, 2]
+        return idx
+
+    while starts.shape[0] < n:
+        s = np.stack([rs.randint(0, dim[k], size=chunk) for k in range(nd)], axis=1)
+        off = rs.randint(-rad, rad + 1, size=(chunk, nd))
+        g = s + off
+        ok = np.all((g >= 0) & (g < dim), axis=1)
+        d = np.abs(off).max(axis=1) * m.res
+        ok &= (d >= min_dist) & (d <= max_dist)
+        ok[ok] &= (m.data[lin(s[ok])] == 0) & (m.data[lin(g[ok])] == 0)
+        starts = np.concatenate([starts, s[ok]])
+        goals = np.concatenate([goals, g[ok]])
+    return m.int_to_float(starts[:n]), m.int_to_float(goals[:n])

@@ -227,6 +227,7 @@ class MapPlanner:
         self._last = None
         self._control = None
         self.traj_cost_ = None
+        self.traj_ = Trajectory()
         self._initialized = False
         # map_planner.h:104-113
         self.search_radius_ = np.zeros(3)
@@ -374,7 +375,16 @@ class MapPlanner:
         self._control = int(s["control"][0])
         self._initialized = True
         self.traj_cost_ = float(res[0]["cost"])
-        return int(res[0]["status"]) in (PLAN_OK, PLAN_START_IS_GOAL)
+        st = int(res[0]["status"])
+        # traj_ is rewritten only where the reference writes it: recoverTraj success or failure (graph_search.h:447-451).
+        # start-not-free (planner_base.h:283-287), start-is-goal (graph_search.h:44), MaxExpandStep and empty queue
+        # (graph_search.h:149-161) leave the previous trajectory in place.
+        if st == PLAN_OK:
+            acts, seg = self.getActions(), self.getSegStates()
+            self.traj_ = Trajectory([Primitive(self.dim, self._control, seg[i], self.U_[acts[i]], self.dt_) for i in range(len(acts))])
+        elif st == PLAN_TRACEBACK_FAILED:
+            self.traj_ = Trajectory()
+        return st in (PLAN_OK, PLAN_START_IS_GOAL)
 
     def result(self):
         return self._last
@@ -397,11 +407,8 @@ class MapPlanner:
         check(lib().mplb_get_seg_states(self._h, ptr(s), s.shape[0]))
         return s[:n]
 
-    def getTraj(self):  # planner_base.h:28 + recoverTraj graph_search.h:369-455
-        if self._last is None or int(self._last["status"]) != PLAN_OK:
-            return Trajectory()
-        acts, st = self.getActions(), self.getSegStates()
-        return Trajectory([Primitive(self.dim, self._control, st[i], self.U_[acts[i]], self.dt_) for i in range(len(acts))])
+    def getTraj(self):  # planner_base.h:28 (traj_ as last written by recoverTraj, graph_search.h:369-455)
+        return self.traj_
 
     def getNodes(self):
         n = check(lib().mplb_get_nodes(self._h, None, 0))

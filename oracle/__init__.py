@@ -16,7 +16,7 @@ WAYPOINT_DTYPE = np.dtype([("pos", "f8", 3), ("vel", "f8", 3), ("acc", "f8", 3),
                            ("yaw", "f8"), ("t", "f8"), ("control", "i4"), ("enable_t", "i4")], align=True)
 RESULT_DTYPE = np.dtype([("status", "i4"), ("n_seg", "i4"), ("cost", "f8"), ("pops", "i4"), ("n_nodes", "i4"),
                          ("n_open", "i4"), ("n_closed", "i4"), ("n_prims", "i8"), ("n_samples", "i8"),
-                         ("n_valid", "i8"), ("pop_hash", "u8"), ("closed_hash", "u8")], align=True)
+                         ("n_valid", "i8"), ("pop_hash", "u8"), ("closed_hash", "u8"), ("device_ms", "f8")], align=True)
 TRACE_DTYPE = np.dtype([("verdict", "i4"), ("n", "i4"), ("n_tested", "i4"), ("block_idx", "i4"), ("cost", "f8"),
                         ("succ", "f8", 13), ("key", "i4", 16)], align=True)
 NODE_DTYPE = np.dtype([("state", "f8", 13), ("t", "f8"), ("g", "f8"), ("h", "f8"), ("key", "i4", 16),
@@ -64,6 +64,8 @@ def lib():
         L.orc_get_pop_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_get_succ_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_plan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_plan_batch_dyn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -201,10 +203,14 @@ class OraclePlanner:
         lib().orc_get_succ_trace(self.h, _ptr(curr), _ptr(rows), rows.size)
         return rows
 
-    def plan_batch(self, starts, goals, nthreads=1, max_seg=0):
+    def plan_batch(self, starts, goals, nthreads=1, max_seg=0, order=None, pin=False, want_busy=False):
+        """Threads pull plans from an atomic queue (in `order` when given); results do not depend on the schedule."""
         n = len(starts)
         res = np.zeros(n, dtype=RESULT_DTYPE)
         acts = np.full((n, max_seg), -1, dtype=np.int32) if max_seg > 0 else None
-        lib().orc_plan_batch(self.h, _ptr(starts), _ptr(goals), n, nthreads, _ptr(res),
-                             _ptr(acts) if acts is not None else None, max_seg)
-        return res, acts
+        order = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+        busy = np.zeros(max(nthreads, 1), dtype=np.float64)
+        lib().orc_plan_batch_dyn(self.h, _ptr(starts), _ptr(goals), n, nthreads, _ptr(res),
+                                 _ptr(acts) if acts is not None else None, max_seg,
+                                 _ptr(order) if order is not None else None, int(bool(pin)), _ptr(busy))
+        return (res, acts, busy) if want_busy else (res, acts)

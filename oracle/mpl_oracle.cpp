@@ -23,8 +23,14 @@
  */
 #include "mpl_oracle.h"
 
+#include <pthread.h>
+#include <sched.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1100,11 +1106,22 @@ int orc_get_succ_trace(void *pp, const orc_waypoint *curr, orc_prim_trace *rows,
   return n;
 }
 
-int orc_plan_batch(void *pp, const orc_waypoint *starts, const orc_waypoint *goals, int n, int nthreads,
-                   orc_result *results, int32_t *actions, int max_seg) {
+/* Dynamic work queue: threads pull the next plan index from an atomic counter (in `order` when given, e.g. longest
+ * first), one private planner per thread (the reference is single-threaded per plan), threads optionally pinned to
+ * cores tid % ncores.  busy_s (nthreads doubles, may be NULL) receives each thread's time inside plan(). */
+int orc_plan_batch_dyn(void *pp, const orc_waypoint *starts, const orc_waypoint *goals, int n, int nthreads,
+                       orc_result *results, int32_t *actions, int max_seg, const int32_t *order, int pin, double *busy_s) {
   Planner *base = (Planner *)pp;
   if (nthreads < 1) nthreads = 1;
+  std::atomic<int> next{0};
   auto worker = [&](int tid) {
+    if (pin) {
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      long nc = sysconf(_SC_NPROCESSORS_ONLN);
+      CPU_SET((int)(tid % (nc > 0 ? nc : 1)), &set);
+      pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+    }
     Planner local;  // same parameters, private search state
     local.dim = base->dim; local.map = base->map; local.w = base->w; local.tol_pos = base->tol_pos;
     local.tol_vel = base->tol_vel; local.tol_acc = base->tol_acc; local.v_max = base->v_max; local.a_max = base->a_max;
@@ -1114,19 +1131,33 @@ int orc_plan_batch(void *pp, const orc_waypoint *starts, const orc_waypoint *goa
     local.potential_weight = base->potential_weight; local.gradient_weight = base->gradient_weight;
     local.wyaw = base->wyaw; local.tol_yaw = base->tol_yaw; local.trig_mode = base->trig_mode;
     local.prior = base->prior; local.prior_goal = base->prior_goal;
-    for (int i = tid; i < n; i += nthreads) {
+    double busy = 0.0;
+    while (true) {
+      const int q = next.fetch_add(1);
+      if (q >= n) break;
+      const int i = order ? order[q] : q;
+      auto t0 = std::chrono::steady_clock::now();
       local.plan(from_c(starts[i]), from_c(goals[i]));
+      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      busy += el;
       results[i] = local.last;
+      results[i].device_ms = el * 1e3;
       if (actions) {
         int ns = (int)local.traj_actions.size();
         for (int k = 0; k < max_seg; k++) actions[(size_t)i * max_seg + k] = k < ns ? local.traj_actions[k] : -1;
       }
     }
+    if (busy_s) busy_s[tid] = busy;
   };
   std::vector<std::thread> th;
   for (int t = 0; t < nthreads; t++) th.emplace_back(worker, t);
   for (auto &t : th) t.join();
   return 0;
+}
+
+int orc_plan_batch(void *pp, const orc_waypoint *starts, const orc_waypoint *goals, int n, int nthreads,
+                   orc_result *results, int32_t *actions, int max_seg) {
+  return orc_plan_batch_dyn(pp, starts, goals, n, nthreads, results, actions, max_seg, nullptr, 0, nullptr);
 }
 
 }  // extern "C"

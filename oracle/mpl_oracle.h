@@ -53,6 +53,8 @@ typedef struct orc_result {
   int64_t n_valid;  /* finite-cost successors (graph_search.h:81 passes) */
   uint64_t pop_hash;/* order-dependent hash over popped lattice keys */
   uint64_t closed_hash; /* order-independent hash over closed lattice keys */
+  double device_ms;  /* same slot as mplb_result.device_ms: here the wall-clock ms this plan took on its CPU thread
+                        (filled by the batch entry points; 0 from orc_plan) */
 } orc_result;
 
 /* One row of the per-primitive trace of env_map::get_succ (env_map.h:147-172). */
@@ -113,6 +115,11 @@ int orc_get_succ_trace(void *p, const orc_waypoint *curr, orc_prim_trace *rows, 
  * the reference itself is single-threaded per plan). actions may be NULL. */
 int orc_plan_batch(void *p, const orc_waypoint *starts, const orc_waypoint *goals, int n, int nthreads,
                    orc_result *results, int32_t *actions, int max_seg);
+
+/* Same, with a dynamic work queue (atomic index, optional processing `order`, optional pinning of thread i to core
+ * i mod ncores) instead of a static stripe; busy_s[nthreads] (may be NULL) receives each thread's seconds inside plan(). */
+int orc_plan_batch_dyn(void *p, const orc_waypoint *starts, const orc_waypoint *goals, int n, int nthreads,
+                       orc_result *results, int32_t *actions, int max_seg, const int32_t *order, int pin, double *busy_s);
 
 #ifdef __cplusplus
 }

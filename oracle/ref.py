@@ -63,6 +63,8 @@ def lib():
         L.ref_get_pop_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ref_get_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ref_plan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_plan_batch_dyn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -164,8 +166,12 @@ class RefPlanner:
         n = lib().ref_get_nodes(self.h, _ptr(a), a.size)
         return a[:n]
 
-    def plan_batch(self, starts, goals, nthreads=1):
+    def plan_batch(self, starts, goals, nthreads=1, order=None, pin=False, want_busy=False):
+        """Threads pull plans from an atomic queue (in `order` when given); results do not depend on the schedule."""
         n = len(starts)
         res = np.zeros(n, dtype=RESULT_DTYPE)
-        lib().ref_plan_batch(self.h, _ptr(starts), _ptr(goals), n, nthreads, _ptr(res))
-        return res
+        order = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+        busy = np.zeros(max(nthreads, 1), dtype=np.float64)
+        lib().ref_plan_batch_dyn(self.h, _ptr(starts), _ptr(goals), n, nthreads, _ptr(res),
+                                 _ptr(order) if order is not None else None, int(bool(pin)), _ptr(busy))
+        return (res, busy) if want_busy else res

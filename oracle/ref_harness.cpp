@@ -18,7 +18,12 @@
 #include <mpl_planner/planner/map_planner.h>
 
 #include <fcntl.h>
+#include <pthread.h>
+#include <sched.h>
 #include <unistd.h>
+
+#include <atomic>
+#include <chrono>
 
 #include <cstring>
 #include <map>
@@ -384,19 +389,43 @@ int ref_get_traj_coeffs(void *p, double *out, int cap_seg) { return ((RefPlanner
 int ref_get_pop_keys(void *p, int32_t *keys16, int cap) { return ((RefPlanner *)p)->p->get_pop_keys(keys16, cap); }
 int ref_get_nodes(void *p, orc_node *nodes, int cap) { return ((RefPlanner *)p)->p->get_nodes(nodes, cap); }
 
-/* n independent plans striped over nthreads std::threads, one private planner per thread (the reference is single-threaded per plan) */
-int ref_plan_batch(void *p, const orc_waypoint *starts, const orc_waypoint *goals, int n, int nthreads, orc_result *results) {
+/* n independent plans pulled from an atomic work queue (in `order` when given) by nthreads std::threads, one private
+ * planner per thread (the reference is single-threaded per plan), threads optionally pinned to cores. */
+int ref_plan_batch_dyn(void *p, const orc_waypoint *starts, const orc_waypoint *goals, int n, int nthreads, orc_result *results,
+                       const int32_t *order, int pin, double *busy_s) {
   RefPlanner *base = (RefPlanner *)p;
   if (nthreads < 1) nthreads = 1;
   QuietStdout q;
+  std::atomic<int> next{0};
   auto worker = [&](int tid) {
+    if (pin) {
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      long nc = sysconf(_SC_NPROCESSORS_ONLN);
+      CPU_SET((int)(tid % (nc > 0 ? nc : 1)), &set);
+      pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+    }
     std::unique_ptr<IPlanner> local(base->p->clone_config());
-    for (int i = tid; i < n; i += nthreads) local->plan(starts[i], goals[i], &results[i]);
+    double busy = 0.0;
+    while (true) {
+      const int k = next.fetch_add(1);
+      if (k >= n) break;
+      const int i = order ? order[k] : k;
+      auto t0 = std::chrono::steady_clock::now();
+      local->plan(starts[i], goals[i], &results[i]);
+      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      busy += el;
+      results[i].device_ms = el * 1e3;
+    }
+    if (busy_s) busy_s[tid] = busy;
   };
   std::vector<std::thread> th;
   for (int t = 0; t < nthreads; t++) th.emplace_back(worker, t);
   for (auto &t : th) t.join();
   return 0;
+}
+int ref_plan_batch(void *p, const orc_waypoint *starts, const orc_waypoint *goals, int n, int nthreads, orc_result *results) {
+  return ref_plan_batch_dyn(p, starts, goals, n, nthreads, results, nullptr, 0, nullptr);
 }
 
 }  // extern "C"

@@ -59,6 +59,11 @@ def _shaping_inputs(m):
     return pot.ravel(), mask.ravel()
 
 
+def _same(a, b):
+    """result records equal in every field but the per-plan time stamp"""
+    return all(np.array_equal(a[f], b[f]) for f in a.dtype.names if f != "device_ms")
+
+
 def _worker(rank, world, port, n, out_path):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -79,6 +84,14 @@ def _worker(rank, world, port, n, out_path):
     s, g = mp.waypoints_array(n), mp.waypoints_array(n)
     s["pos"], g["pos"], s["control"], g["control"] = S, G, mp.ACC, mp.ACC
     res, acts = sp.plan_batch(s, g, max_seg=32)
+    # the query list held by rank 0 only: one broadcast, then every rank plans the stripe it holds in host buffers
+    zs, zg = (s, g) if rank == 0 else (mp.waypoints_array(n), mp.waypoints_array(n))
+    bs, bg = sp.broadcast_queries(zs, zg)
+    assert np.array_equal(bs.view(np.uint8), s.view(np.uint8)) and np.array_equal(bg.view(np.uint8), g.view(np.uint8))
+    idx = mdist.shard_indices(n, rank, world)
+    res4, acts4 = sp.plan_batch_local(np.ascontiguousarray(bs[idx]), np.ascontiguousarray(bg[idx]), n, max_seg=32)
+    if rank == 0:
+        assert _same(res4, res) and np.array_equal(acts4, acts)
     # cost shaping: rank 0 supplies a potential map and a region mask, everyone installs them, then clears them again
     pot, mask = _shaping_inputs(m)
     sp.set_cost_shaping(pot, mask) if rank == 0 else sp.set_cost_shaping()
@@ -108,17 +121,17 @@ def test_sharded_batch_gloo(tmp_path):
     want, want_acts, _ = ref.plan_batch(s, g, max_seg=32)
     z = np.load(out)
     got = z["res"].view(_lib.RESULT_DTYPE).reshape(-1)
-    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+    assert _same(got, want)
     assert np.array_equal(z["acts"], want_acts)
     # shaped batch: same as a single process with the same potential map and mask installed; cleared = plain again
     pot, mask = _shaping_inputs(m)
     ref.setPotentialMap(pot)
     ref.setSearchRegionMask(mask)
     want2, want_acts2, _ = ref.plan_batch(s, g, max_seg=32)
-    assert np.array_equal(z["res2"].view(_lib.RESULT_DTYPE).reshape(-1).view(np.uint8), want2.view(np.uint8))
+    assert _same(z["res2"].view(_lib.RESULT_DTYPE).reshape(-1), want2)
     assert np.array_equal(z["acts2"], want_acts2)
     assert not np.array_equal(want2["cost"], want["cost"])  # the shaping changed something
-    assert np.array_equal(z["res3"], z["res"])
+    assert _same(z["res3"].view(_lib.RESULT_DTYPE).reshape(-1), got)
 
 
 def test_shard_indices_cover_everything():
