@@ -344,6 +344,17 @@ class MapPlanner {
     if (!ignore) std::printf("[MapPlanner] heur_ignore_dynamics = false is not supported (env_base.h:67-211 needs a polynomial root finder)\n");
   }
   void reset() { traj_ = Trajectory<Dim>(); initialized_ = false; last_ = mplb_result{}; } /* planner_base.h:164-167 */
+  void setPriorTrajectory(const Trajectory<Dim> &traj) { /* planner_base.h:249-252 */
+    const auto &segs = traj.segs;
+    std::vector<double> cs(segs.size() * 24, 0.0), ts(segs.size(), 0.0);
+    for (size_t i = 0; i < segs.size(); i++) {
+      for (int k = 0; k < Dim; k++) for (int q = 0; q < 6; q++) cs[i * 24 + k * 6 + q] = segs[i].coeff(k)[q];
+      for (int q = 0; q < 6; q++) cs[i * 24 + 18 + q] = segs[i].coeff_yaw()[q];
+      ts[i] = segs[i].t();
+    }
+    const int ctl = segs.empty() ? 0 : (int)segs.back().control();
+    if (h_ && mplb_planner_set_prior_trajectory(h_, (int)segs.size(), cs.data(), ts.data(), ctl) != MPLB_OK) report();
+  }
   void setTol(decimal_t tol_pos, decimal_t tol_vel = -1, decimal_t tol_acc = -1) { /* planner_base.h:255-265 */
     set(MPLB_TOL_POS, tol_pos); set(MPLB_TOL_VEL, tol_vel); set(MPLB_TOL_ACC, tol_acc);
   }

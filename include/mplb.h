@@ -143,7 +143,11 @@ enum mplb_param {
   MPLB_GRADIENT_WEIGHT = 13,  /* setGradientWeight  map_planner.cpp:35-38, default 0.0 (env_map.h:197) */
   MPLB_WYAW = 14,   /* setWyaw   :221 default 1.0 (env_base.h:372): weight of the heading cost env_map.h:121-128 */
   MPLB_MEM_FRACTION = 100, /* fraction of free device memory the search arenas may take (default 0.6) */
-  MPLB_MAX_SLOTS = 101     /* tuning: cap on concurrently resident plans (CTAs); 0 = all resident CTAs */
+  MPLB_MAX_SLOTS = 101,    /* tuning: cap on concurrently resident plans (CTAs); 0 = all resident CTAs */
+  MPLB_EXACT_PREDS = 102   /* predecessor lists of graph_search.h:100-102 kept per node and resolved by recoverTraj with the
+                              final g values: -1 (default) = exactly where a running best predecessor could differ (epsilon > 1,
+                              a prior-trajectory heuristic, VEL control with v_max below the control bound), 0 = never,
+                              1 = always */
 };
 int mplb_planner_set_param(mplb_planner *p, int key, double value);
 /* setU (planner_base.h:246): n rows of udim doubles, udim = Dim, or Dim + 1 when the last entry is a yaw rate
@@ -168,6 +172,13 @@ int mplb_planner_set_potential_map(mplb_planner *p, const int8_t *pot, size_t n)
  * potential map.  radius/range: 3 doubles (radius[0] = xy radius, radius[2] = z half-height in 3D). */
 int mplb_planner_update_potential_map(mplb_planner *p, const double *pos, const double *radius, const double *range,
                                       double pow);
+
+/* setPriorTrajectory (planner_base.h:249-252 -> env_map::set_prior_trajectory, env_map.h:187-225, heuristic env_base.h:46-53):
+ * n_seg primitives given by their coefficient rows cx, cy, cz, cyaw (6 doubles each, highest order first, as
+ * toPrimitiveROSMsg lays them out: coeffs[n_seg][4][6]) and durations seg_t[n_seg]; control = the prior's Control flags.
+ * While a prior is installed the requested goals are ignored (env_base.h:295-298) and the goal is the prior's end point.
+ * n_seg = 0 clears.  The prior is assumed collision free (traverse_trajectory = 0) and cannot be combined with a potential map. */
+int mplb_planner_set_prior_trajectory(mplb_planner *p, int n_seg, const double *coeffs, const double *seg_t, int control);
 
 /* plan (planner_base.h:275-325).  Returns MPLB_OK when the call itself worked; the reference's bool is
  * (out->status == MPLB_PLAN_OK || out->status == MPLB_PLAN_START_IS_GOAL).  The search state of this plan

@@ -45,6 +45,7 @@ SYMBOLS = {
     "mplb_planner_get_search_region": (C.c_int64, [_VP, _VP, C.c_size_t]),
     "mplb_planner_set_potential_map": (_I, [_VP, _VP, C.c_size_t]),
     "mplb_planner_update_potential_map": (_I, [_VP, _VP, _VP, _VP, _D]),
+    "mplb_planner_set_prior_trajectory": (_I, [_VP, _I, _VP, _VP, _I]),
     "mplb_plan": (_I, [_VP, _VP, _VP, _VP]),
     "mplb_plan_batch": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _I]),
     "mplb_plan_batch_device": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP]),
@@ -64,7 +65,7 @@ SYMBOLS = {
 }
 
 PARAM = dict(v_max=0, a_max=1, j_max=2, yaw_max=3, dt=4, w=5, epsilon=6, max_num=7, tol_pos=8, tol_vel=9,
-             tol_acc=10, t_max=11, potential_weight=12, gradient_weight=13, wyaw=14, mem_fraction=100, max_slots=101)
+             tol_acc=10, t_max=11, potential_weight=12, gradient_weight=13, wyaw=14, mem_fraction=100, max_slots=101, exact_preds=102)
 
 _LIB = None
 

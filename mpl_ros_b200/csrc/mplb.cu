@@ -332,7 +332,7 @@ struct mplb_planner {
   int max_num = -1;
   double mem_fraction = 0.6;
   int max_slots = 0; /* 0 = as many CTAs as are resident */
-  int resident_sig = -1, resident_cached = 0;
+  int resident_sig = -1, resident_cached = 0, hcap_big_cached = 0, sm_count = 0;
   size_t budget_bytes = 0; /* arena budget, measured at the first batch (reset by MPLB_MEM_FRACTION) */
   std::vector<double> U; /* nU x 3 */
   std::vector<double> Uyaw; /* nU yaw rates when the rows have Dim + 1 entries (pr:217), else empty */
@@ -344,6 +344,14 @@ struct mplb_planner {
   size_t pot_cells = 0; /* 0 = no potential map */
   DevBuf<unsigned> d_region;
   std::vector<uint8_t> h_region; /* empty = no search region */
+  /* prior trajectory (pb:249-252): coefficient rows cx, cy, cz, cyaw (6 each, highest order first) and duration per segment */
+  int prior_nseg = 0, prior_control = 0;
+  std::vector<double> prior_coeffs, prior_ts;
+  double prior_start_t = 0; /* t of the start waypoints of the batch being planned (the table is indexed by depth) */
+  double cfg_prior_start_t = 0;
+  DevBuf<double> d_prior;
+  int exact_preds = -1; /* predecessor log: -1 = where the running best predecessor is not provably exact, 0 = never, 1 = always */
+  bool log_mode = false;
 
   /* device-side configuration, rebuilt when dirty */
   bool dirty = true;
@@ -383,14 +391,14 @@ namespace {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
-  size_t off_rows, off_heap, off_table, off_poplog, stride, row_bytes;
-  int tsize_max;
+  size_t off_rows, off_heap, off_table, off_poplog, off_log, stride, row_bytes;
+  int tsize_max, log_cap;
 };
 
 /* Large tiers (hundreds of MB per plan) trade probe length for room: load factor <= 1/2 instead of 1/4. */
 int load_inv_of(int cap) { return cap > 262144 ? 2 : MPLB_LOAD_INV; }
 
-Layout make_layout(int cap, int ns, int nU, bool want_poplog) {
+Layout make_layout(int cap, int ns, int nU, bool want_poplog, bool log_mode) {
   Layout L;
   long long ts = MPLB_TINIT; /* 64-bit: the last tier would overflow an int (the caller stops tiering at 2^30 table slots) */
   while (ts < (long long)load_inv_of(cap) * ((long long)cap + nU) && ts < (1ll << 30)) ts <<= 1;
@@ -406,6 +414,13 @@ Layout make_layout(int cap, int ns, int nU, bool want_poplog) {
   o += align_up((size_t)ts * sizeof(Slot), 256);
   L.off_poplog = o;
   if (want_poplog) o += align_up((size_t)cap * sizeof(int), 256);
+  L.off_log = o;
+  L.log_cap = 0;
+  if (log_mode) { /* predecessor records: every finite-cost edge of every expansion (gs:100-102); 6 per node of capacity */
+    const long long lc = std::min<long long>(6LL * cap + nU, 0x7fffffffLL);
+    L.log_cap = (int)lc;
+    o += align_up((size_t)lc * sizeof(PredRec), 256);
+  }
   L.stride = o;
   return L;
 }
@@ -444,7 +459,9 @@ int build_cfg(mplb_planner *p, int control) {
     return fail(MPLB_ERR_ARG, "v_max must be > 0 for ACC/JRK/SNP controls (the sample divisor of env_map.h:95 is unbounded otherwise)");
   if (p->tol_vel >= 0 && ord < 2) return fail(MPLB_ERR_ARG, "tol_vel >= 0 needs a control order with velocity in the state");
   if (p->tol_acc >= 0 && ord < 3) return fail(MPLB_ERR_ARG, "tol_acc >= 0 needs a control order with acceleration in the state");
-  if (!p->dirty && p->cfg_control == control && p->cfg_map_version == p->map->version) return MPLB_OK;
+  if (!p->dirty && p->cfg_control == control && p->cfg_map_version == p->map->version &&
+      (p->prior_nseg == 0 || p->cfg_prior_start_t == p->prior_start_t))
+    return MPLB_OK;
 
   mplb_map *m = p->map;
   DevCfg &c = p->cfg;
@@ -529,6 +546,79 @@ int build_cfg(mplb_planner *p, int control) {
     if (p->pot_cells) c.pot = p->d_pot.p;
     if (!p->h_region.empty()) c.region = p->d_region.p;
   }
+  /* prior trajectory (eb:46-53, em:187-225 without a potential map) */
+  c.prior = nullptr; c.prior_n = 0; c.prior_on = 0;
+  if (p->prior_nseg > 0) {
+    if (p->pot_cells) return fail(MPLB_ERR_ARG, "a prior trajectory together with a potential map is not supported (em:199-214 is unpinned)");
+    const int D = p->dim, n = p->prior_nseg;
+    std::vector<double> taus(1, 0.0);
+    for (int i = 0; i < n; i++) taus.push_back(p->prior_ts[i] + taus.back()); /* trajectory.h:52-57 */
+    const double total = taus.back();
+    auto power = [](double t, int k) { double tn = 1; while (k > 0) { tn *= t; k--; } return tn; }; /* math.h:197-205 */
+    auto evaluate = [&](double time, mplb_waypoint *out) { /* trajectory.h:66-86 with pr:128-145 */
+      double tau = time;
+      if (tau < 0) tau = 0;
+      if (tau > total) tau = total;
+      std::memset(out, 0, sizeof(*out));
+      for (int id = 0; id < n; id++) {
+        if ((tau >= taus[id] && tau < taus[id + 1]) || id == n - 1) {
+          tau -= taus[id];
+          const double *cs = &p->prior_coeffs[(size_t)id * 24];
+          for (int j = 0; j < D; j++) {
+            const double *q = cs + j * 6;
+            out->pos[j] = q[0] / 120 * power(tau, 5) + q[1] / 24 * power(tau, 4) + q[2] / 6 * power(tau, 3) + q[3] / 2 * tau * tau + q[4] * tau + q[5];
+            out->vel[j] = q[0] / 24 * power(tau, 4) + q[1] / 6 * power(tau, 3) + q[2] / 2 * tau * tau + q[3] * tau + q[4];
+            out->acc[j] = q[0] / 6 * power(tau, 3) + q[1] / 2 * tau * tau + q[2] * tau + q[3];
+            out->jrk[j] = q[0] / 2 * tau * tau + q[1] * tau + q[2];
+          }
+          const double *qy = cs + 18;
+          double yaw = qy[0] / 120 * power(tau, 5) + qy[1] / 24 * power(tau, 4) + qy[2] / 6 * power(tau, 3) + qy[3] / 2 * tau * tau + qy[4] * tau + qy[5];
+          while (yaw > M_PI) yaw -= 2.0 * M_PI; /* math.h:15-19 */
+          while (yaw < -M_PI) yaw += 2.0 * M_PI;
+          out->yaw = yaw;
+          out->control = p->prior_control;
+          return;
+        }
+      }
+    };
+    /* em:196-223: costs[k] = w t (no potential map), total_cost = traverse_trajectory (0: a collision-free prior is assumed,
+     * as in MPL/test/test_planner_2d_with_prior_traj.cpp) + w total; prior_traj_[k] = (evaluate(t), total_cost - costs[int(t/dt)]) */
+    std::vector<double> costs;
+    for (double t = 0; t < total; t += p->dt) costs.push_back(p->w * t);
+    const double total_cost = 0.0 + p->w * total;
+    std::vector<mplb_waypoint> pw;
+    std::vector<double> pc;
+    for (double t = 0; t < total; t += p->dt) {
+      const int id = (int)(t / p->dt);
+      mplb_waypoint wq;
+      evaluate(t, &wq);
+      pw.push_back(wq);
+      pc.push_back(total_cost - costs[std::min<size_t>((size_t)std::max(id, 0), costs.size() - 1)]);
+    }
+    evaluate(total, &c.prior_goal); /* em:224 */
+    /* rows by depth: a depth-d state carries t = start.t + dt + ... + dt (em:161), eb:48-51 indexes with size_t(t / dt) */
+    std::vector<double> rows;
+    double t = p->prior_start_t;
+    for (int d = 0; d < (1 << 20); d++) {
+      const double q = t / p->dt;
+      if (!(q >= 0) || q >= (double)pw.size()) break;
+      const size_t id = (size_t)q;
+      if (id >= pw.size()) break;
+      for (int k = 0; k < 3; k++) rows.push_back(pw[id].pos[k]);
+      rows.push_back(pc[id]);
+      t += p->dt;
+    }
+    c.prior_on = 1;
+    c.prior_n = (int)(rows.size() / 4);
+    if (c.prior_n > 0) {
+      CUDA_TRY(p->d_prior.reserve(rows.size()));
+      CUDA_TRY(cudaMemcpy(p->d_prior.p, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+      c.prior = p->d_prior.p;
+    }
+    p->cfg_prior_start_t = p->prior_start_t;
+  }
+  /* predecessor log (see PredRec): needed wherever a node's g can still drop after it was used to relax a successor */
+  p->log_mode = p->exact_preds > 0 || (p->exact_preds < 0 && (p->eps > 1.0 || p->prior_nseg > 0 || (ord == 1 && !(p->v_max >= umax))));
   {
     int e = 0;
     double mant = std::frexp(p->v_max, &e);
@@ -579,11 +669,19 @@ int build_cfg(mplb_planner *p, int control) {
   return MPLB_OK;
 }
 
+/* shared memory of one CTA: the plan record, plus (|U| > 32 instantiations) `hcap` heap entries of 20 bytes behind it */
+template <int DIM, int ORD, int MAXU, bool POT>
+size_t smem_bytes(int hcap) {
+  using SM = PlanSmem<DIM, ORD, MAXU, POT>;
+  return SM::DYN_HEAP ? heap_dyn_offset<SM>() + (size_t)hcap * 20 : sizeof(SM);
+}
+
 template <int DIM, int ORD, int MAXU, bool POT>
 int launch_batch(const DevCfg &c, const BatchArgs &a, int grid, cudaStream_t s) {
-  size_t smem = sizeof(PlanSmem<DIM, ORD, MAXU, POT>);
+  size_t smem = smem_bytes<DIM, ORD, MAXU, POT>(a.hcap);
   auto kern = astar_batch_kernel<DIM, ORD, MAXU, POT>;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); /* residency is shared-memory bound */
   /* the occupancy bricks are the only data with reuse across pops and plans: keep them resident in L2 */
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
@@ -618,11 +716,12 @@ int launch_batch(const DevCfg &c, const BatchArgs &a, int grid, cudaStream_t s) 
 }
 
 template <int DIM, int ORD, int MAXU, bool POT>
-int resident_ctas(int device) {
+int resident_ctas(int device, int hcap) {
   int per_sm = 0, sms = 0;
-  size_t smem = sizeof(PlanSmem<DIM, ORD, MAXU, POT>);
+  size_t smem = smem_bytes<DIM, ORD, MAXU, POT>(hcap);
   auto kern = astar_batch_kernel<DIM, ORD, MAXU, POT>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MPLB_NT, smem) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
   return per_sm * sms;
@@ -635,12 +734,28 @@ int launch_any(bool shaped, const DevCfg &c, const BatchArgs &a, int grid, cudaS
   return launch_batch<DIM, ORD, MAXU, false>(c, a, grid, s);
 }
 template <int DIM, int ORD, int MAXU>
-int resident_any(bool shaped, int device) {
-  if constexpr (MAXU == 1) { if (shaped) return resident_ctas<DIM, ORD, MAXU, true>(device); }
-  return resident_ctas<DIM, ORD, MAXU, false>(device);
+int resident_any(bool shaped, int device, int hcap) {
+  if constexpr (MAXU == 1) { if (shaped) return resident_ctas<DIM, ORD, MAXU, true>(device, hcap); }
+  return resident_ctas<DIM, ORD, MAXU, false>(device, hcap);
+}
+/* largest shared-memory heap of a |U| > 32 launch that runs one plan per SM */
+template <int DIM, int ORD, int MAXU>
+int hcap_big(int device) {
+  int optin = 0;
+  if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return MPLB_HCAP_SMALL;
+  const long long room = (long long)optin - (long long)heap_dyn_offset<PlanSmem<DIM, ORD, MAXU, false>>() - 1024;
+  long long h = room / 20 / 256 * 256;
+  return (int)std::max<long long>(MPLB_HCAP_SMALL, std::min<long long>(h, 8192));
 }
 
 #define DISPATCH_U(D, O, nu, CALL) do { if ((nu) <= 32) { CALL(D, O, 1); } else { CALL(D, O, 4); } } while (0)
+#ifdef MPLB_BENCH_ONLY /* tuning builds (tools/ab_bench.py): only the two bench instantiations, seconds to compile */
+#define DISPATCH(dim, ord, nu, CALL)                                                          \
+  do {                                                                                        \
+    if (dim == 3 && ord == 2 && (nu) <= 32) { CALL(3, 2, 1); } else if (dim == 3 && ord == 3 && (nu) > 32) { CALL(3, 3, 4); } \
+    else return fail(MPLB_ERR_ARG, "tuning build: only the bench configurations are compiled in");                         \
+  } while (0)
+#else
 #define DISPATCH(dim, ord, nu, CALL)                                                          \
   do {                                                                                        \
     if (dim == 2 && ord == 1) DISPATCH_U(2, 1, nu, CALL); else if (dim == 2 && ord == 2) DISPATCH_U(2, 2, nu, CALL); \
@@ -648,6 +763,7 @@ int resident_any(bool shaped, int device) {
     else if (dim == 3 && ord == 1) DISPATCH_U(3, 1, nu, CALL); else if (dim == 3 && ord == 2) DISPATCH_U(3, 2, nu, CALL); \
     else if (dim == 3 && ord == 3) DISPATCH_U(3, 3, nu, CALL); else DISPATCH_U(3, 4, nu, CALL); \
   } while (0)
+#endif
 
 /* Core: device-resident batch over arena tiers. */
 int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoint *d_goals, int n, mplb_result *d_results,
@@ -668,12 +784,13 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
   const int cfg_sig = (shaped ? 1000 : 0) + c.dim * 100 + c.ord * 10 + (c.nU <= 32 ? 1 : 4);
   if (p->resident_sig != cfg_sig) {
     int r = 0;
-#define RES_CALL(D, O, M) r = resident_any<D, O, M>(shaped, p->device)
+#define RES_CALL(D, O, M) do { r = resident_any<D, O, M>(shaped, p->device, MPLB_HCAP_SMALL); if (M > 1) p->hcap_big_cached = hcap_big<D, O, M>(p->device); } while (0)
     DISPATCH(c.dim, c.ord, c.nU, RES_CALL);
     p->resident_cached = r;
     p->resident_sig = cfg_sig;
   }
   const int resident = p->resident_cached;
+  if (p->sm_count == 0) cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
   if (resident <= 0) return fail(MPLB_ERR_CUDA, "no resident CTA for the search kernel (is this an sm_100 device?)");
 
   if (p->budget_bytes == 0) {
@@ -735,7 +852,7 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
   }
   if (!ev0_done) CUDA_TRY(cudaEventRecord(p->ev0, s));
   while (n_work > 0) {
-    Layout L = make_layout(cap, c.ns, c.nU, retain);
+    Layout L = make_layout(cap, c.ns, c.nU, retain, p->log_mode);
     int slots = std::min(n_work, resident);
     if (p->max_slots > 0) slots = std::min(slots, p->max_slots);
     if ((size_t)slots * L.stride > budget) slots = (int)(budget / L.stride);
@@ -762,6 +879,9 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
     a.max_seg = max_seg; a.work = identity ? nullptr : p->d_work.p; a.n_work = n_work;
     a.work_counter = p->d_ctrl.p; a.arena = p->arena.p; a.stride = L.stride; a.cap = cap; a.tsize_max = L.tsize_max; a.load_inv = load_inv_of(cap);
     a.off_rows = L.off_rows; a.off_heap = L.off_heap; a.off_table = L.off_table; a.off_poplog = L.off_poplog;
+    a.off_log = L.off_log; a.log_cap = L.log_cap;
+    /* |U| > 32: when memory leaves at most one plan per SM anyway, that plan gets a much larger shared-memory heap top */
+    a.hcap = (c.nU > 32 && slots <= p->sm_count && p->hcap_big_cached > 0) ? p->hcap_big_cached : MPLB_HCAP_SMALL;
     a.want_poplog = retain ? 1 : 0; a.slot_of_plan = retain ? p->d_slot.p : nullptr;
     a.overflow_count = p->d_ctrl.p + 1; a.overflow_list = p->d_over.p;
 #ifdef MPLB_PHASE_TIMING
@@ -959,7 +1079,7 @@ void mplb_planner_destroy(mplb_planner *p) {
   p->d_U.release(); p->d_ttab.release(); p->d_toff.release(); p->d_tcnt.release(); p->arena.release();
   p->d_ctrl.release(); p->d_work.release(); p->d_over.release(); p->d_slot.release(); p->d_starts.release();
   p->d_goals.release(); p->d_results.release(); p->d_actions.release(); p->d_segs.release();
-  p->d_keys.release(); p->d_phase.release(); p->d_pot.release(); p->d_region.release(); p->d_Uyaw.release();
+  p->d_keys.release(); p->d_phase.release(); p->d_pot.release(); p->d_region.release(); p->d_Uyaw.release(); p->d_prior.release();
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   delete p;
@@ -999,6 +1119,7 @@ int mplb_planner_set_param(mplb_planner *p, int key, double v) {
       p->budget_bytes = 0;
       break;
     case MPLB_MAX_SLOTS: p->max_slots = (int)v; break;
+    case MPLB_EXACT_PREDS: p->exact_preds = (int)v; break;
     default: return fail(MPLB_ERR_ARG, "unknown parameter key");
   }
   p->dirty = true;
@@ -1212,6 +1333,19 @@ int mplb_planner_update_potential_map(mplb_planner *p, const double *pos, const 
   return MPLB_OK;
 }
 
+int mplb_planner_set_prior_trajectory(mplb_planner *p, int n_seg, const double *coeffs, const double *seg_t, int control) {
+  if (!p) return fail(MPLB_ERR_ARG, "null planner");
+  if (n_seg <= 0) { p->prior_nseg = 0; p->prior_coeffs.clear(); p->prior_ts.clear(); p->dirty = true; return MPLB_OK; }
+  if (!coeffs || !seg_t) return fail(MPLB_ERR_ARG, "null argument");
+  p->prior_nseg = n_seg;
+  p->prior_control = control;
+  p->prior_coeffs.assign(coeffs, coeffs + (size_t)n_seg * 24);
+  p->prior_ts.assign(seg_t, seg_t + n_seg);
+  p->dirty = true;
+  if (p->verbose) std::printf("[PlannerBase] set prior trajectory\n");
+  return MPLB_OK;
+}
+
 int mplb_plan_batch_device(mplb_planner *p, const void *d_starts, const void *d_goals, int n, void *d_results,
                            void *d_actions, void *d_seg_states, int max_seg, void *stream) {
   if (!p || !d_starts || !d_goals || !d_results) return fail(MPLB_ERR_ARG, "null argument");
@@ -1219,10 +1353,11 @@ int mplb_plan_batch_device(mplb_planner *p, const void *d_starts, const void *d_
   if ((d_actions || d_seg_states) && max_seg <= 0) return fail(MPLB_ERR_ARG, "max_seg must be > 0 when trajectories are requested");
   if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
   cudaStream_t s = (cudaStream_t)stream;
-  int control = 0; /* the control mode is a property of the start waypoint (waypoint.h:46-55) */
-  CUDA_TRY(cudaMemcpyAsync(&control, (const char *)d_starts + offsetof(mplb_waypoint, control), sizeof(int),
-                           cudaMemcpyDeviceToHost, s));
+  mplb_waypoint w0; /* the control mode is a property of the start waypoint (waypoint.h:46-55); its t seeds the prior-trajectory table */
+  CUDA_TRY(cudaMemcpyAsync(&w0, d_starts, sizeof(w0), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  const int control = w0.control;
+  p->prior_start_t = w0.t;
   return run_batch(p, (const mplb_waypoint *)d_starts, (const mplb_waypoint *)d_goals, n, (mplb_result *)d_results,
                    (int *)d_actions, (double *)d_seg_states, max_seg, control, false, s);
 }
@@ -1236,7 +1371,9 @@ static int plan_batch_host(mplb_planner *p, const mplb_waypoint *starts, const m
   for (int i = 0; i < n; i++) {
     if (starts[i].control != starts[0].control) return fail(MPLB_ERR_ARG, "all starts of a batch must share one control mode");
     if (starts[i].enable_t) return fail(MPLB_ERR_ARG, "enable_t waypoints are not supported");
+    if (p->prior_nseg > 0 && starts[i].t != starts[0].t) return fail(MPLB_ERR_ARG, "with a prior trajectory all starts of a batch must share one t");
   }
+  p->prior_start_t = starts[0].t;
   cudaStream_t s = 0;
   CUDA_TRY(p->d_starts.reserve(n));
   CUDA_TRY(p->d_goals.reserve(n));

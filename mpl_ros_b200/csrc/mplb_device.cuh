@@ -14,14 +14,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/mplb.h"
+
 namespace mplb {
 
 #ifndef MPLB_NT
-#define MPLB_NT 256   /* threads per CTA: one CTA owns one plan (warp 0 search, warps 1..NW-2 sampling, last warp heap) */
+#define MPLB_NT 224   /* threads per CTA: one CTA owns one plan (warp 0 search, warps 1..NW-2 sampling, last warp heap) */
 #endif
 #define MPLB_MAXU 128 /* max |U| */
 #ifndef MPLB_MIN_CTAS
-#define MPLB_MIN_CTAS 3 /* resident CTAs per SM the search kernel is compiled for (4 caps registers at 64 and spills: measured no faster) */
+#define MPLB_MIN_CTAS 4 /* resident CTAs per SM the search kernel is compiled for.  Measured on the 65 536-query bench list (r02 sweep,
+                           prim/s x 1e9): 256 x 3 2.41, 224 x 4 2.74, 192 x 5 2.60, 256 x 4 2.62; a 1024-query batch is tail bound and flat */
 #endif
 
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
@@ -84,6 +87,12 @@ struct DevCfg {
   double yaw_max, wyaw; /* eb:388 (<= 0 disables the FOV check), eb:372 */
   double cos_yaw_max;   /* correctly rounded cos(yaw_max), prepared on the host */
   const double *Uyaw;   /* yaw rate of every control (column Dim of U), or null */
+  /* prior trajectory (eb:46-53,249-256, em:187-225): row d = (pos of the prior at the time of a depth-d state, remaining
+   * cost), d < prior_n; the prior's end point replaces every requested goal (em:224, eb:295-298) */
+  const double *prior;
+  int prior_n;  /* rows of the table (0 when even a depth-0 state falls behind the prior's end) */
+  int prior_on; /* a prior trajectory is installed: prior_goal replaces the goals */
+  mplb_waypoint prior_goal;
 };
 
 /* ------------------------------------------------------------------------------------------------

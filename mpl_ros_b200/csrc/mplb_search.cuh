@@ -62,6 +62,7 @@ namespace mplb {
 #ifndef MPLB_HCAP
 #define MPLB_HCAP 1536 /* heap entries kept in shared memory (|U| <= 32 instantiations) */
 #endif
+#define MPLB_HCAP_SMALL 1024 /* shared-memory heap entries of the |U| > 32 instantiations when several plans share an SM */
 #ifndef MPLB_B1_INLINE
 #define MPLB_B1_INLINE __forceinline__ /* __noinline__ costs ~2k cycles per pop */
 #endif
@@ -99,9 +100,22 @@ struct __align__(16) RowHdr {
   unsigned long long k0, k1; /* packed lattice key */
   int parent;                /* best predecessor node */
   int slot;                  /* table slot of this node (kept current across table growth) */
-  unsigned long long pad;
+  int pred_head;             /* newest predecessor record of this node in the predecessor log (-1 = none; log mode only) */
+  int depth;                 /* primitives between the start and this node's FIRST discoverer: its stored time is
+                                start.t + depth additions of dt (em:161), which is all the prior-trajectory heuristic needs */
 };
 static_assert(sizeof(RowHdr) == 32, "RowHdr must be 32 bytes");
+
+/* One predecessor record (gs:100-102), kept only in log mode: when a node's g can still change after it was relaxed
+ * (eps > 1, an inconsistent heuristic) recoverTraj (gs:391-405) must see every predecessor with its FINAL g. */
+struct PredRec {
+  double cost; /* pred_action_cost */
+  int pred;    /* pred node */
+  int next;    /* previous record of the same successor (-1 = end): the list runs newest -> oldest */
+  int action;  /* pred_action_id */
+  int pad;
+};
+static_assert(sizeof(PredRec) == 24, "PredRec must be 24 bytes");
 
 struct HeapEnt {
   double f; /* heap key (gs:54,119) */
@@ -135,8 +149,10 @@ struct BatchArgs {
   size_t stride;
   int cap;       /* nodes (and heap entries, pop-log entries) per slot */
   int tsize_max; /* table slots per slot arena (power of two) */
+  int hcap;      /* shared-memory heap entries of this launch (|U| > 32 instantiations; see PlanSmem) */
   int load_inv;  /* table load factor bound 1/load_inv of this tier (MPLB_LOAD_INV in the small tiers, 2 in the large ones) */
-  size_t off_rows, off_heap, off_table, off_poplog;
+  size_t off_rows, off_heap, off_table, off_poplog, off_log;
+  int log_cap; /* predecessor records per slot; 0 = the running best-predecessor is exact for this configuration */
   int want_poplog;
   int *slot_of_plan;   /* optional: which slot ran plan i (retained single plan) */
   int *overflow_count; /* plans whose arena overflowed in this tier ... */
@@ -185,14 +201,27 @@ struct PlanSmem {
   static constexpr int NP = DIM * ORD;
   static constexpr int NS = NP + (POT ? 1 : 0);
   static constexpr int MAXU = 32 * NB;
-  static constexpr int NBUF = (NB == 1) ? 2 : 1; /* expansion records: 2 = B1 of the next pop is pipelined */
+  static constexpr int NBUF = 2; /* expansion records: B1 of the next pop is pipelined into the second one */
   typedef ExpBuf<DIM, ORD, MAXU, POT ? 1 : 0> EB;
   EB eb[NBUF];
   int cur_buf;
-  static constexpr int HCAP = (NB == 1) ? MPLB_HCAP : 1024; /* heap entries kept in shared memory */
-  /* heap top (SoA) */
+  /* heap top (SoA) in shared memory.  |U| <= 32: a fixed MPLB_HCAP entries inside this struct.  |U| > 32: `hcap`
+   * entries in the dynamic shared memory behind the struct, sized per launch (1024 when several plans share an SM, many
+   * more when the arena size leaves one plan per SM anyway, as in the 1024^3 / |U| = 125 configuration). */
+  static constexpr bool DYN_HEAP = (NB > 1);
+  static constexpr int HCAP = DYN_HEAP ? 1 : MPLB_HCAP;
   double hf[HCAP], hg[HCAP];
   int hn[HCAP];
+  int hcap;
+  /* |U| > 32: ancestor cache of the pushes of one pop.  The k-th push of a pop lands on heap position n0 + k, so every
+   * ancestor it can meet lies in one short contiguous range per tree level; those ranges are copied from the global part
+   * of the heap into shared memory in ONE asynchronous round trip and kept coherent by write-through, instead of one
+   * HBM round trip per push (~100 pushes per pop with |U| = 125). */
+  static constexpr int ACAP = DYN_HEAP ? 320 : 1;
+  alignas(16) HeapEnt ac[ACAP];
+  unsigned long long ac_bar; /* mbarrier of the bulk-copy variant (MPLB_BULK_PREFETCH) */
+  int ac_lo[32], ac_off[32], ac_cnt[32]; /* per level l >= 1: first cached position, offset in ac[], count */
+  int ac_valid;
   /* current node */
   double cur[NS];
   unsigned long long cur_k0, cur_k1; /* packed lattice key of the current node */
@@ -216,6 +245,8 @@ struct PlanSmem {
   double yterms[POT ? MAXU * 64 : 1]; /* per-sample yaw cost terms (em:121-128), same indexing */
   double Uyaw[POT ? MAXU : 1];        /* yaw rate of each control */
   int n_before;      /* n_nodes before this expansion */
+  int n_log;         /* predecessor records written (log mode) */
+  int cur_depth, pf_depth; /* RowHdr::depth of the current node / of the prefetched root */
   /* pending sift-down (heap warp) and prefetched root row */
   int sd_pending, sd_n;
   double sd_f, sd_g;
@@ -233,21 +264,31 @@ struct PlanSmem {
 
 /* ---------------------------------------------------------------- heap in shared memory with global spill */
 template <class SM>
+__device__ __forceinline__ constexpr size_t heap_dyn_offset() { return (sizeof(SM) + 15) & ~(size_t)15; }
+
+template <class SM>
 struct HeapView {
   SM &S;
-  HeapEnt *spill; /* global array indexed by heap position (entries >= HCAP live here) */
+  HeapEnt *spill; /* global array indexed by heap position (entries >= hcap live here) */
   NodeHot *hot;
+  __device__ __forceinline__ int hcap() const { return SM::DYN_HEAP ? S.hcap : SM::HCAP; }
+  __device__ __forceinline__ double *hf() const {
+    if (SM::DYN_HEAP) return reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(&S) + heap_dyn_offset<SM>());
+    return S.hf;
+  }
+  __device__ __forceinline__ double *hg() const { return SM::DYN_HEAP ? hf() + S.hcap : S.hg; }
+  __device__ __forceinline__ int *hn() const { return SM::DYN_HEAP ? reinterpret_cast<int *>(hf() + 2 * (size_t)S.hcap) : S.hn; }
   __device__ __forceinline__ void get(int i, double &f, double &g, int &n) const {
-    if (i < SM::HCAP) { f = S.hf[i]; g = S.hg[i]; n = S.hn[i]; }
+    if (i < hcap()) { f = hf()[i]; g = hg()[i]; n = hn()[i]; }
     else { HeapEnt e = spill[i]; f = e.f; g = e.g; n = e.node; }
   }
   __device__ __forceinline__ void set(int i, double f, double g, int n) const {
-    if (i < SM::HCAP) { S.hf[i] = f; S.hg[i] = g; S.hn[i] = n; }
+    if (i < hcap()) { hf()[i] = f; hg()[i] = g; hn()[i] = n; }
     else { HeapEnt e; e.f = f; e.g = g; e.node = n; e.pad = 0; spill[i] = e; }
     hot[n & 0x7fffffff].heap_pos = i;
   }
-  __device__ __forceinline__ int node_at(int i) const { return (i < SM::HCAP) ? S.hn[i] : spill[i].node; }
-  __device__ __forceinline__ void set_g(int i, double g) const { if (i < SM::HCAP) S.hg[i] = g; else spill[i].g = g; }
+  __device__ __forceinline__ int node_at(int i) const { return (i < hcap()) ? hn()[i] : spill[i].node; }
+  __device__ __forceinline__ void set_g(int i, double g) const { if (i < hcap()) hg()[i] = g; else spill[i].g = g; }
 
   /* serial push/increase: sift up while the parent is strictly worse (boost siftup) */
   __device__ __forceinline__ void sift_up(int pos, double f, double g, int n) const {
@@ -275,6 +316,140 @@ struct HeapView {
     if (lane == 0) set((p1 >> stop) - 1, f, g, n);
     __syncwarp();
   }
+  /* ---- |U| > 32: ancestor cache (see PlanSmem::ac).  Called by one full warp. */
+  __device__ __noinline__ void cache_ancestors(int n0, int K, int lane) const {
+    const int hc = hcap();
+    int lo = 0, cnt = 0;
+    if (lane >= 1) { /* lane l prepares level l: ancestors at distance l of the positions [n0, n0 + K) */
+      lo = ((n0 + 1) >> lane) - 1;
+      const int hi = ((n0 + K) >> lane) - 1;
+      if (lo < hc) lo = hc; /* positions below hcap live in shared memory already */
+      lo &= ~1;             /* even start and even count: 16-byte aligned, 48-byte granular ranges of 24-byte entries */
+      cnt = hi - lo + 1;
+      cnt = cnt > 0 ? ((cnt + 1) & ~1) : 0;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const bool fits = total <= SM::ACAP;
+    S.ac_lo[lane] = lo; S.ac_off[lane] = incl - cnt; S.ac_cnt[lane] = fits ? cnt : 0;
+    __syncwarp();
+    if (fits) {
+#ifdef MPLB_BULK_PREFETCH
+      /* one bulk asynchronous copy (TMA engine, cp.async.bulk) per level, completion on a shared-memory mbarrier */
+      const unsigned bar = (unsigned)__cvta_generic_to_shared(&S.ac_bar);
+      if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(total * 24)) : "memory");
+      }
+      __syncwarp();
+      if (cnt > 0) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&S.ac[incl - cnt]);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(spill + lo), "r"((unsigned)(cnt * 24)), "r"(bar)
+                     : "memory");
+      }
+      unsigned done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+      if (lane == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+#else
+      for (int l = 1; l < 32; l++) { /* 8-byte asynchronous copies (LDGSTS), all levels in flight together */
+        const int c_l = S.ac_cnt[l], lo_l = S.ac_lo[l], off_l = S.ac_off[l];
+        for (int q = lane; q < c_l * 3; q += 32) {
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<unsigned long long *>(&S.ac[off_l]) + q);
+          const unsigned long long *src = reinterpret_cast<const unsigned long long *>(spill + lo_l) + q;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+    }
+    __syncwarp();
+    if (lane == 0) S.ac_valid = 1;
+    __syncwarp();
+  }
+  /* entry at position i, which is an ancestor at distance l >= 1 of a position the cache was built for */
+  __device__ __forceinline__ void cget(int i, int l, double &f, double &g, int &n) const {
+    if (i < hcap()) { f = hf()[i]; g = hg()[i]; n = hn()[i]; return; }
+    const int k = i - S.ac_lo[l];
+    if (k >= 0 && k < S.ac_cnt[l]) { const HeapEnt &e = S.ac[S.ac_off[l] + k]; f = e.f; g = e.g; n = e.node; }
+    else { HeapEnt e = spill[i]; f = e.f; g = e.g; n = e.node; }
+  }
+  __device__ __forceinline__ void cset(int i, int l, double f, double g, int n) const {
+    if (i < hcap()) { hf()[i] = f; hg()[i] = g; hn()[i] = n; }
+    else {
+      HeapEnt e; e.f = f; e.g = g; e.node = n; e.pad = 0;
+      spill[i] = e; /* write-through */
+      const int k = i - S.ac_lo[l];
+      if (l >= 1 && k >= 0 && k < S.ac_cnt[l]) S.ac[S.ac_off[l] + k] = e;
+    }
+    hot[n & 0x7fffffff].heap_pos = i;
+  }
+  /* sift_up_warp for a push at position pos covered by the cache: identical result, ancestors read from shared memory */
+  __device__ __forceinline__ void sift_up_warp_cached(int pos, double f, double g, int n, int lane) const {
+    int p1 = pos + 1;
+    int depth = 31 - __clz(p1);
+    int my = (p1 >> (lane + 1)) - 1;
+    bool have = lane < depth;
+    double af = 0.0, ag = 0.0; int an = 0;
+    if (have) cget(my, lane + 1, af, ag, an);
+    bool moves = have && heap_worse(af, ag, f, g);
+    unsigned stopm = __ballot_sync(0xffffffffu, !moves);
+    int stop = __ffs(stopm) - 1;
+    if (lane < stop) cset((p1 >> lane) - 1, lane, af, ag, an);
+    if (lane == 0) cset((p1 >> stop) - 1, stop, f, g, n);
+    __syncwarp();
+  }
+  /* pop by one full warp: the levels inside shared memory are walked as before; below them every round fetches the
+   * 4-level subtree under the current position (30 entries, one per lane, ONE round trip) and walks it with shuffles.
+   * Same comparisons in the same order as sift_down => same heap. */
+  __device__ __noinline__ void sift_down_warp(int n_heap, double f, double g, int n, int lane) const {
+    int pos = 0;
+    const int hc = hcap();
+    bool done = false;
+    while (true) { /* shared-memory levels */
+      const int c = 2 * pos + 1;
+      if (c >= n_heap) { done = true; break; }
+      if (c + 1 >= hc) break;
+      double cf = hf()[c], cg = hg()[c]; int cn = hn()[c]; int cc = c;
+      if (c + 1 < n_heap) {
+        const double rf = hf()[c + 1], rg = hg()[c + 1];
+        if (heap_worse(cf, cg, rf, rg)) { cc = c + 1; cf = rf; cg = rg; cn = hn()[c + 1]; }
+      }
+      if (!heap_worse(cf, cg, f, g)) { if (lane == 0) set(pos, cf, cg, cn); pos = cc; }
+      else { done = true; break; }
+    }
+    while (!done) {
+      const long long p1 = (long long)pos + 1;
+      const int L = 1 + (lane >= 2) + (lane >= 6) + (lane >= 14);
+      const long long q = (p1 << L) - 1 + (lane - ((1 << L) - 2));
+      const bool valid = lane < 30 && q < (long long)n_heap;
+      double ef = 0.0, eg = 0.0; int en = 0;
+      if (valid) get((int)q, ef, eg, en);
+      int j = 0;
+#pragma unroll
+      for (int lv = 1; lv <= 4; lv++) {
+        const int rl = (1 << lv) - 2 + 2 * j; /* lane holding the left child */
+        double cf = __shfl_sync(0xffffffffu, ef, rl), cg = __shfl_sync(0xffffffffu, eg, rl);
+        int cn = __shfl_sync(0xffffffffu, en, rl);
+        const bool cv = __shfl_sync(0xffffffffu, (int)valid, rl) != 0;
+        const double rf = __shfl_sync(0xffffffffu, ef, rl + 1), rg = __shfl_sync(0xffffffffu, eg, rl + 1);
+        const int rn = __shfl_sync(0xffffffffu, en, rl + 1);
+        const bool rv = __shfl_sync(0xffffffffu, (int)valid, rl + 1) != 0;
+        if (!cv) { done = true; break; }
+        int right = 0;
+        if (rv && heap_worse(cf, cg, rf, rg)) { right = 1; cf = rf; cg = rg; cn = rn; }
+        if (!heap_worse(cf, cg, f, g)) { if (lane == 0) set(pos, cf, cg, cn); pos = 2 * pos + 1 + right; j = 2 * j + right; }
+        else { done = true; break; }
+      }
+    }
+    if (lane == 0) set(pos, f, g, n);
+    __syncwarp();
+  }
+
   /* pop: sift the former last element down from the root; ties still move down (boost siftdown) */
   __device__ __forceinline__ void sift_down(int n_heap, int pos, double f, double g, int n) const {
     while (true) {
@@ -642,17 +817,23 @@ __device__ __noinline__ bool goal_test_warp(const DevCfg &c, const SM &S, const 
   return !hit;
 }
 
-/* eb:46-64 (heur_ignore_dynamics_ = true, no prior trajectory) */
+/* eb:46-64 (heur_ignore_dynamics_ = true).  With a prior trajectory (eb:49-51) the target is the prior's waypoint at the
+ * state's own time, plus the prior's remaining cost: row `depth` of c.prior holds both (the state's time is a function of
+ * its depth alone, see RowHdr::depth; rows exist while size_t(t / dt) < prior_traj_.size()). */
 template <int DIM, int ORD, class SM>
 __device__ __forceinline__ double heuristic(const DevCfg &c, const SM &S, const double *st, unsigned long long k0,
-                                            unsigned long long k1) {
+                                            unsigned long long k1, int depth) {
   if (c.eps == 0.0) return 0.0; /* gs:53,87 */
   if (S.goal_key_ok && k0 == S.gk0 && k1 == S.gk1) return 0.0;
+  const bool pr = c.prior_n > 0 && depth < c.prior_n;
+  const double *P = pr ? c.prior + 4 * depth : S.goal_pos;
   double m = 0.0;
 #pragma unroll
-  for (int ax = 0; ax < DIM; ax++) m = fmax(m, fabs(dsub(st[ax], S.goal_pos[ax])));
-  if (c.v_max > 0.0) return (c.vmax_rcp_exact != 0.0) ? dmul(dmul(c.w, m), c.vmax_rcp_exact) : div_exact(dmul(c.w, m), c.v_max);
-  return dmul(c.w, m);
+  for (int ax = 0; ax < DIM; ax++) m = fmax(m, fabs(dsub(st[ax], pr ? __ldg(&P[ax]) : P[ax])));
+  double h;
+  if (c.v_max > 0.0) h = (c.vmax_rcp_exact != 0.0) ? dmul(dmul(c.w, m), c.vmax_rcp_exact) : div_exact(dmul(c.w, m), c.v_max);
+  else h = dmul(c.w, m);
+  return pr ? dadd(h, __ldg(&P[3])) : h;
 }
 
 /* unpack the lattice ints of a node from its packed key */
@@ -679,7 +860,7 @@ __device__ __forceinline__ unsigned long long khash_of_ints(const int *ints, int
  * global memory, so it is correct under every hazard (duplicate siblings, slot collisions).  gs:79-143. */
 template <int DIM, int ORD, class SM>
 __device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, typename SM::EB &E, HeapEnt *spill, Slot *table, NodeHot *hot,
-                                          unsigned char *rows, int i0, int i1, bool wide) {
+                                          unsigned char *rows, int i0, int i1, bool wide, PredRec *plog) {
   const HeapView<SM> H{S, spill, hot}; /* built here: a view whose address escapes would turn heap accesses generic */
   constexpr int NS = SM::NS;
   constexpr size_t ROWB = (sizeof(RowHdr) + NS * sizeof(double) + 15) & ~(size_t)15; /* 16-byte aligned rows */
@@ -696,10 +877,10 @@ __device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, typename SM::E
     NodeHot hn;
     if (nid < 0) { /* gs:84-88 */
       nid = S.n_nodes++;
-      hn.g = kInf; hn.h = heuristic<DIM, ORD>(c, S, &E.es[idx * NS], k0, k1); hn.pg = 0.0; hn.heap_pos = -1; hn.action = -1;
+      hn.g = kInf; hn.h = heuristic<DIM, ORD>(c, S, &E.es[idx * NS], k0, k1, S.cur_depth + 1); hn.pg = 0.0; hn.heap_pos = -1; hn.action = -1;
       hn.flags = 0; hn.pad0 = 0;
       RowHdr *rh = reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB);
-      rh->k0 = k0; rh->k1 = k1; rh->parent = -1; rh->slot = slot; rh->pad = 0;
+      rh->k0 = k0; rh->k1 = k1; rh->parent = -1; rh->slot = slot; rh->pred_head = -1; rh->depth = S.cur_depth + 1;
       double *rs = reinterpret_cast<double *>(rows + (size_t)nid * ROWB + sizeof(RowHdr));
       for (int f = 0; f < NS; f++) rs[f] = E.es[idx * NS + f];
       Slot sl; sl.k0 = k0; sl.k1lo = (unsigned int)k1; sl.node1 = (unsigned)(nid + 1); sl.g = kInf; sl.pg = 0.0;
@@ -713,6 +894,13 @@ __device__ __noinline__ void relax_serial(const DevCfg &c, SM &S, typename SM::E
       const int base_t = E.gbase[idx] * 8, cn_t = E.cnt[idx];
       for (int q = 0; q < cn_t; q++) { acc = dadd(acc, S.terms[base_t + q]); acc = dadd(acc, S.yterms[base_t + q]); }
       ecost = dadd(acc, S.cost[idx]);
+    }
+    if (plog) { /* gs:100-102: every finite-cost edge is recorded, improving or not */
+      RowHdr *rh = reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB);
+      PredRec r; r.cost = ecost; r.pred = cn; r.next = rh->pred_head; r.action = idx; r.pad = 0;
+      const int e = S.n_log++;
+      plog[e] = r;
+      rh->pred_head = e;
     }
     double tentative = dadd(cg, ecost); /* gs:107 */
     if (tentative < hn.g) { /* gs:109-141 */
@@ -874,7 +1062,8 @@ __device__ __forceinline__ void sample_granules_shaped(const DevCfg &c, SM &S, E
 
 /* ---------------------------------------------------------------- the kernel */
 template <int DIM, int ORD, int NB, bool POT>
-__global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ BatchArgs a) {
+__global__ void __launch_bounds__(MPLB_NT, (NB == 1 && !POT) ? MPLB_MIN_CTAS : 2) /* the other instantiations are shared-memory bound at 2 per SM */
+astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ BatchArgs a) {
   constexpr int NP = DIM * ORD;
   constexpr int NS = NP + (POT ? 1 : 0); /* cost-shaping / yaw instantiations carry a yaw slot after the polynomial state */
   constexpr int NW = MPLB_NT / 32;
@@ -892,11 +1081,13 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
   HeapEnt *spill = reinterpret_cast<HeapEnt *>(base + a.off_heap);
   Slot *table = reinterpret_cast<Slot *>(base + a.off_table);
   int *poplog = reinterpret_cast<int *>(base + a.off_poplog);
+  PredRec *plog = a.log_cap > 0 ? reinterpret_cast<PredRec *>(base + a.off_log) : nullptr; /* log mode: see PredRec */
   const bool wide = c.key_wide != 0;
   const bool fast = c.use_fast != 0;
   HeapView<SM> H{S, spill, hot};
 
   /* ---------------- per-launch constants */
+  if (tid == 0) S.hcap = SM::DYN_HEAP ? a.hcap : SM::HCAP;
   for (int i = tid; i < c.nU * 3; i += MPLB_NT) { S.U[i] = c.U[i]; S.Ut[i] = Axis<ORD>::top_of(c.U[i]); }
   if (POT) for (int i = tid; i < c.nU; i += MPLB_NT) S.Uyaw[i] = (c.use_yaw && c.Uyaw) ? c.Uyaw[i] : 0.0;
   for (int i = tid; i < c.nU; i += MPLB_NT) {
@@ -927,12 +1118,15 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
     }
     if (tid == 0) {
       const mplb_waypoint &st = a.starts[pid];
-      const mplb_waypoint &gl = a.goals[pid];
       S.tsize = MPLB_TINIT; S.n_nodes = 0; S.n_heap = 0; S.pops = 0; S.n_closed = 0; S.status = -1;
       S.n_samples = 0; S.n_valid = 0; S.n_before = 0; S.sd_pending = 0; S.pf_node = -1;
+      S.n_log = 0; S.cur_depth = 0; S.pf_depth = 0;
       S.cur_buf = 0;
       for (int q = 0; q < SM::NBUF; q++) { S.eb[q].ready = 0; S.eb[q].node = -1; S.eb[q].key_bad = 0; }
       S.pop_hash = 0ull; S.closed_hash = 0ull; S.goal_hit = 0;
+      /* eb:295-298, em:224: with a prior trajectory installed the requested goal is ignored, the goal stays the prior's end */
+      const mplb_waypoint &gq = a.goals[pid];
+      const mplb_waypoint &gl = c.prior_on ? c.prior_goal : gq;
       for (int ax = 0; ax < 3; ax++) { S.goal_pos[ax] = gl.pos[ax]; S.goal_vel[ax] = gl.vel[ax]; S.goal_acc[ax] = gl.acc[ax]; }
       double s0[NS];
       for (int ax = 0; ax < DIM; ax++) {
@@ -990,12 +1184,12 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
       if (!pack_key_nohash<DIM, ORD, NS>(c, ints, k0, k1)) S.status = MPLB_PLAN_KEY_RANGE;
       else {
         NodeHot n0;
-        n0.g = 0.0; n0.h = heuristic<DIM, ORD>(c, S, S.cur, k0, k1); n0.pg = 0.0; n0.heap_pos = 0; n0.action = -1;
+        n0.g = 0.0; n0.h = heuristic<DIM, ORD>(c, S, S.cur, k0, k1, 0); n0.pg = 0.0; n0.heap_pos = 0; n0.action = -1;
         n0.flags = 3; n0.pad0 = 0;
         hot[0] = n0;
         int slot = table_insert_atomic(table, S.tsize, k0, k1, 0, 0.0, 0.0);
         RowHdr *rh = reinterpret_cast<RowHdr *>(rows);
-        rh->k0 = k0; rh->k1 = k1; rh->parent = -1; rh->slot = slot; rh->pad = 0;
+        rh->k0 = k0; rh->k1 = k1; rh->parent = -1; rh->slot = slot; rh->pred_head = -1; rh->depth = 0;
         double *rs = reinterpret_cast<double *>(rows + sizeof(RowHdr));
         for (int f = 0; f < NS; f++) rs[f] = S.cur[f];
         S.n_nodes = 1; S.n_heap = 0;
@@ -1017,7 +1211,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
     while (S.status < 0) {
       MPLB_TICK(7);
       /* capacity: this expansion can add at most nU nodes / heap entries */
-      if (S.n_nodes + c.nU > a.cap || S.n_heap + c.nU + 1 > a.cap) {
+      if (S.n_nodes + c.nU > a.cap || S.n_heap + c.nU + 1 > a.cap || (plog && S.n_log + c.nU > a.log_cap)) {
         __syncthreads();
         if (tid == 0) S.status = MPLB_INTERNAL_OVERFLOW;
         __syncthreads();
@@ -1058,13 +1252,18 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
       MPLB_TICK(0);
       if (warp == NW - 1) {
         /* ---- heap warp: finish the previous pop's sift-down, prefetch the new root's state row ... */
+        if (SM::DYN_HEAP) { /* |U| > 32: the heap is deep and mostly in global memory -> cooperative sift-down */
+          if (S.sd_pending) H.sift_down_warp(S.n_heap, S.sd_f, S.sd_g, S.sd_n, lane);
+          __syncwarp();
+        }
         if (lane == 0) {
-          if (S.sd_pending) { H.sift_down(S.n_heap, 0, S.sd_f, S.sd_g, S.sd_n); S.sd_pending = 0; }
+          if (!SM::DYN_HEAP && S.sd_pending) H.sift_down(S.n_heap, 0, S.sd_f, S.sd_g, S.sd_n);
+          S.sd_pending = 0;
           int pf = -1;
           if (S.n_heap > 0) {
-            pf = S.hn[0] & 0x7fffffff;
+            pf = H.hn()[0] & 0x7fffffff;
             const RowHdr *rh = reinterpret_cast<const RowHdr *>(rows + (size_t)pf * ROWB);
-            S.pf_k0 = __ldcg(&rh->k0); S.pf_k1 = __ldcg(&rh->k1);
+            S.pf_k0 = __ldcg(&rh->k0); S.pf_k1 = __ldcg(&rh->k1); S.pf_depth = __ldcg(&rh->depth);
             const double *rs = reinterpret_cast<const double *>(rows + (size_t)pf * ROWB + sizeof(RowHdr));
 #pragma unroll
             for (int f = 0; f < NS; f++) S.pf_st[f] = __ldcg(&rs[f]);
@@ -1106,7 +1305,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
               for (int q = 0; q < WIN; q++) sw[q] = load_slot_cg(&table[(h0 + q) & mask]);
             }
             double hv = 0.0;
-            if (probing) hv = heuristic<DIM, ORD>(c, S, &E.es[i * NS], k0, k1);
+            if (probing) hv = heuristic<DIM, ORD>(c, S, &E.es[i * NS], k0, k1, S.cur_depth + 1);
             int nid = -1, slot = -1;
             double g = kInf, pg = 0.0;
             if (probing) {
@@ -1156,6 +1355,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
           if (!S.cur_tag) { S.n_closed++; S.closed_hash += kh; }
         }
         int ns_acc = 0, nv_acc = 0;
+        if (SM::DYN_HEAP) { if (lane == 0) S.ac_valid = 0; __syncwarp(); }
 #pragma unroll
         for (int b = 0; b < NB; b++) {
           const int i = b * 32 + lane;
@@ -1195,10 +1395,14 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
                             (equal keys share the probe sequence, hence its first empty slot) */
                 for (int q = 0; q < b * 32; q++) hazard = hazard || (E.nid[q] >= S.n_before && S.p_slot[q] == r_slot_b);
             }
-            hazard = __any_sync(0xffffffffu, hazard);
+            hazard = __any_sync(0xffffffffu, hazard) || (plog != nullptr); /* log mode relaxes serially: the records live there */
           }
           if (hazard) {
-            if (lane == 0) { MPLB_COUNT(3, 1); relax_serial<DIM, ORD>(c, S, E, spill, table, hot, rows, b * 32, min(c.nU, b * 32 + 32), wide); }
+            if (lane == 0) {
+              MPLB_COUNT(3, 1);
+              relax_serial<DIM, ORD>(c, S, E, spill, table, hot, rows, b * 32, min(c.nU, b * 32 + 32), wide, plog);
+              if (SM::DYN_HEAP) S.ac_valid = 0; /* the serial routine moved heap entries behind the ancestor cache's back */
+            }
             __syncwarp();
             continue;
           }
@@ -1224,7 +1428,7 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
           /* lane-parallel stores */
           if (isnew) { /* gs:84-88: the node's coord is this (first) discoverer's state */
             RowHdr *rh = reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB);
-            rh->k0 = rk0_b; rh->k1 = rk1_b; rh->parent = cn; rh->slot = r_slot_b; rh->pad = 0;
+            rh->k0 = rk0_b; rh->k1 = rk1_b; rh->parent = cn; rh->slot = r_slot_b; rh->pred_head = -1; rh->depth = S.cur_depth + 1;
             double *rs = reinterpret_cast<double *>(rows + (size_t)nid * ROWB + sizeof(RowHdr));
 #pragma unroll
             for (int q = 0; q < NS; q++) rs[q] = E.es[i * NS + q];
@@ -1257,15 +1461,21 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
             if (!jnew && (jfl & 1) && !(jfl & 2)) { /* increase(): f lowered, sift up only (gs:131-133) */
               if (jpos < 0 || jpos >= S.n_heap || (H.node_at(jpos) & 0x7fffffff) != jn) jpos = hot[jn].heap_pos; /* moved by an earlier sift of this pop */
               H.sift_up_warp(jpos, jf, jg, jn, lane);
+              if (SM::DYN_HEAP) { if (lane == 0) S.ac_valid = 0; __syncwarp(); } /* arbitrary position: not through the cache */
             } else {
               int tag = jn;
               if (!jnew && (jfl & 2)) { /* closed node re-pushed (gs:135-141): refresh g copies of its stale entries */
                 for (int q = lane; q < S.n_heap; q += 32) if ((H.node_at(q) & 0x7fffffff) == jn) H.set_g(q, jg);
                 tag = jn | 0x80000000;
                 __syncwarp();
+                if (SM::DYN_HEAP) { if (lane == 0) S.ac_valid = 0; __syncwarp(); }
               }
               const int np = S.n_heap;
               __syncwarp();
+              if (SM::DYN_HEAP && np >= H.hcap()) { /* deep heap: ancestors of this pop's pushes come from the shared-memory cache */
+                if (!S.ac_valid) H.cache_ancestors(np, c.nU, lane);
+                H.sift_up_warp_cached(np, jf, jg, tag, lane);
+              } else
               H.sift_up_warp(np, jf, jg, tag, lane);
               if (lane == 0) S.n_heap = np + 1;
               __syncwarp();
@@ -1285,30 +1495,35 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
           else if (S.n_heap == 0) status = MPLB_PLAN_QUEUE_EMPTY;
           if (status >= 0) S.status = status;
           else {
-            const int tagged = S.hn[0];
-            const double topg = S.hg[0];
+            const int tagged = H.hn()[0];
+            const double topg = H.hg()[0];
             const int n = S.n_heap - 1;
             if (n > 0) { H.get(n, S.sd_f, S.sd_g, S.sd_n); S.sd_pending = 1; } /* sift-down deferred to the heap warp */
             S.n_heap = n;
             const int nx = tagged & 0x7fffffff;
             unsigned long long k0, k1;
+            int ndepth;
             if (nx >= S.n_before) { /* created in this expansion: forward its state from shared memory */
               int j = 0;
               for (int q = 0; q < c.nU; q++) if (E.nid[q] == nx) { j = q; break; }
               k0 = E.k0[j]; k1 = E.k1[j];
+              ndepth = S.cur_depth + 1;
 #pragma unroll
               for (int f = 0; f < NS; f++) S.cur[f] = E.es[j * NS + f];
             } else if (nx == S.pf_node) {
               k0 = S.pf_k0; k1 = S.pf_k1;
+              ndepth = S.pf_depth;
 #pragma unroll
               for (int f = 0; f < NS; f++) S.cur[f] = S.pf_st[f];
             } else {
               const RowHdr *rh = reinterpret_cast<const RowHdr *>(rows + (size_t)nx * ROWB);
               k0 = rh->k0; k1 = rh->k1;
+              ndepth = rh->depth;
               const double *rs = reinterpret_cast<const double *>(rows + (size_t)nx * ROWB + sizeof(RowHdr));
 #pragma unroll
               for (int f = 0; f < NS; f++) S.cur[f] = rs[f];
             }
+            S.cur_depth = ndepth;
             S.cur_k0 = k0; S.cur_k1 = k1;
             S.cur_node = nx;
             S.cur_g = topg;
@@ -1340,6 +1555,26 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
       if (S.status == MPLB_PLAN_OK) {
         int n = 0, cnode = S.cur_node;
         bool ok = true;
+        if (plog) {
+          /* log mode, gs:386-437 verbatim: among the node's predecessor records take the smallest g_pred + cost with the
+           * predecessors' FINAL g, ties -> larger g_pred, then the earliest record; the choice is written back into the
+           * node (parent / action) so that the second pass below and the node getters read it. */
+          while (true) {
+            RowHdr *rh = reinterpret_cast<RowHdr *>(rows + (size_t)cnode * ROWB);
+            int e = rh->pred_head, best = -1;
+            double min_rhs = kInf, min_g = kInf;
+            for (; e >= 0; e = plog[e].next) { /* newest -> oldest: on a full tie the older record replaces the newer one */
+              const double gp = hot[plog[e].pred].g;
+              const double rhs = dadd(gp, plog[e].cost);
+              if (rhs < min_rhs || (rhs == min_rhs && gp >= min_g)) { min_rhs = rhs; min_g = gp; best = e; }
+            }
+            if (best < 0 || n > S.n_nodes) { ok = false; break; }
+            rh->parent = plog[best].pred;
+            hot[cnode].action = (short)plog[best].action;
+            n++; cnode = plog[best].pred;
+            if (cnode == 0) break; /* gs:433: reached the start key */
+          }
+        } else
         while (cnode != 0) {
           int p = reinterpret_cast<const RowHdr *>(rows + (size_t)cnode * ROWB)->parent;
           if (p < 0 || n > S.n_nodes) { ok = false; break; }
@@ -1375,8 +1610,8 @@ __global__ void __launch_bounds__(MPLB_NT, MPLB_MIN_CTAS) astar_batch_kernel(con
       __syncthreads();
       if (tid == 0 && S.sd_pending) { H.sift_down(S.n_heap, 0, S.sd_f, S.sd_g, S.sd_n); S.sd_pending = 0; }
       __syncthreads();
-      for (int i = tid; i < S.n_heap && i < SM::HCAP; i += MPLB_NT) {
-        HeapEnt e; e.f = S.hf[i]; e.g = S.hg[i]; e.node = S.hn[i]; e.pad = 0;
+      for (int i = tid; i < S.n_heap && i < H.hcap(); i += MPLB_NT) {
+        HeapEnt e; e.f = H.hf()[i]; e.g = H.hg()[i]; e.node = H.hn()[i]; e.pad = 0;
         spill[i] = e;
       }
     }

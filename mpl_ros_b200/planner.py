@@ -263,6 +263,24 @@ class MapPlanner:
         if not ignore:
             raise MplbError("heur_ignore_dynamics = false needs the reference's polynomial root finder (env_base.h:67-211); "
                             "not part of this path")
+    def setPriorTrajectory(self, traj):  # planner_base.h:249-252 (None or an empty trajectory clears)
+        segs = traj.getPrimitives() if traj is not None else []
+        n = len(segs)
+        if n == 0:
+            check(lib().mplb_planner_set_prior_trajectory(self._h, 0, None, None, 0))
+            return
+        cs = np.zeros((n, 4, 6))
+        ts = np.zeros(n)
+        for i, pr in enumerate(segs):
+            cs[i, :self.dim] = pr.coeffs
+            if pr.yaw_coeff is not None:
+                cs[i, 3] = pr.yaw_coeff
+            ts[i] = pr.t()
+        check(lib().mplb_planner_set_prior_trajectory(self._h, n, ptr(cs), ptr(ts), int(segs[-1].control)))
+
+    def setExactPreds(self, mode):  # MPLB_EXACT_PREDS: -1 auto, 0 never, 1 always (predecessor lists of graph_search.h:100-102)
+        self._set("exact_preds", mode)
+
     def setMemFraction(self, f): self._set("mem_fraction", f)
     def setMaxSlots(self, n): self._set("max_slots", n)
 

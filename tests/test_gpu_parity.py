@@ -147,8 +147,36 @@ def test_nonzero_start_velocity_and_epsilon():
         pl.plan(sg, gg)
         ro = op.plan(so, go)
         assert_results_equal(pl.result(), ro, eps)
-        if eps <= 1.0:  # with an inflated heuristic only the cost/closed set are pinned, see DESIGN.md
-            assert np.array_equal(pl.getActions(), op.actions(ro["n_seg"]))
+        # eps = 2 re-opens closed nodes: the predecessor log (MPLB_EXACT_PREDS, automatic for eps > 1) makes recoverTraj
+        # resolve every predecessor with its final g, like graph_search.h:391-405
+        assert np.array_equal(pl.getActions(), op.actions(ro["n_seg"])), eps
+        # the stored coord keeps the derivatives below the control order (ACC: pos, vel); the oracle also carries acc = u
+        assert np.array_equal(pl.getSegStates()[:, :6], op.seg_states(ro["n_seg"])[:, :6]), eps
+
+
+def test_epsilon_gt1_trajectories_batch():
+    """Weighted A* (eps = 2 and 3.5, closed nodes re-opened): action sequences and segment states of a whole batch against
+    the oracle's predecessor lists, on levine and on the corridor with a start velocity; and the forced log (exact_preds = 1)
+    at eps = 1 must reproduce the running best-predecessor results exactly."""
+    m = maps.load_fixture("levine")
+    U = maps.make_U(1.0, 1, 3)
+    S, G = maps.sample_queries(m, 48, seed=11)
+    n_reopened = 0
+    for eps, force in ((2.0, -1), (3.5, -1), (1.0, 1)):
+        pl, op = make_pair(m, 3, dict(v_max=2.0, a_max=1.0, dt=1.0, tol_pos=0.5, epsilon=eps), U)
+        pl.setExactPreds(force)
+        sg, so = waypoint_pair(S, mp.ACC)
+        gg, go = waypoint_pair(G, mp.ACC)
+        res, acts, segs = pl.plan_batch(sg, gg, max_seg=64, want_states=True)
+        ro, ao = op.plan_batch(so, go, nthreads=8, max_seg=64)
+        for f in ("status", "n_seg", "cost", "pops", "n_nodes", "n_open", "n_closed", "pop_hash", "closed_hash"):
+            assert np.array_equal(res[f], ro[f]) or (f == "cost" and np.array_equal(res[f][np.isfinite(ro[f])], ro[f][np.isfinite(ro[f])])), (eps, f)
+        assert np.array_equal(acts, ao), eps
+        n_reopened += int((res["pops"] != res["n_closed"]).sum())
+        for i in np.flatnonzero(ro["status"] == 0)[:6]:  # segment states of a few plans against single oracle plans
+            r1 = op.plan(so[i:i + 1], go[i:i + 1])
+            assert np.array_equal(segs[i, :r1["n_seg"], :6], op.seg_states(r1["n_seg"])[:, :6]), (eps, i)
+    assert n_reopened > 0, "no plan re-opened a closed node: the test does not exercise the log"
 
 
 def test_jrk_control_2d():
@@ -298,19 +326,22 @@ def test_synthetic_boxes_jrk125_batch():
 
 
 def test_full_bench_batch_parity():
-    """BASELINE configs[1] at FULL size: the 1024-query levine-256 batch of bench.py, every plan compared with the
-    oracle (status, cost, counters, pop-order hash, closed hash, action rows), plus size-independent invariants."""
+    """BASELINE configs[1] at FULL size: the 1024-query levine-256 batch (the first 1024 queries of bench.py's list), every
+    plan compared with the oracle (status, cost, counters, pop-order hash, closed hash, action rows), plus
+    size-independent invariants."""
     import os
-    import bench
-    m = maps.levine256()
-    U = maps.make_U(1.0, 1, 3)
-    pl, op = make_pair(m, 3, dict(bench.PLAN_PARAMS), U)
-    s, g = bench.make_queries(m, 0)
+    from mpl_ros_b200 import workloads as W
+    m = W.c2_map()
+    U = W.controls(W.C2)
+    pl, op = make_pair(m, 3, dict(W.C2["params"]), U)
+    S, G = W.c2_queries(m, 1024)
+    s, g = mp.waypoints_array(1024), mp.waypoints_array(1024)
+    W.fill(s, g, S, G, W.C2["control"])
     so, go = oracle.make_waypoints(len(s)), oracle.make_waypoints(len(s))
     for f in ("pos", "control"):
         so[f], go[f] = s[f], g[f]
-    rg, ag, _ = pl.plan_batch(s, g, max_seg=bench.MAX_SEG)
-    ro, ao = op.plan_batch(so, go, nthreads=os.cpu_count() or 8, max_seg=bench.MAX_SEG)
+    rg, ag, _ = pl.plan_batch(s, g, max_seg=64)
+    ro, ao = op.plan_batch(so, go, nthreads=os.cpu_count() or 8, max_seg=64)
     for f in RESULT_FIELDS:
         a, b = rg[f], ro[f]
         if f == "cost":

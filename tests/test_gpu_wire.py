@@ -94,3 +94,27 @@ def test_wire_jrk_3d():
     sg, so = waypoint_pair([start], mp.JRK)
     gg, go = waypoint_pair([goal], mp.JRK)
     _check(pl, op, sg, gg, so, go, 3, mp.JRK, Uj, 1.0, 1, 64, 0.0)
+
+
+def test_wire_against_reference_generated_bytes():
+    """Independent expectation (tests/golden/wire_msgs.npz, tools/make_golden_wire.py): trajectories planned by the
+    reference's own sources, coefficient rows read from the reference's Primitive objects, message assembled as
+    primitive_ros_utils.h does and serialised by a generic ROS 1 serialiser driven by the text of
+    planning_ros_msgs/msg/{Trajectory,Primitive,LambdaSeg}.msg.  The GPU plans the same queries and writes the bytes itself."""
+    import os
+    sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools")
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wire_msgs.npz"))
+    src = open(os.path.join(sys_path, "make_golden_wire.py")).read()
+    cases = eval(src[src.index("CASES = {") + len("CASES = "):src.index("}\n\n\ndef main") + 1])  # the generator's own case table
+    for name, (cfgname, control, swap, _, po, z) in cases.items():
+        m, dim, params, U, start, goal = load_config(cfgname)
+        params = dict(params, **po)
+        if swap:
+            start, goal = goal, start
+        pl, _ = make_pair(m, dim, params, U)
+        sg, _ = waypoint_pair([start], control)
+        gg, _ = waypoint_pair([goal], control)
+        rg, ag, segs = pl.plan_batch(sg, gg, max_seg=64, want_states=True)
+        assert rg[0]["status"] == 0 and rg[0]["n_seg"] == int(gold[name + "/n_seg"]), name
+        msgs = pl.serialize_trajectories(rg, ag, segs, z=z, frame_id="map", seq=7, stamp=(12, 345))
+        assert msgs[0] == gold[name + "/bytes"].tobytes(), name
