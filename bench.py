@@ -19,11 +19,11 @@ A "step" is one pass of the whole list through the planner: every rank plans its
 records and action rows (the one data-path collective).  Unit of work: one primitive expansion = one (popped state, u)
 pair entering env_map.h:155.
 
-`value`   : device-resident stripes (ShardedBatchPlanner.plan_stripe_device -> mplb_plan_batch_device + gather), CUDA
-            events on the launch stream, max over ranks.
-`e2e`     : the public host-buffer call (ShardedBatchPlanner.plan_batch -> MapPlanner.plan_batch -> mplb_plan_batch) with
-            pinned host inputs: H2D of the stripe's starts/goals, D2H of results + action rows and the gather inside the
-            timed region.
+`value`   : device-resident stripes (ShardedBatchPlanner.plan_stripe_device -> mplb_plan_stripe_gather_device: the search
+            kernel + the ncclSend/ncclRecv gather inside libmplb), CUDA events on the launch stream, max over ranks.
+`e2e`     : the public host-buffer call (ShardedBatchPlanner.plan_batch -> mplb_plan_batch_sharded) with the full list in
+            pinned host memory on every rank: H2D of the stripe's starts/goals, the gather and D2H of results + action
+            rows inside the timed region.
 `roofline`: ALGORITHMIC bytes per primitive expansion (SURVEY.md §8d formula, recomputed from the kernel's own
             counters) x expansions per launch / launch duration, against MEASURED_PEAKS.json hbm_gbs.
 `cpu_baseline`: the reference's CPU path on this box's host cores, bounded sample (dynamic work queue over the sample,
@@ -308,9 +308,7 @@ def main():
     nq = args.queries or spec["n_queries"]
     m = wl["make_map"]() if rank == 0 else None
 
-    def make_planner(o, d, r, grid):
-        mu = mp.VoxelMapUtil()
-        mu.setMapFromDevice(o, d, grid.data_ptr(), r)
+    def make_planner(o, d, r, mu):  # mu: the MapUtil that mplb_comm_broadcast_map built on this rank's device
         mu.freeUnknown()
         pl = mp.VoxelMapPlanner(False)
         pl.setMapUtil(mu)
@@ -323,7 +321,10 @@ def main():
         pl._keep = mu
         return pl
 
-    sp = mdist.ShardedBatchPlanner(make_planner, dev)
+    # the two data-path collectives (grid broadcast, result gather) run inside libmplb on its own NCCL communicator;
+    # torch.distributed only carries the communicator id, the query list and the timing reductions
+    comm = mdist.Comm.from_process_group(dev)
+    sp = mdist.ShardedBatchPlanner(make_planner, dev, comm=comm)
     if m is not None:
         sp.set_map(m.origin, m.dim, m.res, m.data)
     else:
@@ -375,9 +376,9 @@ def main():
     res_all, _ = sp.unstripe(bufs, nq, MAX_SEG) if rank == 0 else (None, None)
 
     # ---- e2e through the public host-buffer API (pinned inputs, H2D + D2H + gather inside the timed region)
-    s_pin = hs.numpy().view(_lib.WAYPOINT_DTYPE).reshape(-1)
-    g_pin = hg.numpy().view(_lib.WAYPOINT_DTYPE).reshape(-1)
-    sp.plan_batch_local(s_pin, g_pin, nq, MAX_SEG)
+    s_pin = torch.from_numpy(s_all.view(np.uint8).reshape(nq, -1)).pin_memory().numpy().view(_lib.WAYPOINT_DTYPE).reshape(-1)
+    g_pin = torch.from_numpy(g_all.view(np.uint8).reshape(nq, -1)).pin_memory().numpy().view(_lib.WAYPOINT_DTYPE).reshape(-1)
+    sp.plan_batch(s_pin, g_pin, MAX_SEG)
     barrier()
     e2e_steps = max(2, min(args.steps, int(30e3 * args.steps / max(total_ms, 1.0))))
     flush_ms = 0.0
@@ -389,7 +390,7 @@ def main():
     for _ in range(e2e_steps):
         flush.zero_()
         torch.cuda.synchronize()
-        res_h, acts_h = sp.plan_batch_local(s_pin, g_pin, nq, MAX_SEG)
+        res_h, acts_h = sp.plan_batch(s_pin, g_pin, MAX_SEG)
     barrier()
     e2e_ms = ((time.perf_counter() - t0) * 1e3 - flush_ms * e2e_steps) / e2e_steps
     if rank == 0:

@@ -32,6 +32,29 @@
 
 typedef double decimal_t; /* data_type.h:49 */
 
+/* printf colour macros of data_type.h:14-41 (the reference's callers use them in their own messages) */
+#ifndef ANSI_COLOR_RED
+#define ANSI_COLOR_RED "\x1b[1;31m"
+#endif
+#ifndef ANSI_COLOR_GREEN
+#define ANSI_COLOR_GREEN "\x1b[1;32m"
+#endif
+#ifndef ANSI_COLOR_YELLOW
+#define ANSI_COLOR_YELLOW "\x1b[1;33m"
+#endif
+#ifndef ANSI_COLOR_BLUE
+#define ANSI_COLOR_BLUE "\x1b[1;34m"
+#endif
+#ifndef ANSI_COLOR_MAGENTA
+#define ANSI_COLOR_MAGENTA "\x1b[1;35m"
+#endif
+#ifndef ANSI_COLOR_CYAN
+#define ANSI_COLOR_CYAN "\x1b[1;36m"
+#endif
+#ifndef ANSI_COLOR_RESET
+#define ANSI_COLOR_RESET "\x1b[0m"
+#endif
+
 #ifdef MPL_B200_USE_EIGEN
 #include <Eigen/Geometry>
 #include <Eigen/StdVector>
@@ -42,6 +65,13 @@ using Vecf = Eigen::Matrix<decimal_t, N, 1>;
 template <int N>
 using Veci = Eigen::Matrix<int, N, 1>;
 typedef Eigen::Matrix<decimal_t, Eigen::Dynamic, 1> VecDf;
+template <int M, int N>
+using Matf = Eigen::Matrix<decimal_t, M, N>; /* data_type.h:77-101 */
+typedef Matf<2, 2> Mat2f;
+typedef Matf<3, 3> Mat3f;
+typedef Matf<4, 4> Mat4f;
+typedef Matf<6, 6> Mat6f;
+typedef Vecf<6> Vec6f;
 #else
 template <typename T>
 using vec_E = std::vector<T>;
@@ -177,6 +207,15 @@ typedef Primitive<2> Primitive2D;
 typedef Primitive<3> Primitive3D;
 
 /* trajectory.h:42-57,250-254,277-292 */
+/* trajectory.h:19-35 */
+template <int Dim>
+struct Command {
+  Vecf<Dim> pos, vel, acc, jrk;
+  decimal_t yaw{0}, yaw_dot{0}, t{0};
+};
+typedef Command<2> Command2D;
+typedef Command<3> Command3D;
+
 template <int Dim>
 class Trajectory {
  public:
@@ -205,6 +244,38 @@ class Trajectory {
     ws.push_back(segs.back().evaluate(segs.back().t()));
     ws.back().t = t;
     return ws;
+  }
+  /* trajectory.h:95-135 without a time-scaling lambda (a planner's trajectory never carries one): position and its
+   * derivatives, yaw and yaw rate at `time`, clamped to [0, total time] */
+  bool evaluate(decimal_t time, Command<Dim> &p) const {
+    decimal_t tau = time;
+    if (tau < 0) tau = 0;
+    if (tau > total_t_) tau = total_t_;
+    for (size_t id = 0; id < segs.size(); id++) {
+      if (tau >= taus[id] && tau <= taus[id + 1]) {
+        tau -= taus[id];
+        const Waypoint<Dim> w = segs[id].evaluate(tau);
+        p.pos = w.pos; p.vel = w.vel; p.acc = w.acc; p.jrk = w.jrk;
+        const double *cy = segs[id].coeff_yaw();
+        decimal_t a = cy[4] * tau + cy[5];
+        while (a > M_PI) a -= 2.0 * M_PI;
+        while (a < -M_PI) a += 2.0 * M_PI;
+        p.yaw = a;
+        decimal_t b = cy[4];
+        while (b > M_PI) b -= 2.0 * M_PI;
+        while (b < -M_PI) b += 2.0 * M_PI;
+        p.yaw_dot = b;
+        p.t = time;
+        return true;
+      }
+    }
+    return false;
+  }
+  vec_E<Command<Dim>> sample(int N) const { /* trajectory.h:230-237 */
+    vec_E<Command<Dim>> ps(N + 1);
+    const decimal_t dt = total_t_ / N;
+    for (int i = 0; i <= N; i++) evaluate(i * dt, ps[i]);
+    return ps;
   }
   vec_E<Primitive<Dim>> segs;
   std::vector<decimal_t> taus;

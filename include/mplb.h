@@ -231,6 +231,33 @@ int mplb_sincos_cr(const double *x, int n, double *s, double *c);
  * the launch stream), launches = kernels launched, tiers = arena tiers used. Any pointer may be NULL. */
 int mplb_last_batch_stats(mplb_planner *p, double *kernel_ms, int32_t *launches, int32_t *tiers);
 
+/* ---- multi-GPU: one process per GPU, the batch sharded by query (query i -> rank i mod N), NCCL over NVLink.
+ * Exactly two collectives exist on this path: one broadcast of the voxel grid per map and one gather of result records
+ * (and action rows) per batch.  The caller distributes the 128-byte id of rank 0 to the other ranks by whatever means it
+ * has (a ROS parameter, a file, MPI, torch.distributed) — the only out-of-band step, like ncclGetUniqueId itself. */
+#define MPLB_COMM_ID_BYTES 128
+typedef struct mplb_comm mplb_comm;
+int mplb_comm_unique_id(uint8_t *id128);                                     /* rank 0: ncclGetUniqueId */
+int mplb_comm_create(const uint8_t *id128, int rank, int nranks, mplb_comm **out); /* every rank, current device: ncclCommInitRank */
+void mplb_comm_destroy(mplb_comm *c);
+int mplb_comm_rank(const mplb_comm *c);
+int mplb_comm_size(const mplb_comm *c);
+/* MapUtil::setMap on every rank from the root's host grid: ONE ncclBroadcast of the int8 cells (plus a 64-byte header);
+ * non-root ranks pass NULL for ndim / origin / data.  Every rank receives its own mplb_map. */
+int mplb_comm_broadcast_map(mplb_comm *c, int root, int dim, const int32_t *ndim, const double *origin, double res,
+                            const int8_t *data, mplb_map **out);
+/* plan_batch over all ranks.  Every rank passes the SAME full query list (host); rank r plans queries r, r + N, ...;
+ * the root receives results[n] (and actions[n * max_seg] when not NULL) in query order through one grouped
+ * ncclSend/ncclRecv gather.  The other ranks' result pointers may be NULL. */
+int mplb_plan_batch_sharded(mplb_planner *p, mplb_comm *c, const mplb_waypoint *starts, const mplb_waypoint *goals, int n,
+                            mplb_result *results, int32_t *actions, int max_seg, int root);
+/* Device-resident variant: this rank's stripe (n_local plans, device buffers sized for `per` = ceil(n / N) records) is
+ * planned and gathered into the root's internal gather buffer; mplb_comm_unstripe then copies the gathered batch to host
+ * buffers in query order (root only). */
+int mplb_plan_stripe_gather_device(mplb_planner *p, mplb_comm *c, const void *d_starts, const void *d_goals, int n_local, int per,
+                                   void *d_results, void *d_actions, int max_seg, int root, void *stream);
+int mplb_comm_unstripe(mplb_comm *c, int n, int per, int max_seg, mplb_result *results, int32_t *actions);
+
 #ifdef __cplusplus
 }
 #endif

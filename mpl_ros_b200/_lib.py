@@ -56,6 +56,15 @@ SYMBOLS = {
     "mplb_get_open": (_I, [_VP, _VP, _I]),
     "mplb_expand": (_I, [_VP, _VP, _I, _VP]),
     "mplb_last_batch_stats": (_I, [_VP, _VP, _VP, _VP]),
+    "mplb_comm_unique_id": (_I, [_VP]),
+    "mplb_comm_create": (_I, [_VP, _I, _I, _VP]),
+    "mplb_comm_destroy": (None, [_VP]),
+    "mplb_comm_rank": (_I, [_VP]),
+    "mplb_comm_size": (_I, [_VP]),
+    "mplb_comm_broadcast_map": (_I, [_VP, _I, _I, _VP, _VP, _D, _VP, _VP]),
+    "mplb_plan_batch_sharded": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _I]),
+    "mplb_plan_stripe_gather_device": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _I, _I, _VP]),
+    "mplb_comm_unstripe": (_I, [_VP, _I, _I, _I, _VP, _VP]),
     "mplb_sincos_cr": (_I, [_VP, _I, _VP, _VP]),
     "mplb_trajectory_msg_size": (C.c_size_t, [_I, C.c_char_p]),
     "mplb_serialize_trajectories_device": (_I, [_VP, _VP, _VP, _VP, _I, _I, _D, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,

@@ -6,6 +6,8 @@
  * and result getters.  All compute runs in the sm_100a kernels of mplb_search.cuh; there is no CPU path.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <atomic>
@@ -1620,6 +1622,225 @@ int mplb_last_batch_stats(mplb_planner *p, double *kernel_ms, int32_t *launches,
   if (kernel_ms) *kernel_ms = p->last_ms;
   if (launches) *launches = p->last_launches;
   if (tiers) *tiers = p->last_tiers;
+  return MPLB_OK;
+}
+
+
+/* ================================================================== multi-GPU: query sharding over NCCL
+ * One process per GPU.  The path shards by query and only by query, so there are exactly two collectives: one
+ * ncclBroadcast of the voxel grid per map and one grouped ncclSend/ncclRecv gather of fixed-stride result records (and
+ * action rows) per batch.  NCCL is bound at run time (dlopen of libnccl.so.2: the copy a host application such as PyTorch
+ * already loaded, else the system one), so libmplb.so itself has no link-time dependency on it. */
+namespace {
+struct NcclApi {
+  void *h = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+};
+NcclApi &nccl_api() {
+  static NcclApi a;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    a.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!a.h) a.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (a.h) {
+#define MPLB_NCCL_SYM(name) a.name = (decltype(a.name))dlsym(a.h, "nccl" #name)
+      MPLB_NCCL_SYM(GetUniqueId); MPLB_NCCL_SYM(CommInitRank); MPLB_NCCL_SYM(CommDestroy); MPLB_NCCL_SYM(Broadcast);
+      MPLB_NCCL_SYM(Send); MPLB_NCCL_SYM(Recv); MPLB_NCCL_SYM(GroupStart); MPLB_NCCL_SYM(GroupEnd); MPLB_NCCL_SYM(GetErrorString);
+#undef MPLB_NCCL_SYM
+      a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Broadcast && a.Send && a.Recv && a.GroupStart && a.GroupEnd;
+    }
+  }
+  return a;
+}
+#define NCCL_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    ncclResult_t r__ = (expr);                                                                           \
+    if (r__ != ncclSuccess)                                                                              \
+      return fail(MPLB_ERR_CUDA, std::string(#expr) + ": " + (N.GetErrorString ? N.GetErrorString(r__) : "nccl error")); \
+  } while (0)
+}  // namespace
+
+struct mplb_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1, device = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf<unsigned char> gres, gact, hdr; /* gather buffers on the root, header scratch */
+};
+
+int mplb_comm_unique_id(uint8_t *id128) {
+  if (!id128) return fail(MPLB_ERR_ARG, "null argument");
+  NcclApi &N = nccl_api();
+  if (!N.ok) return fail(MPLB_ERR_STATE, "libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  NCCL_TRY(N.GetUniqueId(&id));
+  static_assert(sizeof(id) == MPLB_COMM_ID_BYTES, "ncclUniqueId size");
+  std::memcpy(id128, &id, sizeof(id));
+  return MPLB_OK;
+}
+
+int mplb_comm_create(const uint8_t *id128, int rank, int nranks, mplb_comm **out) {
+  if (!id128 || !out || nranks < 1 || rank < 0 || rank >= nranks) return fail(MPLB_ERR_ARG, "bad communicator arguments");
+  NcclApi &N = nccl_api();
+  if (!N.ok) return fail(MPLB_ERR_STATE, "libnccl.so.2 could not be loaded");
+  mplb_comm *c = new mplb_comm();
+  c->rank = rank; c->nranks = nranks;
+  if (cudaGetDevice(&c->device) != cudaSuccess) { delete c; return fail(MPLB_ERR_CUDA, "no CUDA device (libmplb has no CPU path)"); }
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  ncclResult_t r = N.CommInitRank(&c->comm, nranks, id, rank);
+  if (r != ncclSuccess) { delete c; return fail(MPLB_ERR_CUDA, std::string("ncclCommInitRank: ") + (N.GetErrorString ? N.GetErrorString(r) : "")); }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { N.CommDestroy(c->comm); delete c; return fail(MPLB_ERR_CUDA, "cudaStreamCreate"); }
+  *out = c;
+  return MPLB_OK;
+}
+
+void mplb_comm_destroy(mplb_comm *c) {
+  if (!c) return;
+  NcclApi &N = nccl_api();
+  if (c->comm && N.ok) N.CommDestroy(c->comm);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  c->gres.release(); c->gact.release(); c->hdr.release();
+  delete c;
+}
+
+int mplb_comm_rank(const mplb_comm *c) { return c ? c->rank : -1; }
+int mplb_comm_size(const mplb_comm *c) { return c ? c->nranks : 0; }
+
+int mplb_comm_broadcast_map(mplb_comm *c, int root, int dim, const int32_t *ndim, const double *origin, double res,
+                            const int8_t *data, mplb_map **out) {
+  if (!c || !out || root < 0 || root >= c->nranks) return fail(MPLB_ERR_ARG, "bad argument");
+  NcclApi &N = nccl_api();
+  if (set_device_of(c->device)) return fail(MPLB_ERR_CUDA, "cannot select the communicator's device");
+  double h[8] = {0, 0, 0, 0, 0, 0, 0, 0}; /* dim, origin[3], ndim[3], res */
+  if (c->rank == root) {
+    if (!ndim || !origin || !data || (dim != 2 && dim != 3)) return fail(MPLB_ERR_ARG, "the root must supply the map");
+    h[0] = dim;
+    for (int i = 0; i < dim; i++) { h[1 + i] = origin[i]; h[4 + i] = ndim[i]; }
+    h[7] = res;
+  }
+  CUDA_TRY(c->hdr.reserve(sizeof(h)));
+  CUDA_TRY(cudaMemcpyAsync(c->hdr.p, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+  NCCL_TRY(N.Broadcast(c->hdr.p, c->hdr.p, sizeof(h), ncclUint8, root, c->comm, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(h, c->hdr.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const int d = (int)h[0];
+  int32_t nd[3] = {1, 1, 1};
+  double org[3] = {0, 0, 0};
+  for (int i = 0; i < d && i < 3; i++) { org[i] = h[1 + i]; nd[i] = (int32_t)h[4 + i]; }
+  mplb_map *m = nullptr;
+  int rc = map_alloc(d, nd, org, h[7], &m);
+  if (rc != MPLB_OK) return rc;
+  if (c->rank == root && cudaMemcpyAsync(m->d_grid, data, m->ncell, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+    mplb_map_destroy(m);
+    return fail(MPLB_ERR_CUDA, "cudaMemcpy(map)");
+  }
+  ncclResult_t r = N.Broadcast(m->d_grid, m->d_grid, m->ncell, ncclInt8, root, c->comm, c->stream); /* the one map collective */
+  if (r != ncclSuccess) { mplb_map_destroy(m); return fail(MPLB_ERR_CUDA, std::string("ncclBroadcast(map): ") + N.GetErrorString(r)); }
+  rc = m->rebuild_bricks(c->stream);
+  if (rc != MPLB_OK) { mplb_map_destroy(m); return rc; }
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  *out = m;
+  return MPLB_OK;
+}
+
+/* gather of this rank's `per` result records and action rows (device buffers) into the root's gather buffers:
+ * one ncclGroup of sends/receives */
+static int comm_gather(mplb_comm *c, const void *d_res, const void *d_act, int per, int max_seg, int root, cudaStream_t s) {
+  NcclApi &N = nccl_api();
+  const size_t rb = (size_t)per * sizeof(mplb_result), ab = (size_t)per * max_seg * sizeof(int);
+  if (c->rank == root) {
+    CUDA_TRY(c->gres.reserve(rb * c->nranks));
+    if (ab) CUDA_TRY(c->gact.reserve(ab * c->nranks));
+  }
+  if (c->nranks == 1) {
+    CUDA_TRY(cudaMemcpyAsync(c->gres.p, d_res, rb, cudaMemcpyDeviceToDevice, s));
+    if (ab) CUDA_TRY(cudaMemcpyAsync(c->gact.p, d_act, ab, cudaMemcpyDeviceToDevice, s));
+    return MPLB_OK;
+  }
+  NCCL_TRY(N.GroupStart());
+  if (c->rank == root) {
+    for (int r = 0; r < c->nranks; r++) {
+      if (r == root) continue;
+      NCCL_TRY(N.Recv(c->gres.p + rb * r, rb, ncclUint8, r, c->comm, s));
+      if (ab) NCCL_TRY(N.Recv(c->gact.p + ab * r, ab, ncclUint8, r, c->comm, s));
+    }
+  } else {
+    NCCL_TRY(N.Send(d_res, rb, ncclUint8, root, c->comm, s));
+    if (ab) NCCL_TRY(N.Send(d_act, ab, ncclUint8, root, c->comm, s));
+  }
+  NCCL_TRY(N.GroupEnd());
+  if (c->rank == root) {
+    CUDA_TRY(cudaMemcpyAsync(c->gres.p + rb * root, d_res, rb, cudaMemcpyDeviceToDevice, s));
+    if (ab) CUDA_TRY(cudaMemcpyAsync(c->gact.p + ab * root, d_act, ab, cudaMemcpyDeviceToDevice, s));
+  }
+  return MPLB_OK;
+}
+
+int mplb_plan_stripe_gather_device(mplb_planner *p, mplb_comm *c, const void *d_starts, const void *d_goals, int n_local, int per,
+                                   void *d_results, void *d_actions, int max_seg, int root, void *stream) {
+  if (!p || !c || !d_results || per < n_local) return fail(MPLB_ERR_ARG, "bad argument");
+  int rc = MPLB_OK;
+  if (n_local > 0) rc = mplb_plan_batch_device(p, d_starts, d_goals, n_local, d_results, d_actions, nullptr, max_seg, stream);
+  if (rc != MPLB_OK) return rc;
+  rc = comm_gather(c, d_results, max_seg > 0 ? d_actions : nullptr, per, max_seg > 0 ? max_seg : 0, root, (cudaStream_t)stream);
+  if (rc != MPLB_OK) return rc;
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return MPLB_OK;
+}
+
+int mplb_comm_unstripe(mplb_comm *c, int n, int per, int max_seg, mplb_result *results, int32_t *actions) {
+  if (!c || !results) return fail(MPLB_ERR_ARG, "bad argument");
+  if (set_device_of(c->device)) return fail(MPLB_ERR_CUDA, "cannot select the communicator's device");
+  const size_t rb = (size_t)per * sizeof(mplb_result), ab = (size_t)per * max_seg * sizeof(int);
+  if (c->gres.n < rb * c->nranks) return fail(MPLB_ERR_STATE, "no gathered batch on this rank");
+  std::vector<mplb_result> hr((size_t)per * c->nranks);
+  std::vector<int32_t> ha(actions && max_seg > 0 ? (size_t)per * c->nranks * max_seg : 0);
+  CUDA_TRY(cudaMemcpy(hr.data(), c->gres.p, rb * c->nranks, cudaMemcpyDeviceToHost));
+  if (!ha.empty()) CUDA_TRY(cudaMemcpy(ha.data(), c->gact.p, ab * c->nranks, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) { /* query i was planned by rank i mod N as its (i / N)-th plan */
+    const int r = i % c->nranks, k = i / c->nranks;
+    results[i] = hr[(size_t)r * per + k];
+    if (!ha.empty()) std::memcpy(actions + (size_t)i * max_seg, &ha[((size_t)r * per + k) * max_seg], (size_t)max_seg * sizeof(int32_t));
+  }
+  return MPLB_OK;
+}
+
+int mplb_plan_batch_sharded(mplb_planner *p, mplb_comm *c, const mplb_waypoint *starts, const mplb_waypoint *goals, int n,
+                            mplb_result *results, int32_t *actions, int max_seg, int root) {
+  if (!p || !c || !starts || !goals || n <= 0) return fail(MPLB_ERR_ARG, "bad argument");
+  if (c->rank == root && !results) return fail(MPLB_ERR_ARG, "the root needs a result buffer");
+  if (actions && max_seg <= 0) return fail(MPLB_ERR_ARG, "max_seg must be > 0 when trajectories are requested");
+  if (p->device != c->device) return fail(MPLB_ERR_ARG, "planner and communicator live on different devices");
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  const int N = c->nranks, per = (n + N - 1) / N;
+  std::vector<mplb_waypoint> ls, lg;
+  for (int i = c->rank; i < n; i += N) { ls.push_back(starts[i]); lg.push_back(goals[i]); }
+  const int n_loc = (int)ls.size();
+  const int ms = actions || c->rank != root ? max_seg : 0;
+  CUDA_TRY(p->d_starts.reserve(std::max(per, 1)));
+  CUDA_TRY(p->d_goals.reserve(std::max(per, 1)));
+  CUDA_TRY(p->d_results.reserve(std::max(per, 1)));
+  if (ms > 0) CUDA_TRY(p->d_actions.reserve((size_t)per * ms));
+  CUDA_TRY(cudaMemsetAsync(p->d_results.p, 0, (size_t)per * sizeof(mplb_result), c->stream));
+  if (n_loc > 0) {
+    CUDA_TRY(cudaMemcpyAsync(p->d_starts.p, ls.data(), (size_t)n_loc * sizeof(mplb_waypoint), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_goals.p, lg.data(), (size_t)n_loc * sizeof(mplb_waypoint), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
+  int rc = mplb_plan_stripe_gather_device(p, c, p->d_starts.p, p->d_goals.p, n_loc, per, p->d_results.p, ms > 0 ? p->d_actions.p : nullptr,
+                                          ms, root, c->stream);
+  if (rc != MPLB_OK) return rc;
+  if (c->rank == root) return mplb_comm_unstripe(c, n, per, actions ? max_seg : 0, results, actions);
   return MPLB_OK;
 }
 

@@ -253,6 +253,11 @@ struct PlanSmem {
   int pf_node;
   unsigned long long pf_k0, pf_k1;
   double pf_st[NS];
+#ifdef MPLB_BULK_ROW
+  alignas(16) unsigned char pf_row[(sizeof(RowHdr) + NS * sizeof(double) + 15) & ~15];
+  unsigned long long pf_bar; /* mbarrier of the bulk row copy */
+  unsigned pf_phase;
+#endif
   int n_nodes, n_heap, tsize, pops, n_closed, status, plan_idx;
   long long n_samples, n_valid;
   unsigned long long t_start; /* %globaltimer when this CTA picked the plan up */
@@ -1088,6 +1093,13 @@ astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Bat
 
   /* ---------------- per-launch constants */
   if (tid == 0) S.hcap = SM::DYN_HEAP ? a.hcap : SM::HCAP;
+#ifdef MPLB_BULK_ROW
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&S.pf_bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    S.pf_phase = 0;
+  }
+#endif
   for (int i = tid; i < c.nU * 3; i += MPLB_NT) { S.U[i] = c.U[i]; S.Ut[i] = Axis<ORD>::top_of(c.U[i]); }
   if (POT) for (int i = tid; i < c.nU; i += MPLB_NT) S.Uyaw[i] = (c.use_yaw && c.Uyaw) ? c.Uyaw[i] : 0.0;
   for (int i = tid; i < c.nU; i += MPLB_NT) {
@@ -1263,10 +1275,34 @@ astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Bat
           if (S.n_heap > 0) {
             pf = H.hn()[0] & 0x7fffffff;
             const RowHdr *rh = reinterpret_cast<const RowHdr *>(rows + (size_t)pf * ROWB);
+#ifdef MPLB_BULK_ROW
+            /* A/B variant (profiles/r02_tma_ab.md): the whole state row (header + state, ROWB contiguous 16-byte aligned
+             * bytes) arrives with ONE bulk asynchronous copy (TMA engine, cp.async.bulk) completing on an mbarrier, instead
+             * of 3 + NS scalar loads. */
+            {
+              const unsigned bar = (unsigned)__cvta_generic_to_shared(&S.pf_bar);
+              const unsigned dst = (unsigned)__cvta_generic_to_shared(S.pf_row);
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)ROWB) : "memory");
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(rh),
+                           "r"((unsigned)ROWB), "r"(bar)
+                           : "memory");
+              unsigned done = 0;
+              while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(S.pf_phase) : "memory");
+              S.pf_phase ^= 1u;
+              const RowHdr *sh = reinterpret_cast<const RowHdr *>(S.pf_row);
+              S.pf_k0 = sh->k0; S.pf_k1 = sh->k1; S.pf_depth = sh->depth;
+              const double *ss = reinterpret_cast<const double *>(S.pf_row + sizeof(RowHdr));
+#pragma unroll
+              for (int f = 0; f < NS; f++) S.pf_st[f] = ss[f];
+            }
+#else
             S.pf_k0 = __ldcg(&rh->k0); S.pf_k1 = __ldcg(&rh->k1); S.pf_depth = __ldcg(&rh->depth);
             const double *rs = reinterpret_cast<const double *>(rows + (size_t)pf * ROWB + sizeof(RowHdr));
 #pragma unroll
             for (int f = 0; f < NS; f++) S.pf_st[f] = __ldcg(&rs[f]);
+#endif
           }
           S.pf_node = pf;
         }

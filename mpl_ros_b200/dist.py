@@ -86,18 +86,81 @@ def gather_results(local_results, local_actions, n_total, max_seg, device, dst=0
     return results, actions
 
 
+class Comm:
+    """libmplb's own NCCL communicator (include/mplb.h, mplb_comm_*): the map broadcast and the result gather of the
+    sharded batch run inside the C ABI, so a C++ caller without Python gets the same path.  The 128-byte id of rank 0
+    has to reach the other ranks out of band (here: torch.distributed, a file, an environment variable ...)."""
+
+    def __init__(self, id_bytes, rank, nranks):
+        import ctypes as C
+        h = C.c_void_p()
+        buf = np.frombuffer(bytes(id_bytes), dtype=np.uint8).copy()
+        _lib.check(_lib.lib().mplb_comm_create(_lib.ptr(buf), int(rank), int(nranks), C.byref(h)))
+        self._h, self.rank, self.size = h, int(rank), int(nranks)
+
+    @staticmethod
+    def unique_id():
+        buf = np.zeros(128, dtype=np.uint8)
+        _lib.check(_lib.lib().mplb_comm_unique_id(_lib.ptr(buf)))
+        return buf.tobytes()
+
+    @classmethod
+    def from_process_group(cls, device):
+        """Rank 0 creates the id, the default torch.distributed group carries it to the others (set-up plumbing only)."""
+        rank, world = _rank_world()
+        t = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        if world > 1:
+            dist.broadcast(t, 0)
+        return cls(t.cpu().numpy().tobytes(), rank, world)
+
+    def broadcast_map(self, dim, origin=None, ndim=None, res=0.0, data=None, root=0):
+        """One ncclBroadcast of the grid: returns a planner.MapUtil on this rank's device."""
+        import ctypes as C
+        from .planner import MapUtil
+        h = C.c_void_p()
+        if self.rank == root:
+            o = np.ascontiguousarray(origin, dtype=np.float64)
+            nd = np.ascontiguousarray(ndim, dtype=np.int32)
+            dt = np.ascontiguousarray(data, dtype=np.int8).reshape(-1)
+            _lib.check(_lib.lib().mplb_comm_broadcast_map(self._h, root, int(dim), _lib.ptr(nd), _lib.ptr(o), float(res), _lib.ptr(dt),
+                                                        C.byref(h)))
+        else:
+            _lib.check(_lib.lib().mplb_comm_broadcast_map(self._h, root, 0, None, None, 0.0, None, C.byref(h)))
+        mu = MapUtil(0)
+        mu._h = h
+        mu.dim = len(mu._info_raw()[0])
+        return mu
+
+    def __del__(self):
+        try:
+            _lib.lib().mplb_comm_destroy(self._h)
+        except Exception:
+            pass
+
+
 class ShardedBatchPlanner:
-    """plan_batch over all ranks of the default process group.
+    """plan_batch over all ranks.
 
-    `make_planner(origin, dim, res, grid_tensor)` builds this rank's planner on its device from the broadcast
-    grid (on GPU: MapUtil.setMapFromDevice + MapPlanner; the CPU tests pass a stand-in)."""
+    Without `comm`: torch.distributed collectives (works on gloo for the CPU tests); `make_planner(origin, dim, res,
+    grid_tensor)` builds this rank's planner on its device from the broadcast grid.
+    With `comm` (a dist.Comm): the broadcast and the gather run inside libmplb (mplb_comm_broadcast_map,
+    mplb_plan_batch_sharded, mplb_plan_stripe_gather_device); `make_planner(origin, dim, res, map_util)` then receives the
+    ready planner.MapUtil instead of a tensor."""
 
-    def __init__(self, make_planner, device):
+    def __init__(self, make_planner, device, comm=None):
         self.make_planner = make_planner
         self.device = device
         self.planner = None
+        self.comm = comm
 
     def set_map(self, origin=None, dim=None, res=None, data=None, src=0):
+        if self.comm is not None:
+            mu = self.comm.broadcast_map(len(dim) if dim is not None else 0, origin, dim, res if res is not None else 0.0, data, src)
+            d, o, r = mu._info()
+            self.planner = self.make_planner(o, d, r, mu)
+            return o, d, r
         o, d, r, grid = broadcast_map(origin, dim, res, data, self.device, src)
         self._grid = grid  # keep the receive buffer alive until the planner has copied it
         self.planner = self.make_planner(o, d, r, grid)
@@ -158,6 +221,14 @@ class ShardedBatchPlanner:
         """This rank's stripe (device tensors of waypoint records) through mplb_plan_batch_device, then the one gather of
         result records and action rows on `dst`."""
         rank, world = _rank_world()
+        if self.comm is not None:
+            import ctypes as C
+            vp = lambda x: C.c_void_p(int(x)) if x else None  # noqa: E731
+            _lib.check(_lib.lib().mplb_plan_stripe_gather_device(
+                self.planner._h, self.comm._h, vp(d_starts.data_ptr()), vp(d_goals.data_ptr()), n_local, bufs["res"].shape[0],
+                vp(bufs["res"].data_ptr()), vp(bufs["act"].data_ptr() if max_seg else 0), max_seg, dst,
+                vp(stream.cuda_stream if stream is not None else 0)))
+            return
         self.planner.plan_batch_device(d_starts.data_ptr(), d_goals.data_ptr(), n_local, bufs["res"].data_ptr(),
                                        bufs["act"].data_ptr() if max_seg else 0, 0, max_seg,
                                        stream.cuda_stream if stream is not None else 0)
@@ -170,6 +241,10 @@ class ShardedBatchPlanner:
         rank, world = _rank_world()
         results = np.zeros(n_total, dtype=_lib.RESULT_DTYPE)
         actions = np.full((n_total, max_seg), -1, dtype=np.int32)
+        if self.comm is not None:
+            _lib.check(_lib.lib().mplb_comm_unstripe(self.comm._h, n_total, bufs["res"].shape[0], max_seg, _lib.ptr(results),
+                                                   _lib.ptr(actions) if max_seg else None))
+            return results, actions
         parts = zip(bufs["gres"], bufs["gact"]) if world > 1 else [(bufs["res"], bufs["act"])]
         for r, (tr, ta) in enumerate(parts):
             idx = shard_indices(n_total, r, world)
@@ -186,6 +261,13 @@ class ShardedBatchPlanner:
     def plan_batch(self, starts, goals, max_seg=64, dst=0):
         """starts/goals: full arrays on every rank (host, WAYPOINT_DTYPE). Each rank plans its stripe."""
         rank, world = _rank_world()
+        if self.comm is not None:
+            n = len(starts)
+            res = np.zeros(n, dtype=_lib.RESULT_DTYPE) if rank == dst else None
+            acts = np.full((n, max_seg), -1, dtype=np.int32) if (rank == dst and max_seg) else None
+            _lib.check(_lib.lib().mplb_plan_batch_sharded(self.planner._h, self.comm._h, _lib.ptr(starts), _lib.ptr(goals), n,
+                                                        _lib.ptr(res), _lib.ptr(acts), max_seg, dst))
+            return res, acts
         idx = shard_indices(len(starts), rank, world)
         res, acts, _ = self.planner.plan_batch(np.ascontiguousarray(starts[idx]), np.ascontiguousarray(goals[idx]),
                                                max_seg=max_seg)

@@ -161,6 +161,14 @@ class MapUtil:
         ns = np.ascontiguousarray(ns, dtype=np.int32).reshape(-1, self.dim)
         check(lib().mplb_map_dilate(self._h, ptr(ns), ns.shape[0]))
 
+    def _info_raw(self):
+        d = C.c_int32()
+        nd = np.zeros(3, dtype=np.int32)
+        ori = np.zeros(3, dtype=np.float64)
+        res = C.c_double()
+        check(lib().mplb_map_get_info(self._h, C.byref(d), ptr(nd), ptr(ori), C.byref(res)))
+        return nd[:d.value].copy(), ori[:d.value].copy(), res.value
+
     def _info(self):
         d = C.c_int32()
         nd = np.zeros(3, dtype=np.int32)

@@ -23,17 +23,28 @@ from mpl_ros_b200 import _lib  # noqa: E402
 _lib.LIB_PATH = out
 import mpl_ros_b200 as mp  # noqa: E402
 from mpl_ros_b200 import maps  # noqa: E402
-import bench  # noqa: E402
+from mpl_ros_b200 import workloads as W  # noqa: E402
 
-m = maps.levine256()
+# usage: phase_timing.py [max_slots] [--c5 N_QUERIES]  (default: the first 1024 queries of the C2 list)
+c5 = "--c5" in sys.argv
+spec = W.C5 if c5 else W.C2
+nq = int(sys.argv[sys.argv.index("--c5") + 1]) if c5 else 1024
+m = W.c5_map() if c5 else W.c2_map()
 mu = mp.VoxelMapUtil(); mu.setMap(m.origin, m.dim, m.data, m.res); mu.freeUnknown()
 pl = mp.VoxelMapPlanner(False); pl.setMapUtil(mu)
-pl.setVmax(2.0); pl.setAmax(1.0); pl.setDt(1.0); pl.setU(maps.make_U(1.0, 1, 3)); pl.setTol(0.5)
-s, g = bench.make_queries(m, 0)
+P = spec["params"]
+pl.setVmax(P["v_max"]); pl.setAmax(P["a_max"]); pl.setDt(P["dt"]); pl.setU(W.controls(spec)); pl.setTol(P["tol_pos"])
+if "max_num" in P:
+    pl.setMaxNum(int(os.environ.get("MPLB_MAX_NUM", P["max_num"])))
+if c5:
+    pl.setMemFraction(0.85)
+S, G = (W.c5_queries if c5 else W.c2_queries)(m, nq)
+s, g = mp.waypoints_array(nq), mp.waypoints_array(nq)
+W.fill(s, g, S, G, spec["control"])
 if len(sys.argv) > 1 and sys.argv[1].isdigit():
     pl.setMaxSlots(int(sys.argv[1]))
     print('max_slots', sys.argv[1])
-for _ in range(2):
+for _ in range(1 if c5 else 2):
     res, _, _ = pl.plan_batch(s, g, max_seg=64)
 print("kernel_ms", pl.last_batch_stats())
 ph16 = np.zeros((len(s), 16), dtype=np.int64)
