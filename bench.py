@@ -293,12 +293,12 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    # stdout carries the one JSON line: NCCL's own log (NCCL_DEBUG as the caller set it; libmplb's communicator initialises
+    # NCCL at every world size) goes to a file unless the caller already chose one
+    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl.bench.%h.%p.log")
     if world > 1:
-        # stdout carries the one JSON line: NCCL's own log (NCCL_DEBUG as the caller set it) goes to a file unless the
-        # caller already chose one
-        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl.bench.%h.%p.log")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 

@@ -894,6 +894,7 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
     DISPATCH(c.dim, c.ord, c.nU, LAUNCH_CALL);
     if (rc != MPLB_OK) return rc;
     p->last_launches++; p->last_tiers++;
+    const int slots_total_this_tier = n_work;
     int n_over = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_over, p->d_ctrl.p + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -907,7 +908,10 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
     n_work = n_over;
     identity = false;
     if (cap >= cap_bound || cap > (1 << 27)) { cap = 1 << 30; continue; } /* beyond every budget: the next pass reports NOMEM */
-    cap = (int)std::min<long long>((long long)cap * 8, cap_bound);
+    /* with a MaxExpandStep bound and most plans of this tier overflowing (a search that does not terminate early, like the
+     * jerk lattice of BASELINE configs[4]) the remaining tiers would only repeat work: go straight to the bound */
+    if (c.max_num > 0 && 2 * n_over > slots_total_this_tier) cap = (int)cap_bound;
+    else cap = (int)std::min<long long>((long long)cap * 8, cap_bound);
   }
   CUDA_TRY(cudaEventRecord(p->ev1, s));
   CUDA_TRY(cudaEventSynchronize(p->ev1));

@@ -19,12 +19,16 @@
 namespace mplb {
 
 #ifndef MPLB_NT
-#define MPLB_NT 224   /* threads per CTA: one CTA owns one plan (warp 0 search, warps 1..NW-2 sampling, last warp heap) */
+#define MPLB_NT 160   /* threads per CTA: one CTA owns one plan (warp 0 search, warps 1..NW-2 sampling, last warp heap) */
 #endif
 #define MPLB_MAXU 128 /* max |U| */
 #ifndef MPLB_MIN_CTAS
-#define MPLB_MIN_CTAS 4 /* resident CTAs per SM the search kernel is compiled for.  Measured on the 65 536-query bench list (r02 sweep,
-                           prim/s x 1e9): 256 x 3 2.41, 224 x 4 2.74, 192 x 5 2.60, 256 x 4 2.62; a 1024-query batch is tail bound and flat */
+#define MPLB_MIN_CTAS 6 /* resident CTAs per SM the plain |U| <= 32 search kernel is compiled for.  Measured on the 65 536-query bench
+                           list (profiles/r02_cta_shape_sweep.md, prim/s x 1e9, threads x CTAs/SM): 256x3 2.41, 224x4 2.72, 192x5 2.60,
+                           256x4 2.62, 160x6 2.92, 128x8 2.78; with a 1-slot probe window 224x4 2.88, 192x5 2.77, 160x6 3.07,
+                           128x8 2.99.  More, smaller plans per SM hide the per-pop latency chain better than more sampling warps
+                           per plan once the batch is deep enough to keep every slot busy (a 1024-query batch is tail bound and
+                           prefers 256x3: 1.62 vs 1.29 for 192x5). */
 #endif
 
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }

@@ -51,7 +51,8 @@ namespace mplb {
 #define MPLB_R 1 /* collision granules in flight per sampling thread: 1 -> 10.2k, 2 -> 10.9k, 4 -> 12.2k cycles per pop */
 #endif
 #ifndef MPLB_WIN
-#define MPLB_WIN 2 /* table slots fetched per probe: 2 -> 9.9k, 4 -> 10.9k cycles per pop (load factor <= 1/4) */
+#define MPLB_WIN 1 /* table slots fetched per probe (load factor <= 1/4): r01 at 3 CTAs/SM 2 -> 9.9k, 4 -> 10.9k cycles per pop; r02 at
+                      4-6 CTAs/SM one slot wins (+5 %): the second slot is bandwidth and registers for a 1-in-8 case */
 #endif
 #ifndef MPLB_LOAD_INV
 #define MPLB_LOAD_INV 4 /* table load factor bound 1/4 */
@@ -60,7 +61,7 @@ namespace mplb {
 #define MPLB_TINIT 1024 /* initial table slots (<= smallest tsize_max the host allocates) */
 #endif
 #ifndef MPLB_HCAP
-#define MPLB_HCAP 1536 /* heap entries kept in shared memory (|U| <= 32 instantiations) */
+#define MPLB_HCAP 512 /* heap entries kept in shared memory (|U| <= 32 instantiations): 6 CTAs of 160 threads per SM need <= 37 KB each */
 #endif
 #define MPLB_HCAP_SMALL 1024 /* shared-memory heap entries of the |U| > 32 instantiations when several plans share an SM */
 #ifndef MPLB_B1_INLINE
@@ -222,6 +223,10 @@ struct PlanSmem {
   unsigned long long ac_bar; /* mbarrier of the bulk-copy variant (MPLB_BULK_PREFETCH) */
   int ac_lo[32], ac_off[32], ac_cnt[32]; /* per level l >= 1: first cached position, offset in ac[], count */
   int ac_valid;
+  /* pushes of one 32-control batch, in control order (block-parallel push, see push_batch_blocks) */
+  static constexpr int QCAP = DYN_HEAP ? 32 : 1;
+  double q_f[QCAP], q_g[QCAP];
+  int q_n[QCAP], q_defer[QCAP];
   /* current node */
   double cur[NS];
   unsigned long long cur_k0, cur_k1; /* packed lattice key of the current node */
@@ -322,7 +327,8 @@ struct HeapView {
     __syncwarp();
   }
   /* ---- |U| > 32: ancestor cache (see PlanSmem::ac).  Called by one full warp. */
-  __device__ __noinline__ void cache_ancestors(int n0, int K, int lane) const {
+  /* (forceinline on purpose: a HeapView whose address escapes into a call turns every shared-memory access generic) */
+  __device__ __forceinline__ void cache_ancestors(int n0, int K, int lane) const {
     const int hc = hcap();
     int lo = 0, cnt = 0;
     if (lane >= 1) { /* lane l prepares level l: ancestors at distance l of the positions [n0, n0 + K) */
@@ -408,10 +414,57 @@ struct HeapView {
     if (lane == 0) cset((p1 >> stop) - 1, stop, f, g, n);
     __syncwarp();
   }
+  /* ---- |U| > 32: R new heap entries (S.q_f/q_g/q_n, control order) pushed at positions n0 .. n0 + R - 1, same result as R
+   * sequential pushes, most of them done in parallel.
+   * Positions whose (pos + 1) >> G agree form a block: they share their ancestors from distance G upwards, and the
+   * ancestors at distances 1 .. G of a block are ancestors of no other block ("private").  A push that comes to rest after
+   * examining only private ancestors (it moves up fewer than G levels) commutes with every push of another block, so one
+   * lane per block runs its block's pushes one after another while the other lanes do the same for theirs (pass 1).  A push
+   * that would have to look beyond distance G, and everything after it in its block, is deferred; pass 2 executes the
+   * deferred pushes in control order with the warp-cooperative sift-up.  Measured on the |U| = 125 workload 58 % of the
+   * pushes do not move at all and 6 % move 3 levels or more. */
+  __device__ __forceinline__ void push_batch_blocks(int n0, int R, int lane) const {
+    constexpr int G = 3;
+    const int b0 = (n0 + 1) >> G;
+    const int bid = b0 + lane;
+    int r_lo = (bid << G) - (n0 + 1), r_hi = ((bid + 1) << G) - (n0 + 1);
+    if (r_lo < 0) r_lo = 0;
+    if (r_hi > R) r_hi = R;
+    int defer_from = r_hi;
+    for (int r = r_lo; r < r_hi; r++) {
+      const int p1 = n0 + r + 1;
+      const double f = S.q_f[r], g = S.q_g[r];
+      const int n = S.q_n[r];
+      double af[G], ag[G];
+      int an[G];
+      int s = 0;
+      bool beyond = false;
+#pragma unroll
+      for (int d = 1; d <= G; d++) { /* examine the ancestors at distances 1 .. G while they are strictly worse */
+        if (s == d - 1 && !beyond) {
+          cget((p1 >> d) - 1, d, af[d - 1], ag[d - 1], an[d - 1]);
+          if (heap_worse(af[d - 1], ag[d - 1], f, g)) { s = d; if (d == G) beyond = true; }
+        }
+      }
+      if (beyond) { defer_from = r; break; } /* it would have to examine distance G + 1: nothing was written yet */
+#pragma unroll
+      for (int d = 1; d <= G; d++) /* ancestors 1 .. s move down one level each */
+        if (d <= s) cset((p1 >> (d - 1)) - 1, d - 1, af[d - 1], ag[d - 1], an[d - 1]);
+      cset((p1 >> s) - 1, s, f, g, n);
+    }
+    S.q_defer[lane] = defer_from;
+    __syncwarp();
+    for (int r = 0; r < R; r++) { /* pass 2: the deferred pushes, in control order */
+      const int k = ((n0 + r + 1) >> G) - b0;
+      if (r >= S.q_defer[k]) sift_up_warp_cached(n0 + r, S.q_f[r], S.q_g[r], S.q_n[r], lane);
+    }
+    __syncwarp();
+  }
+
   /* pop by one full warp: the levels inside shared memory are walked as before; below them every round fetches the
    * 4-level subtree under the current position (30 entries, one per lane, ONE round trip) and walks it with shuffles.
    * Same comparisons in the same order as sift_down => same heap. */
-  __device__ __noinline__ void sift_down_warp(int n_heap, double f, double g, int n, int lane) const {
+  __device__ __forceinline__ void sift_down_warp(int n_heap, double f, double g, int n, int lane) const {
     int pos = 0;
     const int hc = hcap();
     bool done = false;
@@ -1487,6 +1540,17 @@ astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Bat
           MPLB_TICK(4);
           /* heap operations in control order (gs:129-141) */
           unsigned hm = __ballot_sync(0xffffffffu, isnew || improve);
+          if (SM::DYN_HEAP && hm != 0u && hm == newm && S.n_heap >= H.hcap()) {
+            /* deep heap and nothing but first-time pushes in this batch: block-parallel (see push_batch_blocks) */
+            const int n0 = S.n_heap, R = __popc(hm);
+            if (isnew) { const int r = __popc(newm & lt_mask); S.q_f[r] = f; S.q_g[r] = tentative; S.q_n[r] = nid; }
+            __syncwarp();
+            if (!S.ac_valid) H.cache_ancestors(n0, c.nU, lane);
+            H.push_batch_blocks(n0, R, lane);
+            if (lane == 0) S.n_heap = n0 + R;
+            __syncwarp();
+            hm = 0u;
+          }
           while (hm) {
             const int j = __ffs(hm) - 1;
             hm &= hm - 1;
@@ -1509,8 +1573,17 @@ astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Bat
               const int np = S.n_heap;
               __syncwarp();
               if (SM::DYN_HEAP && np >= H.hcap()) { /* deep heap: ancestors of this pop's pushes come from the shared-memory cache */
+#ifdef MPLB_PHASE_TIMING
+                long long tq0 = clock64();
+#endif
                 if (!S.ac_valid) H.cache_ancestors(np, c.nU, lane);
+#ifdef MPLB_PHASE_TIMING
+                long long tq1 = clock64();
+#endif
                 H.sift_up_warp_cached(np, jf, jg, tag, lane);
+#ifdef MPLB_PHASE_TIMING
+                if (lane == 0) { MPLB_COUNT(5, tq1 - tq0); MPLB_COUNT(6, clock64() - tq1); MPLB_COUNT(7, 1); }
+#endif
               } else
               H.sift_up_warp(np, jf, jg, tag, lane);
               if (lane == 0) S.n_heap = np + 1;

@@ -44,21 +44,24 @@ def _run(name, tmp_path):
     if not os.path.exists(exe):
         pytest.skip("tests/cpp/_refbin/%s was not built (needs /root/reference at build time)" % name)
     out = subprocess.check_output([exe, _corridor_bin(tmp_path)], cwd=str(tmp_path), stderr=subprocess.STDOUT, timeout=300).decode()
-    return out, [int(x) for x in re.findall(r"expanded states: (\d+)", out)]
+    return out, [int(x) for x in re.findall(r"expanded states: (\d+)", out)], [int(x) for x in re.findall(r"Expand \[(\d+)\] nodes", out)]
 
 
-# closed-set sizes the oracle (validated against the reference's sources) gives for each flow, in print order
-EXPECTED = {
-    "test_planner_2d": [615],
-}
+# what the runs must print: closed-set sizes ("expanded states", the reference's own printf) and pops per plan ("Expand [n]
+# nodes!", the planner's verbose line, graph_search.h:168) — MPL/README.md:200 for test_planner_2d, the oracle's answers for the
+# distance-map flow (tests/test_oracle_shaping.py: 2732 expansions), both pinned against the reference's sources
+EXPECTED_STATES = {"test_planner_2d": [615], "test_distance_map_planner_2d": [615, 2732]}
+EXPECTED_FIRST_POPS = {"test_planner_2d": 615, "test_distance_map_planner_2d": 615, "test_distance_map_planner_2d_iterative": 2732}  # the iterative test keeps its plain planner quiet: the first verbose plan is the shaped one
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", brt.TESTS)
 def test_reference_test_runs_on_gpu(name, tmp_path):
-    out, counts = _run(name, tmp_path)
-    assert counts, out
+    out, counts, pops = _run(name, tmp_path)
+    assert pops, out  # every test plans at least once with a verbose planner
     assert "[stand-in drawing]" in out  # the run reached its plotting section, i.e. every planner call returned
-    if name in EXPECTED:
-        assert counts == EXPECTED[name], out
-    print(name, counts)
+    if name in EXPECTED_STATES:
+        assert counts == EXPECTED_STATES[name], out
+    if name in EXPECTED_FIRST_POPS:
+        assert pops[0] == EXPECTED_FIRST_POPS[name], out
+    print(name, counts, pops)
