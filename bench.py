@@ -397,12 +397,30 @@ def main():
         for f in ("status", "pops", "n_nodes", "pop_hash", "closed_hash", "n_seg"):
             assert np.array_equal(res_h[f], res_all[f]), "host-API results differ from device-API results: " + f
 
+    # ---- secondary, N > 1 only: weak scaling — every rank plans the WHOLE list (65 536 plans per GPU, the launch size of the
+    # N = 1 line), no gather; reported beside the strong-scaling headline as config.weak_scaling
+    weak_ms = 0.0
+    if world > 1 and args.workload == "c2":
+        dsa = torch.from_numpy(s_all.view(np.uint8).reshape(nq, -1)).to(dev)
+        dga = torch.from_numpy(g_all.view(np.uint8).reshape(nq, -1)).to(dev)
+        wres = torch.zeros(nq, _lib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        for _ in range(1):
+            pl.plan_batch_device(dsa.data_ptr(), dga.data_ptr(), nq, wres.data_ptr(), 0, 0, 0, stream.cuda_stream)
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(stream)
+        for _ in range(2):
+            pl.plan_batch_device(dsa.data_ptr(), dga.data_ptr(), nq, wres.data_ptr(), 0, 0, 0, stream.cuda_stream)
+        w1.record(stream)
+        barrier()
+        weak_ms = w0.elapsed_time(w1) / 2
+
     # ---- multi-GPU: max over ranks of the timed region
-    tot = np.array([total_ms, e2e_ms, float(np.mean(kernel_ms))])
+    tot = np.array([total_ms, e2e_ms, float(np.mean(kernel_ms)), weak_ms])
     if dist is not None:
         t = torch.tensor(tot, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms, kms_max = (float(x) for x in t.cpu().numpy())
+        total_ms, e2e_ms, kms_max, weak_ms = (float(x) for x in t.cpu().numpy())
     else:
         kms_max = float(np.mean(kernel_ms))
     if rank != 0:
@@ -449,6 +467,9 @@ def main():
            "success_rate": float(ok.mean()), "unreachable_rate": float((res_all["status"] == 3).mean()),
            "max_expand_rate": float((res_all["status"] == 2).mean()),
            "mean_samples_per_prim": s_mean, "p_valid": p_valid, "e2e_steps": e2e_steps}
+    if weak_ms > 0:
+        cfg["weak_scaling"] = {"what": "every rank plans the whole %d-query list (the N = 1 launch size), no gather; max over ranks" % nq,
+                               "value": world * prims_all / (weak_ms * 1e-3), "unit": "prim_exp/s", "ms_per_step": weak_ms, "steps": 2}
     line = {
         "metric": "primitive_expansions_per_sec", "value": value, "unit": "prim_exp/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,

@@ -64,6 +64,12 @@ namespace mplb {
 #define MPLB_HCAP 512 /* heap entries kept in shared memory (|U| <= 32 instantiations): 6 CTAs of 160 threads per SM need <= 37 KB each */
 #endif
 #define MPLB_HCAP_SMALL 1024 /* shared-memory heap entries of the |U| > 32 instantiations when several plans share an SM */
+/* The ancestor ranges of the deep-heap pushes are fetched with the bulk asynchronous copy engine (cp.async.bulk + mbarrier,
+ * UBLKCP / SYNCS in SASS): one copy per tree level, <= 23 per pop.  -DMPLB_NO_BULK_PREFETCH selects the 8-byte cp.async
+ * (LDGSTS) variant; the two measure within 1.3 % of each other on the |U| = 125 workload (profiles/r02_tma_ab.md). */
+#if !defined(MPLB_NO_BULK_PREFETCH) && !defined(MPLB_BULK_PREFETCH)
+#define MPLB_BULK_PREFETCH 1
+#endif
 #ifndef MPLB_B1_INLINE
 #define MPLB_B1_INLINE __forceinline__ /* __noinline__ costs ~2k cycles per pop */
 #endif
@@ -365,6 +371,7 @@ struct HeapView {
       unsigned done = 0;
       while (!done)
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+      __syncwarp(); /* nobody polls the barrier any more */
       if (lane == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 #else
       for (int l = 1; l < 32; l++) { /* 8-byte asynchronous copies (LDGSTS), all levels in flight together */
