@@ -155,6 +155,10 @@ class ShardedBatchPlanner:
         self.planner = None
         self.comm = comm
 
+    def _rw(self):
+        """(rank, world): the communicator's when one is attached, else the default torch.distributed group's"""
+        return (self.comm.rank, self.comm.size) if self.comm is not None else _rank_world()
+
     def set_map(self, origin=None, dim=None, res=None, data=None, src=0):
         if self.comm is not None:
             mu = self.comm.broadcast_map(len(dim) if dim is not None else 0, origin, dim, res if res is not None else 0.0, data, src)
@@ -171,7 +175,7 @@ class ShardedBatchPlanner:
         per cell, env_base::set_search_region) on every rank's planner: rank `src` supplies them (e.g. the map its own
         planner rewrote with updatePotentialMap), the others receive them with one broadcast each.  None on `src`
         clears that piece everywhere."""
-        rank, world = _rank_world()
+        rank, world = self._rw()
         flags = torch.zeros(2, dtype=torch.int64, device=self.device)
         if rank == src:
             flags[0] = 0 if potential is None else int(np.asarray(potential).size)
@@ -194,7 +198,7 @@ class ShardedBatchPlanner:
 
     def broadcast_queries(self, starts, goals, src=0):
         """Rank `src` holds the query list; every rank returns it (one broadcast of the two waypoint arrays)."""
-        rank, world = _rank_world()
+        rank, world = self._rw()
         if world == 1:
             return starts, goals
         n = len(starts)
@@ -208,7 +212,7 @@ class ShardedBatchPlanner:
 
     # ---- device-resident stripes (inputs and outputs stay in HBM; the gather moves device buffers)
     def make_device_buffers(self, n_total, max_seg, dst=0):
-        rank, world = _rank_world()
+        rank, world = self._rw()
         per = (n_total + world - 1) // world
         b = {"res": torch.zeros(per, _lib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=self.device),
              "act": torch.zeros(per, max(max_seg, 1), dtype=torch.int32, device=self.device), "gres": None, "gact": None}
@@ -220,7 +224,7 @@ class ShardedBatchPlanner:
     def plan_stripe_device(self, d_starts, d_goals, n_local, bufs, max_seg, stream=None, dst=0):
         """This rank's stripe (device tensors of waypoint records) through mplb_plan_batch_device, then the one gather of
         result records and action rows on `dst`."""
-        rank, world = _rank_world()
+        rank, world = self._rw()
         if self.comm is not None:
             import ctypes as C
             vp = lambda x: C.c_void_p(int(x)) if x else None  # noqa: E731
@@ -238,7 +242,7 @@ class ShardedBatchPlanner:
 
     def unstripe(self, bufs, n_total, max_seg):
         """On the gather destination: (results[n_total], actions[n_total, max_seg]) in global query order."""
-        rank, world = _rank_world()
+        rank, world = self._rw()
         results = np.zeros(n_total, dtype=_lib.RESULT_DTYPE)
         actions = np.full((n_total, max_seg), -1, dtype=np.int32)
         if self.comm is not None:
@@ -260,7 +264,7 @@ class ShardedBatchPlanner:
 
     def plan_batch(self, starts, goals, max_seg=64, dst=0):
         """starts/goals: full arrays on every rank (host, WAYPOINT_DTYPE). Each rank plans its stripe."""
-        rank, world = _rank_world()
+        rank, world = self._rw()
         if self.comm is not None:
             n = len(starts)
             res = np.zeros(n, dtype=_lib.RESULT_DTYPE) if rank == dst else None
