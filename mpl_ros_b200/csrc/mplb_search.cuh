@@ -1384,12 +1384,16 @@ astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Bat
           if (lane == 0) { E2.node = pf; E2.ready = (pf >= 0) ? 1 : 0; }
         }
       } else {
-        if (warp == 0) {
+        if (NB > 1 || warp == 0) {
           /* issue the table probes — WIN consecutive 32-byte slots per candidate, one HBM round trip in all but a
-           * few per cent of the cases at load factor <= 1/4 — and compute h while they fly */
+           * few per cent of the cases at load factor <= 1/4 — and compute h while they fly.  |U| > 32: the 32-control
+           * batches are dealt to the search and sampling warps (batch b -> warp b mod (NW - 1)), whose round trips then
+           * overlap instead of following each other on the search warp; the sampling warps sample afterwards (sampling is
+           * the short phase of this shape). */
           constexpr int WIN = (NB == 1) ? MPLB_WIN : 2;
 #pragma unroll
           for (int b = 0; b < NB; b++) {
+            if (NB > 1 && (b % (NW - 1)) != warp) continue;
             const int i = b * 32 + lane;
             const bool probing = (i < c.nU) && (E.verdict[i] >= 4);
             const unsigned long long k0 = probing ? E.k0[i] : 0ull, k1 = probing ? E.k1[i] : 0ull;
@@ -1420,7 +1424,8 @@ astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Bat
             if (i < c.nU) { S.p_nid[i] = nid; S.p_slot[i] = slot; S.p_g[i] = g; S.p_pg[i] = pg; S.p_h[i] = hv; }
           }
           MPLB_TICK(1);
-        } else {
+        }
+        if (warp != 0) {
           if (warp == 1) { /* ---- goal test (gs:146) and parity hash of the current node (needed only in P3) */
             bool gh = goal_test_warp<DIM, ORD>(c, S, S.cur, lane);
             if (lane == 0) { /* parity hash of the lattice ints (off the serial chain) */
@@ -1475,6 +1480,9 @@ astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Bat
           const bool isnew = valid && r_nid_b < 0;
           /* hazards: two successors -> one node or one table slot; later batches vs nodes created earlier in this pop */
           bool hazard = false;
+#ifdef MPLB_PHASE_TIMING
+          long long td0 = clock64();
+#endif
           {
             unsigned newm = __ballot_sync(0xffffffffu, isnew);
             unsigned fndm = __ballot_sync(0xffffffffu, found);
@@ -1493,6 +1501,10 @@ astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Bat
             }
             hazard = __any_sync(0xffffffffu, hazard) || (plog != nullptr); /* log mode relaxes serially: the records live there */
           }
+#ifdef MPLB_PHASE_TIMING
+          long long td1 = clock64();
+          if (lane == 0) MPLB_COUNT(0, td1 - td0);
+#endif
           if (hazard) {
             if (lane == 0) {
               MPLB_COUNT(3, 1);
@@ -1544,6 +1556,9 @@ astar_batch_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ Bat
             reinterpret_cast<RowHdr *>(rows + (size_t)nid * ROWB)->parent = cn;
           }
           if (lane == 0) S.n_nodes += n_new;
+#ifdef MPLB_PHASE_TIMING
+          if (lane == 0) MPLB_COUNT(1, clock64() - td1);
+#endif
           MPLB_TICK(4);
           /* heap operations in control order (gs:129-141) */
           unsigned hm = __ballot_sync(0xffffffffu, isnew || improve);
