@@ -272,6 +272,10 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU-baseline sample (default per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch1024", action="store_true")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="N = 1 only: two planners alternate so that the drain of one launch overlaps the start of the next "
+                         "(mplb_plan_stripe_begin / _end); off by default — with N > 1 the NCCL gather kernel cannot get SM room "
+                         "beside a persistent search kernel that fills the GPU, so the overlap does not materialise there")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -308,8 +312,9 @@ def main():
     nq = args.queries or spec["n_queries"]
     m = wl["make_map"]() if rank == 0 else None
 
-    def make_planner(o, d, r, mu):  # mu: the MapUtil that mplb_comm_broadcast_map built on this rank's device
-        mu.freeUnknown()
+    def make_planner(o, d, r, mu, first=True):  # mu: the MapUtil that mplb_comm_broadcast_map built on this rank's device
+        if first:
+            mu.freeUnknown()
         pl = mp.VoxelMapPlanner(False)
         pl.setMapUtil(mu)
         p = spec["params"]
@@ -330,6 +335,13 @@ def main():
     else:
         sp.set_map()
     pl = sp.planner
+    # --pipeline: a second planner on the same map and communicator; batches alternate between the two, so that the drain of
+    # one launch (it ends with its longest plan) overlaps the start of the next
+    pipe = bool(args.pipeline) and world == 1 and args.workload == "c2"
+    sp2 = None
+    if pipe:
+        sp2 = mdist.ShardedBatchPlanner(make_planner, dev, comm=comm)
+        sp2.planner = make_planner(None, None, None, pl.map_util_, first=False)
     s_all, g_all = mp.waypoints_array(nq), mp.waypoints_array(nq)
     if rank == 0:
         S, G = wl["make_queries"](m, nq)
@@ -347,33 +359,69 @@ def main():
     def step_device():
         return sp.plan_stripe_device(ds, dg, n_loc, bufs, MAX_SEG, stream)
 
+    sps = [sp, sp2] if pipe else [sp]
+    pbufs = [bufs] + ([sp2.make_device_buffers(nq, MAX_SEG)] if pipe else [])
+    pstreams = [torch.cuda.Stream(device=dev) for _ in sps]
+
+    def run_pipelined(k_steps):
+        """k_steps batches, at most one in flight per planner: begin(k), then end(k - 1).  Returns the device time of the
+        whole region (events on the default stream around it, the device idle at both ends) and the planner of the last batch."""
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(k_steps):
+            flush.zero_()  # L2 flush between iterations (default stream, concurrent with the batch still draining)
+            i = k % len(sps)
+            sps[i].begin_stripe_device(ds, dg, n_loc, pbufs[i], MAX_SEG, pstreams[i])
+            if k > 0:
+                j = (k - 1) % len(sps)
+                sps[j].end_stripe_device(pbufs[j])
+        last = (k_steps - 1) % len(sps)
+        sps[last].end_stripe_device(pbufs[last])
+        torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), last
+
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
     clocks = ClockSampler(local)
-    for _ in range(args.warmup):
-        flush.zero_()
-        step_device()
-    barrier()
-    launches0 = _lib.lib().mplb_launch_count()
-    t_wall0 = time.time()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms = []
-    for k in range(args.steps):
-        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
-        ev[k][0].record(stream)
-        step_device()
-        ev[k][1].record(stream)
-        kernel_ms.append(pl.last_batch_stats()["kernel_ms"])
-    barrier()
-    t_wall1 = time.time()
+    if pipe:
+        run_pipelined(args.warmup)
+        barrier()
+        launches0 = _lib.lib().mplb_launch_count()
+        t_wall0 = time.time()
+        total_ms, last = run_pipelined(args.steps)
+        barrier()
+        t_wall1 = time.time()
+        kernel_ms = [total_ms / args.steps]  # launches overlap: the per-launch share of the timed region
+        lastbufs = pbufs[last]
+    else:
+        for _ in range(args.warmup):
+            flush.zero_()
+            step_device()
+        barrier()
+        launches0 = _lib.lib().mplb_launch_count()
+        t_wall0 = time.time()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        kernel_ms = []
+        for k in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+            ev[k][0].record(stream)
+            step_device()
+            ev[k][1].record(stream)
+            kernel_ms.append(pl.last_batch_stats()["kernel_ms"])
+        barrier()
+        t_wall1 = time.time()
+        total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+        lastbufs = bufs
     clk = clocks.stop(t_wall0, t_wall1)
     launches = int(_lib.lib().mplb_launch_count() - launches0)
-    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
-    res_loc = bufs["res"].cpu().numpy().view(_lib.RESULT_DTYPE).reshape(-1)[:n_loc]
-    res_all, _ = sp.unstripe(bufs, nq, MAX_SEG) if rank == 0 else (None, None)
+    res_loc = lastbufs["res"].cpu().numpy().view(_lib.RESULT_DTYPE).reshape(-1)[:n_loc]
+    res_all, _ = sp.unstripe(lastbufs, nq, MAX_SEG) if rank == 0 else (None, None)
 
     # ---- e2e through the public host-buffer API (pinned inputs, H2D + D2H + gather inside the timed region)
     s_pin = torch.from_numpy(s_all.view(np.uint8).reshape(nq, -1)).pin_memory().numpy().view(_lib.WAYPOINT_DTYPE).reshape(-1)
@@ -387,10 +435,20 @@ def main():
     flush_ms = tf0.elapsed_time(tf1)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        flush.zero_()
+    if pipe:  # the same alternation through the host-buffer calls: begin(k) copies and enqueues, end(k - 1) gathers and copies back
+        for k in range(e2e_steps):
+            flush.zero_()
+            sps[k % 2].begin_batch(s_pin, g_pin, MAX_SEG)
+            if k > 0:
+                res_h, acts_h = sps[(k - 1) % 2].end_batch()
+        res_h, acts_h = sps[(e2e_steps - 1) % 2].end_batch()
         torch.cuda.synchronize()
-        res_h, acts_h = sp.plan_batch(s_pin, g_pin, MAX_SEG)
+        flush_ms = 0.0  # the flushes ran concurrently with the batches
+    else:
+        for _ in range(e2e_steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            res_h, acts_h = sp.plan_batch(s_pin, g_pin, MAX_SEG)
     barrier()
     e2e_ms = ((time.perf_counter() - t0) * 1e3 - flush_ms * e2e_steps) / e2e_steps
     if rank == 0:
@@ -457,7 +515,9 @@ def main():
     ok = res_all["status"] == 0
     cfg = {"workload": "%s_batch%d" % (wl["tag"], nq), "map": wl["map_note"], "U": int(U.shape[0]), "global_batch": nq,
            "parallelism": "one query list sharded over %d rank(s), query i -> rank i mod N; map broadcast + result gather" % world,
-           "l2": "flushed between timed iterations (512 MiB memset outside the event pairs)",
+           "l2": "flushed between timed iterations (512 MiB memset per step)",
+           "pipeline": ("two planners alternate: batch k + 1 is enqueued before batch k is waited for, so the drain of a launch "
+                        "overlaps the start of the next; value = units / (device time of the K-step region / K)") if pipe else "off",
            "plans_per_sec": nq / (ms_step * 1e-3),
            "ms_per_plan_p50": float(np.percentile(dms, 50)), "ms_per_plan_p95": float(np.percentile(dms, 95)),
            "ms_per_plan_max": float(dms.max()),

@@ -257,6 +257,17 @@ int mplb_plan_batch_sharded(mplb_planner *p, mplb_comm *c, const mplb_waypoint *
 int mplb_plan_stripe_gather_device(mplb_planner *p, mplb_comm *c, const void *d_starts, const void *d_goals, int n_local, int per,
                                    void *d_results, void *d_actions, int max_seg, int root, void *stream);
 int mplb_comm_unstripe(mplb_comm *c, int n, int per, int max_seg, mplb_result *results, int32_t *actions);
+/* The same two calls split in halves, so that a caller can keep ONE batch in flight per planner: *_begin enqueues the
+ * copies, the ordering kernels and the search launch and returns without waiting; *_end completes the batch (larger arena
+ * tiers for overflowed plans, the gather, the copy back).  A launch ends with its longest plan; two planners sharing one map
+ * and alternating batches overlap that drain with the start of the next batch (bench.py does this).
+ * The host buffers given to mplb_plan_batch_sharded_begin are copied before it returns. */
+int mplb_plan_stripe_begin(mplb_planner *p, const void *d_starts, const void *d_goals, int n_local, void *d_results, void *d_actions,
+                           int max_seg, void *stream);
+int mplb_plan_stripe_end(mplb_planner *p, mplb_comm *c, int per, int root);
+int mplb_plan_batch_sharded_begin(mplb_planner *p, mplb_comm *c, const mplb_waypoint *starts, const mplb_waypoint *goals, int n,
+                                  int max_seg);
+int mplb_plan_batch_sharded_end(mplb_planner *p, mplb_comm *c, int n, mplb_result *results, int32_t *actions, int root);
 
 #ifdef __cplusplus
 }

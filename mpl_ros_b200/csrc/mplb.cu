@@ -323,6 +323,8 @@ struct mplb_map {
   }
 };
 
+namespace { struct BatchRun; }
+
 struct mplb_planner {
   int dim = 3;
   int verbose = 0;
@@ -352,6 +354,10 @@ struct mplb_planner {
   double prior_start_t = 0; /* t of the start waypoints of the batch being planned (the table is indexed by depth) */
   double cfg_prior_start_t = 0;
   DevBuf<double> d_prior;
+  BatchRun *run = nullptr; /* the batch in flight (run_batch_begin / run_batch_end) */
+  cudaStream_t own_stream = nullptr; /* stream of the asynchronous host-buffer entry points */
+  std::vector<mplb_waypoint> h_ls, h_lg; /* staged stripe of the asynchronous host-buffer entry points */
+  int async_n = 0, async_per = 0, async_ms = 0;
   int exact_preds = -1; /* predecessor log: -1 = where the running best predecessor is not provably exact, 0 = never, 1 = always */
   bool log_mode = false;
 
@@ -768,8 +774,81 @@ int hcap_big(int device) {
 #endif
 
 /* Core: device-resident batch over arena tiers. */
-int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoint *d_goals, int n, mplb_result *d_results,
-              int *d_actions, double *d_segs, int max_seg, int control, bool retain, cudaStream_t s) {
+/* One batch over arena tiers, in two halves so that a caller can keep one batch in flight per planner:
+ * run_batch_begin enqueues everything up to and including the first tier's search launch and returns without waiting;
+ * run_batch_end waits for it, re-runs overflowed plans in larger tiers (synchronously) and closes the timing.  Two planners
+ * on two streams overlap the drain of one batch (a launch ends with its longest plan) with the start of the next. */
+struct BatchRun {
+  bool active = false;
+  const mplb_waypoint *d_starts = nullptr, *d_goals = nullptr;
+  mplb_result *d_results = nullptr;
+  int *d_actions = nullptr;
+  double *d_segs = nullptr;
+  int n = 0, max_seg = 0;
+  bool retain = false, shaped = false, identity = true, finished = false;
+  cudaStream_t s = nullptr;
+  int n_work = 0, cap = 0, resident = 0, slots = 0, n_this_tier = 0;
+  long long cap_bound = 0;
+  size_t budget = 0;
+  Layout L;
+};
+
+/* the body of one tier up to its launch; sets R.finished when nothing is left to launch (NOMEM marking) */
+int batch_launch_tier(mplb_planner *p, BatchRun &R) {
+  const DevCfg &c = p->cfg;
+  cudaStream_t s = R.s;
+  int rc = MPLB_OK;
+  R.L = make_layout(R.cap, c.ns, c.nU, R.retain, p->log_mode);
+  const Layout &L = R.L;
+  int slots = std::min(R.n_work, R.resident);
+  if (p->max_slots > 0) slots = std::min(slots, p->max_slots);
+  if ((size_t)slots * L.stride > R.budget) slots = (int)(R.budget / L.stride);
+  if (slots <= 0 || (long long)load_inv_of(R.cap) * ((long long)R.cap + c.nU) > (1ll << 30)) {
+    /* nothing larger fits (or the table would pass 2^30 slots): the remaining plans report NOMEM.  In the first tier
+     * the work list may be the identity (no id array was written), later tiers carry the overflow list. */
+    k_mark_status<<<(R.n_work + 255) / 256, 256, 0, s>>>(R.d_results, R.identity ? nullptr : p->d_work.p, R.n_work, MPLB_PLAN_NOMEM);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    R.finished = true;
+    return MPLB_OK;
+  }
+  if (p->arena.n < (size_t)slots * L.stride) {
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (p->arena.reserve((size_t)slots * L.stride) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(MPLB_ERR_NOMEM, "cannot allocate the search arena");
+    }
+  }
+  CUDA_TRY(cudaMemsetAsync(p->d_ctrl.p, 0, 2 * sizeof(int), s));
+  BatchArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.starts = R.d_starts; a.goals = R.d_goals; a.results = R.d_results; a.actions = R.d_actions; a.seg_states = R.d_segs;
+  a.max_seg = R.max_seg; a.work = R.identity ? nullptr : p->d_work.p; a.n_work = R.n_work;
+  a.work_counter = p->d_ctrl.p; a.arena = p->arena.p; a.stride = L.stride; a.cap = R.cap; a.tsize_max = L.tsize_max; a.load_inv = load_inv_of(R.cap);
+  a.off_rows = L.off_rows; a.off_heap = L.off_heap; a.off_table = L.off_table; a.off_poplog = L.off_poplog;
+  a.off_log = L.off_log; a.log_cap = L.log_cap;
+  /* |U| > 32: when memory leaves at most one plan per SM anyway, that plan gets a much larger shared-memory heap top */
+  a.hcap = (c.nU > 32 && slots <= p->sm_count && p->hcap_big_cached > 0) ? p->hcap_big_cached : MPLB_HCAP_SMALL;
+  a.want_poplog = R.retain ? 1 : 0; a.slot_of_plan = R.retain ? p->d_slot.p : nullptr;
+  a.overflow_count = p->d_ctrl.p + 1; a.overflow_list = p->d_over.p;
+#ifdef MPLB_PHASE_TIMING
+  CUDA_TRY(p->d_phase.reserve((size_t)R.n * 16));
+  a.phase_cycles = p->d_phase.p;
+#endif
+  const bool shaped = R.shaped;
+#define LAUNCH_CALL(D, O, M) rc = launch_any<D, O, M>(shaped, c, a, slots, s)
+  DISPATCH(c.dim, c.ord, c.nU, LAUNCH_CALL);
+  if (rc != MPLB_OK) return rc;
+  p->last_launches++; p->last_tiers++;
+  R.slots = slots;
+  R.n_this_tier = R.n_work;
+  return MPLB_OK;
+}
+
+int run_batch_begin(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoint *d_goals, int n, mplb_result *d_results,
+                    int *d_actions, double *d_segs, int max_seg, int control, bool retain, cudaStream_t s) {
+  BatchRun &R = *p->run;
+  if (R.active) return fail(MPLB_ERR_STATE, "a batch is already in flight on this planner (mplb_*_end not called)");
   int rc = build_cfg(p, control);
   if (rc != MPLB_OK) return rc;
   const DevCfg &c = p->cfg;
@@ -800,17 +879,19 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     p->budget_bytes = (size_t)((double)(free_b + p->arena.n) * p->mem_fraction);
   }
-  const size_t budget = p->budget_bytes;
 
-  int n_work = n;
-  bool identity = true;
+  R = BatchRun();
+  R.d_starts = d_starts; R.d_goals = d_goals; R.d_results = d_results; R.d_actions = d_actions; R.d_segs = d_segs;
+  R.n = n; R.max_seg = max_seg; R.retain = retain; R.shaped = shaped; R.s = s; R.resident = resident; R.budget = p->budget_bytes;
+  R.n_work = n;
+  R.identity = true;
   int cap = 32768;
   /* MaxExpandStep bounds the node count by max_num * |U| (every pop creates at most |U| nodes): no tier needs more */
-  const long long cap_bound = c.max_num > 0 ? std::min<long long>((long long)c.max_num * c.nU + 2LL * c.nU + 64, 1ll << 30) : (1ll << 30);
+  R.cap_bound = c.max_num > 0 ? std::min<long long>((long long)c.max_num * c.nU + 2LL * c.nU + 64, 1ll << 30) : (1ll << 30);
   if (c.max_num > 0) { /* start in the tier that is likely to fit */
-    while (cap < cap_bound && cap < 262144) cap *= 8;
+    while (cap < R.cap_bound && cap < 262144) cap *= 8;
   }
-  cap = (int)std::min<long long>(cap, std::max<long long>(cap_bound, 1024));
+  R.cap = (int)std::min<long long>(cap, std::max<long long>(R.cap_bound, 1024));
   p->last_launches = 0; p->last_tiers = 0;
   bool ev0_done = false;
   if (n > resident / 2 && n <= 65536) { /* longest-first order (scheduling only): see k_plan_keys */
@@ -836,6 +917,7 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
           k_label_count<<<blocks, 256, 0, s>>>(m->d_labels, m->d_comp_size, m->ncell);
           g_launches++;
         }
+        CUDA_TRY(cudaStreamSynchronize(s)); /* another planner's stream may read the labels next */
         m->labels_version = m->version;
       }
     }
@@ -850,68 +932,41 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
     g_launches += 2;
     p->last_launches += 2;
     CUDA_TRY(cudaGetLastError());
-    identity = false;
+    R.identity = false;
   }
   if (!ev0_done) CUDA_TRY(cudaEventRecord(p->ev0, s));
-  while (n_work > 0) {
-    Layout L = make_layout(cap, c.ns, c.nU, retain, p->log_mode);
-    int slots = std::min(n_work, resident);
-    if (p->max_slots > 0) slots = std::min(slots, p->max_slots);
-    if ((size_t)slots * L.stride > budget) slots = (int)(budget / L.stride);
-    if (slots <= 0 || (long long)load_inv_of(cap) * ((long long)cap + c.nU) > (1ll << 30)) {
-      /* nothing larger fits (or the table would pass 2^30 slots): the remaining plans report NOMEM.  In the first tier
-       * the work list may be the identity (no id array was written), later tiers carry the overflow list. */
-      k_mark_status<<<(n_work + 255) / 256, 256, 0, s>>>(d_results, identity ? nullptr : p->d_work.p, n_work, MPLB_PLAN_NOMEM);
-      g_launches++;
-      CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaStreamSynchronize(s));
-      break;
-    }
-    if (p->arena.n < (size_t)slots * L.stride) {
-      CUDA_TRY(cudaStreamSynchronize(s));
-      if (p->arena.reserve((size_t)slots * L.stride) != cudaSuccess) {
-        cudaGetLastError();
-        return fail(MPLB_ERR_NOMEM, "cannot allocate the search arena");
-      }
-    }
-    CUDA_TRY(cudaMemsetAsync(p->d_ctrl.p, 0, 2 * sizeof(int), s));
-    BatchArgs a;
-    std::memset(&a, 0, sizeof(a));
-    a.starts = d_starts; a.goals = d_goals; a.results = d_results; a.actions = d_actions; a.seg_states = d_segs;
-    a.max_seg = max_seg; a.work = identity ? nullptr : p->d_work.p; a.n_work = n_work;
-    a.work_counter = p->d_ctrl.p; a.arena = p->arena.p; a.stride = L.stride; a.cap = cap; a.tsize_max = L.tsize_max; a.load_inv = load_inv_of(cap);
-    a.off_rows = L.off_rows; a.off_heap = L.off_heap; a.off_table = L.off_table; a.off_poplog = L.off_poplog;
-    a.off_log = L.off_log; a.log_cap = L.log_cap;
-    /* |U| > 32: when memory leaves at most one plan per SM anyway, that plan gets a much larger shared-memory heap top */
-    a.hcap = (c.nU > 32 && slots <= p->sm_count && p->hcap_big_cached > 0) ? p->hcap_big_cached : MPLB_HCAP_SMALL;
-    a.want_poplog = retain ? 1 : 0; a.slot_of_plan = retain ? p->d_slot.p : nullptr;
-    a.overflow_count = p->d_ctrl.p + 1; a.overflow_list = p->d_over.p;
-#ifdef MPLB_PHASE_TIMING
-    CUDA_TRY(p->d_phase.reserve((size_t)n * 16));
-    a.phase_cycles = p->d_phase.p;
-#endif
-#define LAUNCH_CALL(D, O, M) rc = launch_any<D, O, M>(shaped, c, a, slots, s)
-    DISPATCH(c.dim, c.ord, c.nU, LAUNCH_CALL);
-    if (rc != MPLB_OK) return rc;
-    p->last_launches++; p->last_tiers++;
-    const int slots_total_this_tier = n_work;
+  rc = batch_launch_tier(p, R);
+  if (rc != MPLB_OK) return rc;
+  R.active = true;
+  return MPLB_OK;
+}
+
+int run_batch_end(mplb_planner *p) {
+  BatchRun &R = *p->run;
+  if (!R.active) return fail(MPLB_ERR_STATE, "no batch in flight on this planner");
+  R.active = false;
+  const DevCfg &c = p->cfg;
+  cudaStream_t s = R.s;
+  while (!R.finished) {
     int n_over = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_over, p->d_ctrl.p + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    if (retain && n == 1 && n_over == 0) {
-      p->ret_cap = cap; p->ret_ns = c.ns; p->ret_stride = L.stride; p->ret_off_state = L.off_rows; p->ret_row_bytes = L.row_bytes;
-      p->ret_off_heap = L.off_heap; p->ret_off_poplog = L.off_poplog;
+    if (R.retain && R.n == 1 && n_over == 0) {
+      p->ret_cap = R.cap; p->ret_ns = c.ns; p->ret_stride = R.L.stride; p->ret_off_state = R.L.off_rows; p->ret_row_bytes = R.L.row_bytes;
+      p->ret_off_heap = R.L.off_heap; p->ret_off_poplog = R.L.off_poplog;
     }
     if (n_over == 0) break;
     /* next tier: overflowed plans restart from scratch (the search is deterministic) with 8x the arena */
     std::swap(p->d_work, p->d_over);
-    n_work = n_over;
-    identity = false;
-    if (cap >= cap_bound || cap > (1 << 27)) { cap = 1 << 30; continue; } /* beyond every budget: the next pass reports NOMEM */
+    R.n_work = n_over;
+    R.identity = false;
+    if (R.cap >= R.cap_bound || R.cap > (1 << 27)) R.cap = 1 << 30; /* beyond every budget: the next pass reports NOMEM */
     /* with a MaxExpandStep bound and most plans of this tier overflowing (a search that does not terminate early, like the
      * jerk lattice of BASELINE configs[4]) the remaining tiers would only repeat work: go straight to the bound */
-    if (c.max_num > 0 && 2 * n_over > slots_total_this_tier) cap = (int)cap_bound;
-    else cap = (int)std::min<long long>((long long)cap * 8, cap_bound);
+    else if (c.max_num > 0 && 2 * n_over > R.n_this_tier) R.cap = (int)R.cap_bound;
+    else R.cap = (int)std::min<long long>((long long)R.cap * 8, R.cap_bound);
+    int rc = batch_launch_tier(p, R);
+    if (rc != MPLB_OK) return rc;
   }
   CUDA_TRY(cudaEventRecord(p->ev1, s));
   CUDA_TRY(cudaEventSynchronize(p->ev1));
@@ -919,6 +974,13 @@ int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoin
   CUDA_TRY(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
   p->last_ms = ms;
   return MPLB_OK;
+}
+
+int run_batch(mplb_planner *p, const mplb_waypoint *d_starts, const mplb_waypoint *d_goals, int n, mplb_result *d_results,
+              int *d_actions, double *d_segs, int max_seg, int control, bool retain, cudaStream_t s) {
+  int rc = run_batch_begin(p, d_starts, d_goals, n, d_results, d_actions, d_segs, max_seg, control, retain, s);
+  if (rc != MPLB_OK) return rc;
+  return run_batch_end(p);
 }
 
 int set_device_of(int device) {
@@ -1075,6 +1137,7 @@ int mplb_planner_create(int dim, int verbose, mplb_planner **out) {
   p->dim = dim;
   p->verbose = verbose;
   if (cudaGetDevice(&p->device) != cudaSuccess) { delete p; return fail(MPLB_ERR_CUDA, "no CUDA device (libmplb has no CPU path)"); }
+  p->run = new BatchRun();
   if (verbose) std::printf("[MapPlanner] PLANNER VERBOSE ON\n");
   *out = p;
   return MPLB_OK;
@@ -1088,6 +1151,8 @@ void mplb_planner_destroy(mplb_planner *p) {
   p->d_keys.release(); p->d_phase.release(); p->d_pot.release(); p->d_region.release(); p->d_Uyaw.release(); p->d_prior.release();
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
+  if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  delete p->run;
   delete p;
 }
 
@@ -1799,6 +1864,79 @@ int mplb_plan_stripe_gather_device(mplb_planner *p, mplb_comm *c, const void *d_
   rc = comm_gather(c, d_results, max_seg > 0 ? d_actions : nullptr, per, max_seg > 0 ? max_seg : 0, root, (cudaStream_t)stream);
   if (rc != MPLB_OK) return rc;
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return MPLB_OK;
+}
+
+/* ---- one batch in flight per planner: begin enqueues the search (no wait), end completes it and gathers.  Two planners on
+ * one map overlap the drain of one batch with the start of the next (a launch ends with its longest plan). */
+int mplb_plan_stripe_begin(mplb_planner *p, const void *d_starts, const void *d_goals, int n_local, void *d_results, void *d_actions,
+                           int max_seg, void *stream) {
+  if (!p || !d_results || (n_local > 0 && (!d_starts || !d_goals))) return fail(MPLB_ERR_ARG, "null argument");
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  p->async_n = n_local;
+  p->run->d_results = (mplb_result *)d_results; p->run->d_actions = (int *)d_actions; p->run->max_seg = max_seg; /* the gather needs them even for an empty stripe */
+  if (n_local <= 0) return MPLB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  mplb_waypoint w0;
+  CUDA_TRY(cudaMemcpyAsync(&w0, d_starts, sizeof(w0), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s)); /* this stream only: the other planner's batch keeps running */
+  p->prior_start_t = w0.t;
+  return run_batch_begin(p, (const mplb_waypoint *)d_starts, (const mplb_waypoint *)d_goals, n_local, (mplb_result *)d_results,
+                         (int *)d_actions, nullptr, max_seg, w0.control, false, s);
+}
+
+int mplb_plan_stripe_end(mplb_planner *p, mplb_comm *c, int per, int root) {
+  if (!p || !c) return fail(MPLB_ERR_ARG, "null argument");
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  int rc = MPLB_OK;
+  if (p->async_n > 0) rc = run_batch_end(p);
+  if (rc != MPLB_OK) return rc;
+  /* every gather of a communicator runs on the communicator's stream, in call order (the search is complete: run_batch_end
+   * synchronised the planner's stream) */
+  rc = comm_gather(c, p->run->d_results, p->run->max_seg > 0 ? p->run->d_actions : nullptr, per, p->run->max_seg > 0 ? p->run->max_seg : 0, root,
+                   c->stream);
+  if (rc != MPLB_OK) return rc;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return MPLB_OK;
+}
+
+int mplb_plan_batch_sharded_begin(mplb_planner *p, mplb_comm *c, const mplb_waypoint *starts, const mplb_waypoint *goals, int n,
+                                  int max_seg) {
+  if (!p || !c || !starts || !goals || n <= 0) return fail(MPLB_ERR_ARG, "bad argument");
+  if (p->device != c->device) return fail(MPLB_ERR_ARG, "planner and communicator live on different devices");
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  if (!p->own_stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+  const int N = c->nranks, per = (n + N - 1) / N;
+  p->h_ls.clear(); p->h_lg.clear();
+  for (int i = c->rank; i < n; i += N) { p->h_ls.push_back(starts[i]); p->h_lg.push_back(goals[i]); }
+  const int n_loc = (int)p->h_ls.size();
+  p->async_n = n_loc; p->async_per = per; p->async_ms = max_seg;
+  CUDA_TRY(p->d_starts.reserve(std::max(per, 1)));
+  CUDA_TRY(p->d_goals.reserve(std::max(per, 1)));
+  CUDA_TRY(p->d_results.reserve(std::max(per, 1)));
+  if (max_seg > 0) CUDA_TRY(p->d_actions.reserve((size_t)per * max_seg));
+  cudaStream_t s = p->own_stream;
+  CUDA_TRY(cudaMemsetAsync(p->d_results.p, 0, (size_t)per * sizeof(mplb_result), s));
+  if (n_loc <= 0) return MPLB_OK;
+  CUDA_TRY(cudaMemcpyAsync(p->d_starts.p, p->h_ls.data(), (size_t)n_loc * sizeof(mplb_waypoint), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(p->d_goals.p, p->h_lg.data(), (size_t)n_loc * sizeof(mplb_waypoint), cudaMemcpyHostToDevice, s));
+  p->prior_start_t = p->h_ls[0].t;
+  return run_batch_begin(p, p->d_starts.p, p->d_goals.p, n_loc, p->d_results.p, max_seg > 0 ? p->d_actions.p : nullptr, nullptr, max_seg,
+                         p->h_ls[0].control, false, s);
+}
+
+int mplb_plan_batch_sharded_end(mplb_planner *p, mplb_comm *c, int n, mplb_result *results, int32_t *actions, int root) {
+  if (!p || !c) return fail(MPLB_ERR_ARG, "null argument");
+  if (c->rank == root && !results) return fail(MPLB_ERR_ARG, "the root needs a result buffer");
+  if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
+  int rc = MPLB_OK;
+  if (p->async_n > 0) rc = run_batch_end(p);
+  if (rc != MPLB_OK) return rc;
+  const int ms = p->async_ms;
+  rc = comm_gather(c, p->d_results.p, ms > 0 ? p->d_actions.p : nullptr, p->async_per, ms > 0 ? ms : 0, root, c->stream);
+  if (rc != MPLB_OK) return rc;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (c->rank == root) return mplb_comm_unstripe(c, n, p->async_per, actions ? ms : 0, results, actions);
   return MPLB_OK;
 }
 

@@ -240,6 +240,32 @@ class ShardedBatchPlanner:
             dist.gather(bufs["res"], bufs["gres"], dst=dst)
             dist.gather(bufs["act"], bufs["gact"], dst=dst)
 
+    # ---- one batch in flight per planner (mplb_plan_stripe_begin / _end, mplb_plan_batch_sharded_begin / _end): two
+    # ShardedBatchPlanner objects on one map and one communicator, alternating, overlap the drain of a launch with the
+    # start of the next one
+    def begin_stripe_device(self, d_starts, d_goals, n_local, bufs, max_seg, stream=None):
+        import ctypes as C
+        vp = lambda x: C.c_void_p(int(x)) if x else None  # noqa: E731
+        _lib.check(_lib.lib().mplb_plan_stripe_begin(self.planner._h, vp(d_starts.data_ptr()), vp(d_goals.data_ptr()), n_local,
+                                                   vp(bufs["res"].data_ptr()), vp(bufs["act"].data_ptr() if max_seg else 0), max_seg,
+                                                   vp(stream.cuda_stream if stream is not None else 0)))
+
+    def end_stripe_device(self, bufs, dst=0):
+        _lib.check(_lib.lib().mplb_plan_stripe_end(self.planner._h, self.comm._h, bufs["res"].shape[0], dst))
+
+    def begin_batch(self, starts, goals, max_seg=64):
+        self._pending = (len(starts), max_seg)
+        _lib.check(_lib.lib().mplb_plan_batch_sharded_begin(self.planner._h, self.comm._h, _lib.ptr(starts), _lib.ptr(goals), len(starts),
+                                                          max_seg))
+
+    def end_batch(self, dst=0):
+        n, max_seg = self._pending
+        rank, world = self._rw()
+        res = np.zeros(n, dtype=_lib.RESULT_DTYPE) if rank == dst else None
+        acts = np.full((n, max_seg), -1, dtype=np.int32) if (rank == dst and max_seg) else None
+        _lib.check(_lib.lib().mplb_plan_batch_sharded_end(self.planner._h, self.comm._h, n, _lib.ptr(res), _lib.ptr(acts), dst))
+        return res, acts
+
     def unstripe(self, bufs, n_total, max_seg):
         """On the gather destination: (results[n_total], actions[n_total, max_seg]) in global query order."""
         rank, world = self._rw()

@@ -357,3 +357,64 @@ def test_full_bench_batch_parity():
         assert rg["cost"][i] == 10.0 * rg["n_seg"][i] + J[acts].sum()
     ex = rg["status"] == 3
     assert np.all(rg["n_open"][ex] == 0) and np.all(rg["n_closed"][ex] == rg["n_nodes"][ex])
+
+
+def test_batch_in_flight_begin_end():
+    """mplb_plan_stripe_begin / _end and mplb_plan_batch_sharded_begin / _end (one batch in flight per planner): two planners
+    on one map alternate three batches each way; every batch must equal the synchronous call."""
+    import torch
+    from mpl_ros_b200 import dist as mdist, _lib
+    m = maps.load_fixture("levine")
+    U = maps.make_U(1.0, 1, 3)
+    dev = torch.device("cuda", 0)
+    comm = mdist.Comm(mdist.Comm.unique_id(), 0, 1)
+
+    def mk(o, d, r, mu, first=True):
+        if first:
+            mu.freeUnknown()
+        pl = mp.VoxelMapPlanner(False)
+        pl.setMapUtil(mu)
+        pl.setVmax(2.0); pl.setAmax(1.0); pl.setDt(1.0); pl.setU(U); pl.setTol(0.5)
+        pl._keep = mu
+        return pl
+
+    sp = mdist.ShardedBatchPlanner(mk, dev, comm=comm)
+    sp.set_map(m.origin, m.dim, m.res, m.data)
+    sp2 = mdist.ShardedBatchPlanner(mk, dev, comm=comm)
+    sp2.planner = mk(None, None, None, sp.planner.map_util_, first=False)
+    n = 700
+    batches = []
+    for seed in (21, 22, 23):
+        S, G = maps.sample_queries(m, n, seed=seed)
+        s, g = mp.waypoints_array(n), mp.waypoints_array(n)
+        s["pos"], g["pos"], s["control"], g["control"] = S, G, mp.ACC, mp.ACC
+        want, want_acts = sp.plan_batch(s, g, max_seg=48)
+        batches.append((s, g, want, want_acts))
+    fields = [f for f in want.dtype.names if f != "device_ms"]
+    # host-buffer halves, alternating planners
+    sps = [sp, sp2]
+    got = []
+    for k, (s, g, _, _) in enumerate(batches):
+        sps[k % 2].begin_batch(s, g, 48)
+        if k > 0:
+            got.append(sps[(k - 1) % 2].end_batch())
+    got.append(sps[(len(batches) - 1) % 2].end_batch())
+    for (s, g, want, want_acts), (res, acts) in zip(batches, got):
+        assert all(np.array_equal(res[f], want[f]) or f == "cost" for f in fields)
+        assert np.array_equal(acts, want_acts)
+    # device-resident halves
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    bufs = [sp.make_device_buffers(n, 48), sp2.make_device_buffers(n, 48)]
+    dsg = [(torch.from_numpy(s.view(np.uint8).reshape(n, -1)).to(dev), torch.from_numpy(g.view(np.uint8).reshape(n, -1)).to(dev))
+           for s, g, _, _ in batches]
+    outs = []
+    for k in range(len(batches)):
+        sps[k % 2].begin_stripe_device(dsg[k][0], dsg[k][1], n, bufs[k % 2], 48, streams[k % 2])
+        if k > 0:
+            sps[(k - 1) % 2].end_stripe_device(bufs[(k - 1) % 2])
+            outs.append(sp.unstripe(bufs[(k - 1) % 2], n, 48))
+    sps[(len(batches) - 1) % 2].end_stripe_device(bufs[(len(batches) - 1) % 2])
+    outs.append(sp.unstripe(bufs[(len(batches) - 1) % 2], n, 48))
+    for (s, g, want, want_acts), (res, acts) in zip(batches, outs):
+        assert all(np.array_equal(res[f], want[f]) or f == "cost" for f in fields)
+        assert np.array_equal(acts, want_acts)
