@@ -156,6 +156,12 @@ class Primitive {
     for (int k = 0; k < 6; k++) cyaw_[k] = 0;
     if (((int)control_ & 16) && (int)u.size() > Dim) { cyaw_[4] = u[Dim]; cyaw_[5] = p.yaw; } /* pr_yaw_ = Primitive1D(p.yaw, u(Dim)) */
   }
+  /* Primitive(cs, t, control), primitive.h:309-313: coefficient rows given directly (Dim rows, optionally a yaw row) */
+  Primitive(const double *rows6, const double *yaw6, decimal_t t, Control::Control control) : t_(t), control_(control) {
+    for (int i = 0; i < Dim; i++)
+      for (int k = 0; k < 6; k++) c_[i][k] = rows6[i * 6 + k];
+    for (int k = 0; k < 6; k++) cyaw_[k] = yaw6 ? yaw6[k] : 0;
+  }
   decimal_t t() const { return t_; }
   Control::Control control() const { return control_; }
   const double *coeff(int k) const { return c_[k]; } /* float64[6] row of planning_ros_msgs/Primitive (cx, cy, cz) */
@@ -171,28 +177,36 @@ class Primitive {
       p.jrk(k) = c[0] / 2 * t * t + c[1] * t + c[2];
     }
     if (p.use_yaw) { /* primitive.h:328 with normalize_angle (math.h:15-19) */
-      decimal_t a = cyaw_[4] * t + cyaw_[5];
+      const double *c = cyaw_; /* Primitive1D::p, primitive.h:128-131 (a planner's yaw row has only c[4], c[5]) */
+      const double t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
+      decimal_t a = c[0] / 120 * t5 + c[1] / 24 * t4 + c[2] / 6 * t3 + c[3] / 2 * t * t + c[4] * t + c[5];
       while (a > M_PI) a -= 2.0 * M_PI;
       while (a < -M_PI) a += 2.0 * M_PI;
       p.yaw = a;
     }
     return p;
   }
-  decimal_t J(const Control::Control &control) const { /* primitive.h:92-122,403-407 for c0 = 0 rows */
+  decimal_t J(const Control::Control &control) const { /* primitive.h:92-122 (full rows), summed over the axes :403-407 */
     decimal_t j = 0;
+    const double t = t_;
+    auto pw = [](double x, int n) { double r = 1; while (n-- > 0) r *= x; return r; }; /* math.h:197-203 */
     for (int k = 0; k < Dim; k++) {
       const double *c = c_[k];
-      const double t = t_;
-      const int base = (int)control & 15; /* primitive.h:94-117: the yaw variants share the branch */
+      const int base = (int)control & 15; /* the yaw variants share the branch */
       if (base == Control::VEL)
-        j += (c[1] * c[1] / 252) * std::pow(t, 7) + (c[1] * c[2] / 36) * std::pow(t, 6) + (c[2] * c[2] / 20 + c[1] * c[3] / 15) * std::pow(t, 5) +
-             (c[2] * c[3] / 4 + c[1] * c[4] / 12) * std::pow(t, 4) + (c[3] * c[3] / 3 + c[2] * c[4] / 3) * t * t * t + c[3] * c[4] * t * t + c[4] * c[4] * t;
+        j += c[0] * c[0] / 5184 * pw(t, 9) + c[0] * c[1] / 576 * pw(t, 8) + (c[1] * c[1] / 252 + c[0] * c[2] / 168) * pw(t, 7) +
+             (c[0] * c[3] / 72 + c[1] * c[2] / 36) * pw(t, 6) + (c[2] * c[2] / 20 + c[0] * c[4] / 60 + c[1] * c[3] / 15) * pw(t, 5) +
+             (c[2] * c[3] / 4 + c[1] * c[4] / 12) * pw(t, 4) + (c[3] * c[3] / 3 + c[2] * c[4] / 3) * pw(t, 3) + c[3] * c[4] * t * t +
+             c[4] * c[4] * t;
       else if (base == Control::ACC)
-        j += (c[1] * c[1] / 20) * std::pow(t, 5) + (c[1] * c[2] / 4) * std::pow(t, 4) + (c[2] * c[2] / 3 + c[1] * c[3] / 3) * t * t * t + c[2] * c[3] * t * t + c[3] * c[3] * t;
+        j += c[0] * c[0] / 252 * pw(t, 7) + c[0] * c[1] / 36 * pw(t, 6) + (c[1] * c[1] / 20 + c[0] * c[2] / 15) * pw(t, 5) +
+             (c[0] * c[3] / 12 + c[1] * c[2] / 4) * pw(t, 4) + (c[2] * c[2] / 3 + c[1] * c[3] / 3) * pw(t, 3) + c[2] * c[3] * t * t +
+             c[3] * c[3] * t;
       else if (base == Control::JRK)
-        j += (c[1] * c[1]) / 3 * t * t * t + c[1] * c[2] * t * t + c[2] * c[2] * t;
+        j += c[0] * c[0] / 20 * pw(t, 5) + c[0] * c[1] / 4 * pw(t, 4) + (c[1] * c[1] + c[0] * c[2]) / 3 * pw(t, 3) + c[1] * c[2] * t * t +
+             c[2] * c[2] * t;
       else if (base == Control::SNP)
-        j += c[1] * c[1] * t;
+        j += c[0] * c[0] / 3 * pw(t, 3) + c[0] * c[1] * t * t + c[1] * c[1] * t;
     }
     return j;
   }

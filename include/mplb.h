@@ -213,6 +213,32 @@ int mplb_serialize_trajectories(mplb_planner *p, const mplb_result *results, con
                                 int n, int max_seg, double z, uint32_t seq, uint32_t stamp_sec, uint32_t stamp_nsec,
                                 const char *frame_id, uint8_t *out, size_t stride, uint32_t *len);
 
+/* ---- trajectory post-processing: TrajSolver<Dim>(control, yaw_control) with setWaypoints + setDts,
+ * then solve() (include/mpl_traj_solver/traj_solver.h:12-109 over PolySolver<Dim>::solve, src/mpl_traj_solver/poly_solver.cpp:23-221
+ * and PolyTraj::toPrimitives, src/mpl_traj_solver/poly_traj.cpp:75-92) for a BATCH of independent waypoint lists, one CTA each.
+ * This is the refinement map_planner_node.cpp:216-227 applies to a planned trajectory (waypoints = traj.getWaypoints() with
+ * the interior ones set to Control::VEL, dts = traj.getSegmentTimes(), TrajSolver3D(Control::JRK)).
+ *   control      MPLB_CONTROL_VEL / ACC / JRK (+ the xYAW variants): minimum velocity / acceleration / jerk spline
+ *                (PolySolver(0,1) / (1,2) / (2,3)); SNP has no solver in the reference ("only works up to third order") and
+ *                gives empty trajectories here too (n_segs = 0)
+ *   yaw_control  MPLB_CONTROL_VEL / ACC / JRK: order of the 1-D yaw spline (traj_solver.h:31-36, 86-103)
+ *   wp_offsets   n_traj + 1 ints, wp_offsets[0] = 0: trajectory i owns waypoints wp_offsets[i] .. wp_offsets[i+1]-1; the
+ *                `control` field of a waypoint says which of its derivatives are fixed (use_pos .. use_jrk); its yaw is the
+ *                yaw key frame
+ *   dts          one duration per segment, concatenated: trajectory i owns max(W_i - 1, 0) entries (TrajSolver::setDts)
+ *   coefs        per segment, same concatenation: (dim + 1) rows (the axes, then yaw) of six Primitive coefficients, highest
+ *                order first — Trajectory::segs[s].pr(a).coeff() / pr_yaw().coeff(), i.e. the cx, cy, [cz,] cyaw rows of
+ *                planning_ros_msgs/Primitive
+ *   n_segs       (may be NULL) segments of trajectory i's result: W_i - 1, or 0 where the reference returns an empty
+ *                Trajectory (fewer than two waypoints, solver not initialised)
+ * Host buffers; the _device variant takes wps / dts / coefs in HBM (wp_offsets and n_segs stay host arrays) and orders its
+ * work on `stream`.  FP64, every operation in the reference's order with Eigen's unblocked partial-pivot LU restated
+ * (DESIGN.md section 4.11 states what that pins and the tolerance against a real Eigen build). */
+int mplb_traj_solve_batch(int dim, int control, int yaw_control, int n_traj, const int32_t *wp_offsets, const mplb_waypoint *wps,
+                          const double *dts, double *coefs, int32_t *n_segs);
+int mplb_traj_solve_batch_device(int dim, int control, int yaw_control, int n_traj, const int32_t *wp_offsets, const void *d_wps,
+                                 const void *d_dts, void *d_coefs, int32_t *n_segs, void *stream);
+
 /* Result getters of the retained single plan (two-call pattern: pass cap = 0 to get the size). */
 int mplb_get_actions(mplb_planner *p, int32_t *actions, int cap);      /* returns n_seg; recoverTraj graph_search.h:369-455 */
 int mplb_get_seg_states(mplb_planner *p, double *states13, int cap);   /* returns n_seg */

@@ -70,6 +70,8 @@ SYMBOLS = {
     "mplb_plan_batch_sharded_begin": (_I, [_VP, _VP, _VP, _VP, _I, _I]),
     "mplb_plan_batch_sharded_end": (_I, [_VP, _VP, _I, _VP, _VP, _I]),
     "mplb_sincos_cr": (_I, [_VP, _I, _VP, _VP]),
+    "mplb_traj_solve_batch": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "mplb_traj_solve_batch_device": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mplb_trajectory_msg_size": (C.c_size_t, [_I, C.c_char_p]),
     "mplb_serialize_trajectories_device": (_I, [_VP, _VP, _VP, _VP, _I, _I, _D, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
                                                 _VP, C.c_size_t, _VP, _VP]),

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/mplb.h"
+#include "mplb_internal.h"
 #include "mplb_search.cuh"
 
 using namespace mplb;
@@ -1021,6 +1022,9 @@ int map_alloc(int dim, const int32_t *ndim, const double *origin, double res, mp
 }
 
 }  // namespace
+
+int mplb_internal_fail(int code, const char *msg) { return fail(code, msg ? msg : ""); }
+void mplb_internal_count_launches(int n) { g_launches += n; }
 
 /* ================================================================== C ABI */
 extern "C" {

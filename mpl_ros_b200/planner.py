@@ -72,6 +72,15 @@ class Primitive:
                    4: (0, u[k], j, a, v, p)}[order]
             self.coeffs[k] = row
 
+    @classmethod
+    def from_coeffs(cls, dim, coeffs, yaw_coeff, t, control):
+        """Primitive(cs, t, control), primitive.h:309-313: coefficient rows given directly (TrajSolver output)."""
+        pr = cls.__new__(cls)
+        pr.dim, pr.control, pr.t_ = dim, control, float(t)
+        pr.coeffs = np.array(coeffs, dtype=np.float64).reshape(dim, 6)
+        pr.yaw_coeff = None if yaw_coeff is None else np.array(yaw_coeff, dtype=np.float64)
+        return pr
+
     def t(self):
         return self.t_
 

@@ -25,8 +25,8 @@ NODE_DTYPE = np.dtype([("state", "f8", 13), ("t", "f8"), ("g", "f8"), ("h", "f8"
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "mpl_oracle.cpp")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("mpl_oracle.cpp", "poly_oracle.cpp", "mpl_oracle.h")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -214,3 +214,26 @@ class OraclePlanner:
                                  _ptr(acts) if acts is not None else None, max_seg,
                                  _ptr(order) if order is not None else None, int(bool(pin)), _ptr(busy))
         return (res, acts, busy) if want_busy else (res, acts)
+
+
+def traj_solve(dim, control, wps, dts, yaw_control=1):
+    """TrajSolver<dim>(control, yaw_control): setWaypoints(wps), setDts(dts), solve() (oracle/poly_oracle.cpp).
+    Returns (n_seg, dim + 1, 6) Primitive coefficient rows (axes, then yaw; highest order first)."""
+    L = lib()
+    L.orc_traj_solve.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    wps = np.ascontiguousarray(wps, dtype=WAYPOINT_DTYPE)
+    dts = np.ascontiguousarray(dts, dtype=np.float64)
+    out = np.zeros((max(len(wps) - 1, 1), dim + 1, 6), dtype=np.float64)
+    n = L.orc_traj_solve(dim, int(control), int(yaw_control), len(wps), _ptr(wps), _ptr(dts), _ptr(out))
+    return out[:n]
+
+
+def traj_allocate_time(dim, pts, v):
+    """TrajSolver::allocate_time (traj_solver.h:122-131)."""
+    L = lib()
+    L.orc_traj_allocate_time.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p]
+    p3 = np.zeros((len(pts), 3), dtype=np.float64)
+    p3[:, :dim] = np.asarray(pts, dtype=np.float64)[:, :dim]
+    dts = np.zeros(max(len(pts) - 1, 1), dtype=np.float64)
+    n = L.orc_traj_allocate_time(dim, len(pts), _ptr(p3), float(v), _ptr(dts))
+    return dts[:n]

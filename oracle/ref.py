@@ -19,7 +19,7 @@ def build(force=False):
     """Builds the harness when the reference tree is present; returns the path or None."""
     if not os.path.isdir(REF_ROOT):
         return _SO if os.path.exists(_SO) else None
-    src = [os.path.join(_HERE, "ref_harness.cpp"), os.path.join(_HERE, "mpl_oracle.h")]
+    src = [os.path.join(_HERE, "ref_harness.cpp"), os.path.join(_HERE, "ref_traj_harness.cpp"), os.path.join(_HERE, "mpl_oracle.h")]
     for root, _, files in os.walk(os.path.join(_HERE, "shim")):
         src += [os.path.join(root, f) for f in files]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in src):
@@ -175,3 +175,27 @@ class RefPlanner:
         lib().ref_plan_batch_dyn(self.h, _ptr(starts), _ptr(goals), n, nthreads, _ptr(res),
                                  _ptr(order) if order is not None else None, int(bool(pin)), _ptr(busy))
         return (res, busy) if want_busy else res
+
+
+def traj_solve(dim, control, wps, dts, yaw_control=1):
+    """The reference's TrajSolver<dim> (traj_solver.h:73-109) on explicit waypoints and segment times."""
+    from . import WAYPOINT_DTYPE
+    L = lib()
+    L.ref_traj_solve.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    wps = np.ascontiguousarray(wps, dtype=WAYPOINT_DTYPE)
+    dts = np.ascontiguousarray(dts, dtype=np.float64)
+    out = np.zeros((max(len(wps) - 1, 1), dim + 1, 6), dtype=np.float64)
+    n = L.ref_traj_solve(dim, int(control), int(yaw_control), len(wps), _ptr(wps), _ptr(dts), _ptr(out))
+    return out[:n]
+
+
+def traj_solve_path(dim, control, pts, v):
+    """The reference's setPath / setV / solve flow (MPL/test/test_traj_solver.cpp:29-34). Returns (coefs, dts)."""
+    L = lib()
+    L.ref_traj_solve_path.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    p3 = np.zeros((len(pts), 3), dtype=np.float64)
+    p3[:, :dim] = np.asarray(pts, dtype=np.float64)[:, :dim]
+    out = np.zeros((max(len(pts) - 1, 1), dim + 1, 6), dtype=np.float64)
+    dts = np.zeros(max(len(pts) - 1, 1), dtype=np.float64)
+    n = L.ref_traj_solve_path(dim, int(control), len(pts), _ptr(p3), float(v), _ptr(out), _ptr(dts))
+    return out[:n], dts[:n]

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 REF_TEST = "/root/reference/motion_primitive_library/test"
 OUT = os.path.join(HERE, "_refbin")
 TESTS = ["test_planner_2d", "test_planner_2d_with_yaw", "test_planner_2d_with_prior_traj", "test_distance_map_planner_2d",
-         "test_distance_map_planner_2d_with_yaw", "test_distance_map_planner_2d_iterative"]
+         "test_distance_map_planner_2d_with_yaw", "test_distance_map_planner_2d_iterative", "test_traj_solver"]
 
 
 def available():
@@ -25,7 +25,8 @@ def build(force=False):
     from mpl_ros_b200.build import build_lib
     so = build_lib()
     os.makedirs(OUT, exist_ok=True)
-    deps = [os.path.join(ROOT, "include", "mpl_b200", "map_planner.hpp"), os.path.join(ROOT, "include", "mplb.h"),
+    deps = [os.path.join(ROOT, "include", "mpl_b200", "map_planner.hpp"), os.path.join(ROOT, "include", "mpl_b200", "traj_solver.hpp"),
+            os.path.join(ROOT, "include", "mplb.h"),
             os.path.join(HERE, "standins", "read_map.hpp"), os.path.join(HERE, "standins", "opencv_drawing.hpp"),
             os.path.join(ROOT, "oracle", "shim", "Eigen", "Core")]
     out = {}
