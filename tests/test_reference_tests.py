@@ -58,7 +58,7 @@ EXPECTED_FIRST_POPS = {"test_planner_2d": 615, "test_distance_map_planner_2d": 6
 def test_reference_test_runs_on_gpu(name, tmp_path):
     out, counts, pops = _run(name, tmp_path)
     if name == "test_traj_solver":  # no planner: three splines (min vel / acc / jrk) through four key frames, 3 segments each
-        assert "test_traj_solver: 4 points, 0 circles, 9 trajectory segments" in out, out
+        assert "4 points, 0 circles, 9 trajectory segments" in out, out
         return
     assert pops, out  # every test plans at least once with a verbose planner
     assert "[stand-in drawing]" in out  # the run reached its plotting section, i.e. every planner call returned
