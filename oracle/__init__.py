@@ -78,7 +78,14 @@ def make_waypoints(n=1):
     return np.zeros(n, dtype=WAYPOINT_DTYPE)
 
 
+from .lpa import LpaMixin, map_set_cells as _map_set_cells  # noqa: E402
+
+
 class OracleMap:
+    def set_cells(self, cells, value):
+        """the caller's getMap / edit / setMap (map_replanner_node.cpp:181-196)"""
+        _map_set_cells(lib(), "orc_", self.h, cells, value)
+
     def __init__(self, origin, dim, data, res):
         origin = np.ascontiguousarray(origin, dtype=np.float64)
         dim = np.ascontiguousarray(dim, dtype=np.int32)
@@ -108,8 +115,21 @@ class OracleMap:
             pass
 
 
-class OraclePlanner:
+class OraclePlanner(LpaMixin):
     """Mirrors the reference setters (planner_base.h:179-265) over the oracle."""
+    _lpa_prefix = "orc_"
+
+    @staticmethod
+    def _lpa_lib():
+        return lib()
+
+    def lpa_actions(self):
+        L = lib()
+        L.orc_lpa_get_actions.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        n = L.orc_lpa_get_actions(self.h, None, 0)
+        a = np.zeros(max(n, 1), dtype=np.int32)
+        n = L.orc_lpa_get_actions(self.h, _ptr(a), a.size)
+        return a[:n]
 
     def __init__(self, dim):
         self.dim = dim

@@ -840,6 +840,382 @@ struct Planner {
     }
   }
 
+  /* ================================================================== LPA* 
+   * A literal restatement of GraphSearch::LPAstar (gs:194-365), StateSpace::getSubStateSpace / increaseCost / decreaseCost /
+   * updateNode / calculateKey (ss:116-282), MapPlanner::getLinkedNodes / updateBlockedNodes / updateClearedNodes
+   * (map_planner.cpp:125-185) and env_map::is_free(Primitive) (em:60-76).  Node objects live in `ln` (a new State is a new
+   * entry, like make_shared); hm_ is `lhm` (key -> entry) plus `lorder`, its iteration order, defined as INSERTION order
+   * (Boost leaves it unspecified; see oracle/shim/boost/unordered_map.hpp).  Boost.Heap's erase = unconditional sift-up to the
+   * root, then pop. */
+  struct LNode {
+    WP coord;
+    Key key;
+    std::vector<WP> succ_coord; std::vector<int> succ_act; std::vector<double> succ_cost;
+    std::vector<WP> pred_coord; std::vector<int> pred_act; std::vector<double> pred_cost;
+    int heap_entry = -1;
+    double g = kInf, rhs = kInf, h = kInf;
+    bool opened = false, closed = false;
+  };
+  struct LHeap { /* d_ary_heap<pair<fval, StatePtr>, arity<2>, mutable_<true>, compare_pair> */
+    struct Entry { double f; int node; int pos; };
+    std::vector<Entry> entries;
+    std::vector<int> q;
+    const std::vector<LNode> *nodes = nullptr;
+    bool worse(int ea, int eb) const { /* compare_pair, ss:15-27 */
+      const Entry &a = entries[ea], &b = entries[eb];
+      if (a.f == b.f) {
+        const LNode &na = (*nodes)[a.node], &nb = (*nodes)[b.node];
+        return std::min(na.g, na.rhs) > std::min(nb.g, nb.rhs);
+      }
+      return a.f > b.f;
+    }
+    void place(int pos, int e) { q[pos] = e; entries[e].pos = pos; }
+    void sift_up(int pos, bool force) {
+      while (pos != 0) {
+        int parent = (pos - 1) / 2;
+        if (force || worse(q[parent], q[pos])) { int a = q[parent], b = q[pos]; place(parent, b); place(pos, a); pos = parent; }
+        else return;
+      }
+    }
+    void sift_down(int pos) {
+      int n = (int)q.size();
+      while (2 * pos + 1 < n) {
+        int c = 2 * pos + 1;
+        if (c + 1 < n && worse(q[c], q[c + 1])) c = c + 1;
+        if (!worse(q[c], q[pos])) { int a = q[c], b = q[pos]; place(pos, a); place(c, b); pos = c; }
+        else return;
+      }
+    }
+    int push(double f, int node) {
+      int e = (int)entries.size();
+      entries.push_back({f, node, (int)q.size()});
+      q.push_back(e);
+      sift_up((int)q.size() - 1, false);
+      return e;
+    }
+    void pop() {
+      int last = q.back();
+      int first = q[0];
+      place(0, last);
+      q.pop_back();
+      entries[first].pos = -1;
+      if (!q.empty()) sift_down(0);
+    }
+    void erase(int e) { sift_up(entries[e].pos, true); pop(); }
+    bool empty() const { return q.empty(); }
+    void clear() { q.clear(); entries.clear(); }
+  };
+  std::vector<LNode> ln;
+  std::unordered_map<Key, int, KeyHasher> lhm;
+  std::vector<int> lorder; /* hm_ iteration order */
+  LHeap lpq;
+  std::vector<int> best_child;
+  double l_eps = 1, start_g = 0, start_rhs = 0, start_t = 0;
+  bool lpa_init = false;
+  int l_expand_iteration = 0;
+  std::vector<int> ltraj_actions, ltraj_nodes;
+  std::vector<Key> l_explored; /* nodes whose successors were generated in the last call */
+  bool lpa_fault = false;      /* a step the reference leaves undefined was reached (see lpa_sub_state_space) */
+  /* lhm_ of MapPlanner: voxel index -> (node coord, pred index) in insertion order */
+  std::unordered_map<int, std::vector<std::pair<Key, int>>> linked;
+
+  void lpa_reset() { /* pb:164-167 */
+    ln.clear(); lhm.clear(); lorder.clear(); lpq.clear(); best_child.clear(); lpa_init = false;
+    start_g = start_rhs = start_t = 0; l_expand_iteration = 0; ltraj_actions.clear(); ltraj_nodes.clear(); linked.clear();
+  }
+  int l_find(const Key &k) const { auto it = lhm.find(k); return it == lhm.end() ? -1 : it->second; }
+  int l_new_state(const WP &c) { /* make_shared<State>(coord); h as gs:279-281 */
+    LNode n;
+    n.coord = c;
+    n.key = make_key(c, dim);
+    ln.push_back(n);
+    return (int)ln.size() - 1;
+  }
+  double l_key(int id) const { return std::min(ln[id].g, ln[id].rhs) + l_eps * ln[id].h; } /* ss:270-272 */
+  void l_update_node(int id) { /* ss:242-267 */
+    if (ln[id].rhs != start_rhs) {
+      ln[id].rhs = kInf;
+      for (size_t i = 0; i < ln[id].pred_coord.size(); i++) {
+        const int p = l_find(make_key(ln[id].pred_coord[i], dim));
+        if (ln[id].rhs > ln[p].g + ln[id].pred_cost[i]) ln[id].rhs = ln[p].g + ln[id].pred_cost[i];
+      }
+    }
+    if (ln[id].opened && !ln[id].closed) { lpq.erase(ln[id].heap_entry); ln[id].closed = true; }
+    if (ln[id].g != ln[id].rhs) {
+      ln[id].heap_entry = lpq.push(l_key(id), id);
+      ln[id].opened = true;
+      ln[id].closed = false;
+    }
+  }
+  /* em:60-76 */
+  bool is_free_prim(const Prim &pr) const {
+    double max_v = 0;
+    for (int i = 0; i < dim; i++)
+      if (pr.max_vel(i) > max_v) max_v = pr.max_vel(i);
+    const int n = (int)std::ceil(max_v * pr.T / map->res);
+    const double dts = pr.T / n; /* Primitive::sample, pr:415-420: N + 1 points at i * dt */
+    for (int i = 0; i <= n; i++) {
+      WP pt = pr.evaluate(i * dts);
+      int pn[3] = {0, 0, 0};
+      map->float_to_int(pt.pos, pn);
+      if (map->occupied(pn) || map->outside(pn)) return false;
+      if (!search_region.empty() && !search_region[map->index(pn)]) return false;
+    }
+    return true;
+  }
+
+  int lpa_plan(const WP &start, const WP &goal_) {
+    std::memset(&last, 0, sizeof(last));
+    last.cost = kInf;
+    l_explored.clear();
+    int pn[3] = {0, 0, 0};
+    map->float_to_int(start.pos, pn);
+    if (!map->is_free(pn)) { last.status = 1; return 1; } /* pb:283-287 */
+    if (!lpa_init) { lpa_reset(); lpa_init = true; l_eps = eps; lpq.nodes = &ln; } /* pb:296-304: StateSpace(epsilon_) only once */
+    lpq.nodes = &ln;
+    goal = goal_; /* pb:306 */
+    if (is_goal(start)) { last.status = 5; last.cost = 0; return 5; } /* gs:200-205 */
+    const Key skey = make_key(start, dim);
+    int curr = l_find(skey); /* gs:208: hm_[start_coord] (inserts the slot) */
+    if (curr < 0) {
+      curr = l_new_state(start);
+      ln[curr].g = kInf;
+      ln[curr].rhs = 0;
+      ln[curr].h = l_eps == 0 ? 0 : get_heur(start, skey);
+      ln[curr].heap_entry = lpq.push(l_key(curr), curr);
+      ln[curr].opened = true;
+      ln[curr].closed = false;
+      lhm[skey] = curr;
+      lorder.push_back(curr);
+    }
+    /* gs:224-241: goal node */
+    int goal_node;
+    if (!best_child.empty() && is_goal(ln[best_child.back()].coord)) goal_node = best_child.back();
+    else {
+      goal_node = l_new_state(WP()); /* a detached State(Coord()): never in hm_ */
+      ln[goal_node].g = kInf; ln[goal_node].rhs = kInf; ln[goal_node].h = 0;
+    }
+    int expand_iteration = 0;
+    int status = 0;
+    std::vector<WP> succ; std::vector<double> scost; std::vector<int> sact;
+    while (true) {
+      if (lpq.empty()) { status = 3; break; } /* the reference would read pq_.top() of an empty heap here: undefined; reported as "queue empty" */
+      if (!(lpq.entries[lpq.q[0]].f < l_key(goal_node) || ln[goal_node].rhs != ln[goal_node].g)) break; /* gs:244-245 */
+      expand_iteration++;
+      curr = lpq.entries[lpq.q[0]].node;
+      lpq.pop();
+      ln[curr].closed = true;
+      if (ln[curr].g > ln[curr].rhs) ln[curr].g = ln[curr].rhs; /* gs:252-257 */
+      else { ln[curr].g = kInf; l_update_node(curr); }
+      succ = ln[curr].succ_coord; scost = ln[curr].succ_cost; sact = ln[curr].succ_act; /* gs:261-272 */
+      const bool explored = !ln[curr].succ_coord.empty();
+      if (!explored) {
+        l_explored.push_back(ln[curr].key);
+        last.n_prims += (int64_t)U.size();
+        WP cw = ln[curr].coord;
+        get_succ(cw, succ, scost, sact, nullptr, &last.n_samples);
+        for (double c : scost) if (!std::isinf(c)) last.n_valid++;
+        ln[curr].succ_coord.resize(succ.size()); ln[curr].succ_act.resize(succ.size()); ln[curr].succ_cost.resize(succ.size());
+      }
+      for (size_t s = 0; s < succ.size(); s++) { /* gs:287-316 */
+        const Key sk = make_key(succ[s], dim);
+        int sid = l_find(sk);
+        if (sid < 0) {
+          sid = l_new_state(succ[s]);
+          ln[sid].h = l_eps == 0 ? 0 : get_heur(succ[s], sk);
+          lhm[sk] = sid;
+          lorder.push_back(sid);
+        }
+        ln[curr].succ_coord[s] = succ[s]; ln[curr].succ_act[s] = sact[s]; ln[curr].succ_cost[s] = scost[s];
+        int id = -1;
+        for (size_t i = 0; i < ln[sid].pred_coord.size(); i++)
+          if (make_key(ln[sid].pred_coord[i], dim) == ln[curr].key) { id = (int)i; break; }
+        if (id == -1) {
+          ln[sid].pred_coord.push_back(ln[curr].coord);
+          ln[sid].pred_cost.push_back(scost[s]);
+          ln[sid].pred_act.push_back(sact[s]);
+        }
+        l_update_node(sid);
+      }
+      if (is_goal(ln[curr].coord)) goal_node = curr;                                    /* gs:319 */
+      if (max_num > 0 && expand_iteration >= max_num) { status = 2; break; }            /* gs:322-328 */
+      if (lpq.empty()) { status = 3; break; }                                           /* gs:331-336 */
+    }
+    auto fill = [&]() {
+      last.n_nodes = (int)lorder.size();
+      last.n_open = (int)lpq.q.size();
+      uint64_t ch = 0; int nc = 0;
+      for (int id : lorder) if (ln[id].closed) { ch += key_hash(ln[id].key); nc++; }
+      last.n_closed = nc; last.closed_hash = ch;
+      uint64_t ph = 0xCBF29CE484222325ull;
+      for (const Key &k : l_explored) ph = (ph ^ key_hash(k)) * 0x100000001B3ull;
+      last.pop_hash = ph;
+    };
+    if (status != 0) { last.status = status; last.pops = expand_iteration; fill(); return status; }
+    l_expand_iteration = expand_iteration; /* gs:358 */
+    last.pops = expand_iteration;
+    /* recoverTraj, gs:369-455 (best_child_ rebuilt, traj_ replaced even on failure) */
+    best_child.clear();
+    ltraj_actions.clear(); ltraj_nodes.clear();
+    bool found = false;
+    int c = goal_node;
+    std::vector<int> acts, parents;
+    while (!ln[c].pred_coord.empty()) {
+      best_child.push_back(c);
+      int min_id = -1;
+      double min_rhs = kInf, min_g = kInf;
+      const LNode &cn = ln[c];
+      for (size_t i = 0; i < cn.pred_coord.size(); i++) {
+        const double pg = ln[l_find(make_key(cn.pred_coord[i], dim))].g;
+        if (min_rhs > pg + cn.pred_cost[i]) { min_rhs = pg + cn.pred_cost[i]; min_g = pg; min_id = (int)i; }
+        else if (!std::isinf(cn.pred_cost[i]) && min_rhs == pg + cn.pred_cost[i]) {
+          if (min_g < pg) { min_g = pg; min_id = (int)i; }
+        }
+      }
+      if (min_id >= 0) {
+        acts.push_back(cn.pred_act[min_id]);
+        c = l_find(make_key(cn.pred_coord[min_id], dim));
+        parents.push_back(c);
+      } else break;
+      if (ln[c].key == skey) { best_child.push_back(c); found = true; break; }
+    }
+    std::reverse(best_child.begin(), best_child.end());
+    fill();
+    if (!found) { last.status = 4; return 4; }
+    std::reverse(acts.begin(), acts.end());
+    std::reverse(parents.begin(), parents.end());
+    ltraj_actions = acts; ltraj_nodes = parents;
+    last.n_seg = (int)acts.size();
+    last.cost = ln[goal_node].g - start_g; /* gs:362 */
+    last.status = 0;
+    return 0;
+  }
+
+  /* ss:116-204 */
+  int lpa_sub_state_space(int time_step) {
+    if (best_child.empty() || time_step < 0 || time_step >= (int)best_child.size()) return (int)lorder.size();
+    int curr = best_child[time_step];
+    start_g = ln[curr].g; start_rhs = ln[curr].rhs; start_t = ln[curr].coord.t;
+    ln[curr].pred_cost.clear(); ln[curr].pred_act.clear(); ln[curr].pred_coord.clear();
+    for (int id : lorder) {
+      ln[id].g = kInf; ln[id].rhs = kInf;
+      ln[id].pred_cost.clear(); ln[id].pred_act.clear(); ln[id].pred_coord.clear();
+    }
+    ln[curr].g = start_g; ln[curr].rhs = start_rhs;
+    std::unordered_map<Key, int, KeyHasher> new_hm;
+    std::vector<int> new_order;
+    LHeap epq;
+    epq.nodes = &ln;
+    ln[curr].heap_entry = epq.push(ln[curr].rhs, curr);
+    new_hm[ln[curr].key] = curr; new_order.push_back(curr);
+    while (!epq.empty()) {
+      curr = epq.entries[epq.q[0]].node;
+      epq.pop();
+      for (size_t i = 0; i < ln[curr].succ_coord.size(); i++) {
+        const Key sk = make_key(ln[curr].succ_coord[i], dim);
+        int sid;
+        auto it = new_hm.find(sk);
+        if (it == new_hm.end()) { /* ss:158-159 */
+          sid = l_find(sk);
+          if (sid < 0) { lpa_fault = true; continue; } /* "critical bug!!!!" (ss:160-163): the reference dereferences a null State here */
+          new_hm[sk] = sid; new_order.push_back(sid);
+        } else sid = it->second;
+        int id = -1;
+        for (size_t k = 0; k < ln[sid].pred_coord.size(); k++)
+          if (make_key(ln[sid].pred_coord[k], dim) == ln[curr].key) { id = (int)k; break; }
+        if (id == -1) {
+          ln[sid].pred_coord.push_back(ln[curr].coord);
+          ln[sid].pred_cost.push_back(ln[curr].succ_cost[i]);
+          ln[sid].pred_act.push_back(ln[curr].succ_act[i]);
+        }
+        const double tentative = ln[curr].rhs + ln[curr].succ_cost[i];
+        if (tentative < ln[sid].rhs) {
+          ln[sid].rhs = tentative;
+          if (ln[sid].closed) {
+            ln[sid].g = ln[sid].rhs;
+            ln[sid].heap_entry = epq.push(ln[sid].rhs, sid);
+          }
+        }
+      }
+    }
+    lhm = new_hm; lorder = new_order;
+    lpq.clear();
+    lpq.nodes = &ln;
+    for (int id : lorder)
+      if (ln[id].opened && !ln[id].closed) ln[id].heap_entry = lpq.push(l_key(id), id);
+    return (int)lorder.size();
+  }
+
+  /* map_planner.cpp:125-158 */
+  int lpa_linked_nodes(std::vector<std::array<double, 3>> &pts) {
+    linked.clear();
+    pts.clear();
+    for (int nid : lorder) {
+      const LNode &nd_ = ln[nid];
+      for (size_t i = 0; i < nd_.pred_coord.size(); i++) {
+        const int p = l_find(make_key(nd_.pred_coord[i], dim));
+        Prim pr(ln[p].coord, U[nd_.pred_act[i]].data(), dt, dim);
+        double max_v = 0;
+        for (int k = 0; k < dim; k++) max_v = std::max(max_v, pr.max_vel(k));
+        const int n = (int)(1.0 * std::ceil(max_v * pr.T / map->res));
+        int prev_id = -1;
+        const double dts = pr.T / n;
+        for (int s = 0; s <= n; s++) {
+          WP w = pr.evaluate(s * dts);
+          int pn[3] = {0, 0, 0};
+          map->float_to_int(w.pos, pn);
+          const int id = map->index(pn);
+          if (id != prev_id) {
+            std::array<double, 3> q = {0, 0, 0};
+            for (int k = 0; k < dim; k++) q[k] = (pn[k] + 0.5) * map->res + map->origin[k]; /* intToFloat, mu:110-114 */
+            pts.push_back(q);
+            linked[id].push_back(std::make_pair(nd_.key, (int)i));
+            prev_id = id;
+          }
+        }
+      }
+    }
+    return (int)pts.size();
+  }
+  /* map_planner.cpp:160-185 + ss:207-240 */
+  int lpa_update(const int32_t *pns3, int n, bool blocked) {
+    std::vector<std::pair<Key, int>> affected;
+    for (int i = 0; i < n; i++) {
+      int pn[3] = {pns3[i * 3], pns3[i * 3 + 1], pns3[i * 3 + 2]};
+      const int id = map->index(pn);
+      auto it = linked.find(id);
+      if (it != linked.end()) for (const auto &nd_ : it->second) affected.push_back(nd_);
+    }
+    for (const auto &a : affected) {
+      const int sid = l_find(a.first);
+      const int i = a.second;
+      if (blocked) { /* increaseCost */
+        if (!std::isinf(ln[sid].pred_cost[i])) {
+          ln[sid].pred_cost[i] = kInf;
+          l_update_node(sid);
+          const int p = l_find(make_key(ln[sid].pred_coord[i], dim));
+          const int act = ln[sid].pred_act[i];
+          for (size_t j = 0; j < ln[p].succ_act.size(); j++)
+            if (act == ln[p].succ_act[j]) { ln[p].succ_cost[j] = kInf; break; }
+        }
+      } else { /* decreaseCost */
+        if (std::isinf(ln[sid].pred_cost[i])) {
+          const WP parent_key = ln[sid].pred_coord[i];
+          Prim pr(parent_key, U[ln[sid].pred_act[i]].data(), dt, dim);
+          if (is_free_prim(pr)) {
+            ln[sid].pred_cost[i] = pr.J(pr.control) + w * dt; /* eb:343-345 */
+            l_update_node(sid);
+            const int p = l_find(make_key(parent_key, dim));
+            const int act = ln[sid].pred_act[i];
+            for (size_t j = 0; j < ln[p].succ_act.size(); j++)
+              if (act == ln[p].succ_act[j]) { ln[p].succ_cost[j] = ln[sid].pred_cost[i]; break; }
+          }
+        }
+      }
+    }
+    return (int)affected.size();
+  }
+
   int plan(const WP &start, const WP &goal_) {
     nodes.clear(); hm.clear(); heap = Heap(); pop_order.clear(); traj_actions.clear(); traj_nodes.clear();
     std::memset(&last, 0, sizeof(last));
@@ -1046,6 +1422,85 @@ int64_t orc_map_get_data(void *map, int8_t *out, int64_t cap) {
   int64_t n = (int64_t)m->data.size();
   for (int64_t i = 0; i < n && i < cap; i++) out[i] = m->data[i];
   return n;
+}
+
+void orc_map_set_cells(void *map, const int32_t *cells3, int n, int8_t value) {
+  Map *m = (Map *)map;
+  for (int i = 0; i < n; i++) { int pn[3] = {cells3[i * 3], cells3[i * 3 + 1], cells3[i * 3 + 2]}; m->data[m->index(pn)] = value; }
+}
+void orc_lpa_reset(void *pp) { ((Planner *)pp)->lpa_reset(); }
+int orc_lpa_plan(void *pp, const orc_waypoint *start, const orc_waypoint *goal, orc_result *out) {
+  Planner *p = (Planner *)pp;
+  int st = p->lpa_plan(from_c(*start), from_c(*goal));
+  if (out) *out = p->last;
+  return st;
+}
+int orc_lpa_get_sub_state_space(void *pp, int k) { Planner *p = (Planner *)pp; int n = p->lpa_sub_state_space(k); return p->lpa_fault ? -1 : n; }
+int orc_lpa_get_linked_nodes(void *pp, double *pts3, int cap) {
+  std::vector<std::array<double, 3>> pts;
+  const int n = ((Planner *)pp)->lpa_linked_nodes(pts);
+  for (int i = 0; i < n && i < cap; i++) for (int k = 0; k < 3; k++) pts3[(size_t)i * 3 + k] = pts[i][k];
+  return n;
+}
+int orc_lpa_update_blocked_nodes(void *pp, const int32_t *pns3, int n) { return ((Planner *)pp)->lpa_update(pns3, n, true); }
+int orc_lpa_update_cleared_nodes(void *pp, const int32_t *pns3, int n) { return ((Planner *)pp)->lpa_update(pns3, n, false); }
+static uint64_t lpa_mix(uint64_t h, uint64_t x) { return (h ^ x) * 0x100000001B3ull; }
+static uint64_t lpa_bits(double d) { uint64_t u; std::memcpy(&u, &d, 8); return u; }
+int orc_lpa_dump_nodes(void *pp, orc_lpa_node *nodes, int cap) {
+  Planner *p = (Planner *)pp;
+  int n = 0;
+  for (int id : p->lorder) {
+    if (n < cap) {
+      orc_lpa_node &o = nodes[n];
+      std::memset(&o, 0, sizeof(o));
+      const Planner::LNode &st = p->ln[id];
+      for (int k = 0; k < st.key.n; k++) o.key[k] = st.key.v[k];
+      o.key[15] = st.key.n;
+      o.g = st.g; o.rhs = st.rhs; o.h = st.h; o.opened = st.opened; o.closed = st.closed;
+      o.n_succ = (int)st.succ_coord.size(); o.n_pred = (int)st.pred_coord.size();
+      uint64_t hs = 0xCBF29CE484222325ull, hp = hs;
+      for (size_t i = 0; i < st.succ_coord.size(); i++) hs = lpa_mix(lpa_mix(lpa_mix(hs, key_hash(make_key(st.succ_coord[i], p->dim))), (uint64_t)st.succ_act[i]), lpa_bits(st.succ_cost[i]));
+      for (size_t i = 0; i < st.pred_coord.size(); i++) hp = lpa_mix(lpa_mix(lpa_mix(hp, key_hash(make_key(st.pred_coord[i], p->dim))), (uint64_t)st.pred_act[i]), lpa_bits(st.pred_cost[i]));
+      o.succ_hash = hs; o.pred_hash = hp;
+    }
+    n++;
+  }
+  return n;
+}
+int orc_lpa_dump_heap(void *pp, orc_lpa_heap_entry *e, int cap) {
+  Planner *p = (Planner *)pp;
+  int n = 0;
+  for (int ent : p->lpq.q) {
+    if (n < cap) { e[n].fval = p->lpq.entries[ent].f; e[n].key_hash = key_hash(p->ln[p->lpq.entries[ent].node].key); }
+    n++;
+  }
+  return n;
+}
+int orc_lpa_best_child(void *pp, int32_t *keys16, int cap) {
+  Planner *p = (Planner *)pp;
+  for (int i = 0; i < (int)p->best_child.size() && i < cap; i++) {
+    int32_t *k = keys16 + (size_t)i * 16;
+    std::memset(k, 0, 64);
+    const Key &key = p->ln[p->best_child[i]].key;
+    for (int j = 0; j < key.n; j++) k[j] = key.v[j];
+    k[15] = key.n;
+  }
+  return (int)p->best_child.size();
+}
+int orc_lpa_best_child_states(void *pp, double *states13, int cap) {
+  Planner *p = (Planner *)pp;
+  for (int i = 0; i < (int)p->best_child.size() && i < cap; i++) {
+    const WP &w = p->ln[p->best_child[i]].coord;
+    double *s = states13 + (size_t)i * 13;
+    for (int k = 0; k < 3; k++) { s[k] = w.pos[k]; s[3 + k] = w.vel[k]; s[6 + k] = w.acc[k]; s[9 + k] = w.jrk[k]; }
+    s[12] = w.yaw;
+  }
+  return (int)p->best_child.size();
+}
+int orc_lpa_get_actions(void *pp, int32_t *actions, int cap) {
+  Planner *p = (Planner *)pp;
+  for (int i = 0; i < (int)p->ltraj_actions.size() && i < cap; i++) actions[i] = p->ltraj_actions[i];
+  return (int)p->ltraj_actions.size();
 }
 
 int orc_plan(void *pp, const orc_waypoint *start, const orc_waypoint *goal, orc_result *out) {

@@ -76,6 +76,19 @@ typedef struct orc_node {
   int32_t opened, closed;
 } orc_node;
 
+/* One node of the LPA* state space (State<Coord>, state_space.h:36-70) in hm_ iteration order (insertion order, see
+ * oracle/shim/boost/unordered_map.hpp), for exact comparisons between the oracle, the reference's sources and the CUDA path. */
+typedef struct orc_lpa_node {
+  int32_t key[16];  /* lattice key ints, key[15] = count */
+  double g, rhs, h;
+  int32_t opened, closed, n_succ, n_pred;
+  uint64_t succ_hash, pred_hash; /* order-dependent, over (key hash of the other end, action id, cost bits) of the stored lists */
+} orc_lpa_node;
+typedef struct orc_lpa_heap_entry { /* pq_ in its internal array order */
+  double fval;
+  uint64_t key_hash;
+} orc_lpa_heap_entry;
+
 void *orc_map_create(int dim, const int32_t *ndim, const double *origin, double res, const int8_t *data);
 void orc_map_destroy(void *map);
 void orc_map_free_unknown(void *map);
@@ -120,6 +133,23 @@ int orc_plan_batch(void *p, const orc_waypoint *starts, const orc_waypoint *goal
  * i mod ncores) instead of a static stripe; busy_s[nthreads] (may be NULL) receives each thread's seconds inside plan(). */
 int orc_plan_batch_dyn(void *p, const orc_waypoint *starts, const orc_waypoint *goals, int n, int nthreads,
                        orc_result *results, int32_t *actions, int max_seg, const int32_t *order, int pin, double *busy_s);
+
+/* ---- LPA* (SURVEY section 8f.3): PlannerBase::setLPAstar + plan (planner_base.h:170-176,275-325 -> GraphSearch::LPAstar,
+ * graph_search.h:194-365), getSubStateSpace (state_space.h:116-204), MapPlanner::getLinkedNodes / updateBlockedNodes /
+ * updateClearedNodes (map_planner.cpp:125-185 -> StateSpace::increaseCost / decreaseCost / updateNode, state_space.h:207-282).
+ * The search state persists across orc_lpa_plan calls until orc_lpa_reset. */
+void orc_map_set_cells(void *map, const int32_t *cells3, int n, int8_t value); /* getMap / edit / setMap of the caller (map_replanner_node.cpp:181-196) */
+void orc_lpa_reset(void *p);                                                   /* PlannerBase::reset, planner_base.h:164-167 */
+int orc_lpa_plan(void *p, const orc_waypoint *start, const orc_waypoint *goal, orc_result *out);
+int orc_lpa_get_sub_state_space(void *p, int time_step);                       /* returns hm_.size() afterwards */
+int orc_lpa_get_linked_nodes(void *p, double *pts3, int cap);                  /* returns the number of linked points */
+int orc_lpa_update_blocked_nodes(void *p, const int32_t *pns3, int n);         /* returns the number of (node, pred) pairs handed to increaseCost */
+int orc_lpa_update_cleared_nodes(void *p, const int32_t *pns3, int n);
+int orc_lpa_dump_nodes(void *p, orc_lpa_node *nodes, int cap);                 /* hm_ order; returns hm_.size() */
+int orc_lpa_dump_heap(void *p, orc_lpa_heap_entry *entries, int cap);          /* pq_ array order; returns pq_.size() */
+int orc_lpa_best_child(void *p, int32_t *keys16, int cap);                     /* best_child_ (start .. goal); returns its length */
+int orc_lpa_best_child_states(void *p, double *states13, int cap);             /* stored coords of best_child_ (pos3 vel3 acc3 jrk3 yaw) */
+int orc_lpa_get_actions(void *p, int32_t *actions, int cap);                   /* action ids of the last LPA* trajectory; returns n_seg */
 
 #ifdef __cplusplus
 }

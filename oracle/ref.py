@@ -70,6 +70,10 @@ def lib():
 
 
 class RefMap:
+    def set_cells(self, cells, value):
+        from .lpa import map_set_cells
+        map_set_cells(lib(), "ref_", self.h, cells, value)
+
     def __init__(self, origin, dim, data, res):
         origin = np.ascontiguousarray(origin, dtype=np.float64)
         dim = np.ascontiguousarray(dim, dtype=np.int32)
@@ -96,8 +100,16 @@ class RefMap:
             pass
 
 
-class RefPlanner:
+from .lpa import LpaMixin  # noqa: E402
+
+
+class RefPlanner(LpaMixin):
     """Same call shapes as oracle.OraclePlanner, over the reference's MapPlanner<Dim>."""
+    _lpa_prefix = "ref_"
+
+    @staticmethod
+    def _lpa_lib():
+        return lib()
 
     def __init__(self, dim):
         self.dim = dim

@@ -91,6 +91,16 @@ struct IPlanner {
   virtual int get_nodes(orc_node *nodes, int cap) = 0;
   virtual void set_prior(IPlanner *raw) = 0;
   virtual IPlanner *clone_config() = 0;
+  /* LPA* (graph_search.h:194-365, state_space.h:116-282, map_planner.cpp:125-185) */
+  virtual void lpa_reset() = 0;
+  virtual int lpa_plan(const orc_waypoint &s, const orc_waypoint &g, orc_result *out) = 0;
+  virtual int lpa_sub_state_space(int k) = 0;
+  virtual int lpa_linked_nodes(double *pts3, int cap) = 0;
+  virtual int lpa_update(const int32_t *pns3, int n, bool blocked) = 0;
+  virtual int lpa_dump_nodes(orc_lpa_node *nodes, int cap) = 0;
+  virtual int lpa_dump_heap(orc_lpa_heap_entry *e, int cap) = 0;
+  virtual int lpa_best_child(int32_t *keys16, int cap) = 0;
+  virtual int lpa_best_child_states(double *states13, int cap) = 0;
 };
 
 template <int Dim>
@@ -267,6 +277,108 @@ struct PlannerT : public IPlanner {
     }
     return n;
   }
+  /* ---- LPA*: the reference's own setLPAstar / plan / getSubStateSpace / getLinkedNodes / update*Nodes, recorded */
+  bool lpa_on = false;
+  void lpa_reset() override { pl->reset(); lpa_on = false; }
+  int lpa_plan(const orc_waypoint &s, const orc_waypoint &g, orc_result *out) override {
+    if (!lpa_on) { pl->setLPAstar(true); lpa_on = true; }
+    RecEnv<Dim> *env = pl->env();
+    env->pops.clear(); env->n_prims = 0; env->n_valid = 0;
+    const Waypoint<Dim> ws = to_wp(s), wg = to_wp(g);
+    const bool start_free = env->is_free(ws.pos);
+    bool ok = false;
+    if (start_free) ok = pl->plan(ws, wg);
+    std::memset(&last, 0, sizeof(last));
+    have_traj = false;
+    last.cost = std::numeric_limits<double>::infinity();
+    if (!start_free) last.status = 1;
+    else {
+      if (ok && pl->getTrajCost() == 0 && env->is_goal(ws)) { last.status = 5; last.cost = 0; } /* graph_search.h:200-205 */
+      else if (ok) { last.status = 0; last.cost = pl->getTrajCost(); last.n_seg = (int)pl->traj().segs.size(); have_traj = true; last.pops = pl->ss()->expand_iteration_; }
+      else last.status = -1; /* the reference's bool does not say why */
+      last.n_prims = env->n_prims; last.n_valid = env->n_valid; last.n_samples = -1;
+      if (pl->ss()) {
+        last.n_nodes = (int)pl->ss()->hm_.size();
+        last.n_open = (int)pl->ss()->pq_.size();
+        uint64_t ch = 0;
+        for (const auto &it : pl->ss()->hm_)
+          if (it.second && it.second->iterationclosed) { int32_t k[16]; int n = key_ints(it.second->coord, k); ch += key_hash(k, n); last.n_closed++; }
+        last.closed_hash = ch;
+        uint64_t ph = 0xCBF29CE484222325ull; /* over the nodes whose successors were generated in this call, in order */
+        for (const auto &w : env->pops) { int32_t k[16]; int n = key_ints(w, k); ph = (ph ^ key_hash(k, n)) * 0x100000001B3ull; }
+        last.pop_hash = ph;
+      }
+    }
+    if (out) *out = last;
+    return last.status;
+  }
+  int lpa_sub_state_space(int k) override {
+    if (!pl->ss()) return 0;
+    pl->getSubStateSpace(k);
+    return (int)pl->ss()->hm_.size();
+  }
+  int lpa_linked_nodes(double *pts3, int cap) override {
+    const vec_Vecf<Dim> pts = pl->getLinkedNodes();
+    for (int i = 0; i < (int)pts.size() && i < cap; i++) { for (int k = 0; k < 3; k++) pts3[(size_t)i * 3 + k] = 0; for (int k = 0; k < Dim; k++) pts3[(size_t)i * 3 + k] = pts[i](k); }
+    return (int)pts.size();
+  }
+  int lpa_update(const int32_t *pns3, int n, bool blocked) override {
+    vec_Veci<Dim> pns;
+    for (int i = 0; i < n; i++) { Veci<Dim> v; for (int k = 0; k < Dim; k++) v(k) = pns3[(size_t)i * 3 + k]; pns.push_back(v); }
+    if (blocked) pl->updateBlockedNodes(pns); else pl->updateClearedNodes(pns);
+    return 0;
+  }
+  static uint64_t mix(uint64_t h, uint64_t x) { return (h ^ x) * 0x100000001B3ull; }
+  static uint64_t bits(double d) { uint64_t u; std::memcpy(&u, &d, 8); return u; }
+  int lpa_dump_nodes(orc_lpa_node *nodes, int cap) override {
+    if (!pl->ss()) return 0;
+    int n = 0;
+    for (const auto &it : pl->ss()->hm_) {
+      if (n < cap) {
+        orc_lpa_node &o = nodes[n];
+        std::memset(&o, 0, sizeof(o));
+        if (it.second) {
+          const auto &st = *it.second;
+          o.key[15] = key_ints(st.coord, o.key);
+          o.g = st.g; o.rhs = st.rhs; o.h = st.h; o.opened = st.iterationopened; o.closed = st.iterationclosed;
+          o.n_succ = (int)st.succ_coord.size(); o.n_pred = (int)st.pred_coord.size();
+          uint64_t hs = 0xCBF29CE484222325ull, hp = hs;
+          for (size_t i = 0; i < st.succ_coord.size(); i++) { int32_t k[16]; int m = key_ints(st.succ_coord[i], k); hs = mix(mix(mix(hs, key_hash(k, m)), (uint64_t)st.succ_action_id[i]), bits(st.succ_action_cost[i])); }
+          for (size_t i = 0; i < st.pred_coord.size(); i++) { int32_t k[16]; int m = key_ints(st.pred_coord[i], k); hp = mix(mix(mix(hp, key_hash(k, m)), (uint64_t)st.pred_action_id[i]), bits(st.pred_action_cost[i])); }
+          o.succ_hash = hs; o.pred_hash = hp;
+        }
+      }
+      n++;
+    }
+    return n;
+  }
+  int lpa_dump_heap(orc_lpa_heap_entry *e, int cap) override {
+    if (!pl->ss()) return 0;
+    int n = 0;
+    for (const auto &it : pl->ss()->pq_) {
+      if (n < cap) { int32_t k[16]; int m = key_ints(it.second->coord, k); e[n].fval = it.first; e[n].key_hash = key_hash(k, m); }
+      n++;
+    }
+    return n;
+  }
+  int lpa_best_child(int32_t *keys16, int cap) override {
+    if (!pl->ss()) return 0;
+    const auto &bc = pl->ss()->best_child_;
+    for (int i = 0; i < (int)bc.size() && i < cap; i++) { int32_t *k = keys16 + (size_t)i * 16; std::memset(k, 0, 64); k[15] = key_ints(bc[i]->coord, k); }
+    return (int)bc.size();
+  }
+  int lpa_best_child_states(double *states13, int cap) override {
+    if (!pl->ss()) return 0;
+    const auto &bc = pl->ss()->best_child_;
+    for (int i = 0; i < (int)bc.size() && i < cap; i++) {
+      double *o = states13 + (size_t)i * 13;
+      for (int k = 0; k < 13; k++) o[k] = 0;
+      const Waypoint<Dim> &w = bc[i]->coord;
+      for (int k = 0; k < Dim; k++) { o[k] = w.pos(k); o[3 + k] = w.vel(k); o[6 + k] = w.acc(k); o[9 + k] = w.jrk(k); }
+      o[12] = w.yaw;
+    }
+    return (int)bc.size();
+  }
   IPlanner *clone_config() override { /* same map, parameters, controls and cost shaping; private search state */
     PlannerT<Dim> *c = new PlannerT<Dim>();
     c->params = params; c->U = U;
@@ -385,6 +497,28 @@ void ref_planner_set_prior_trajectory(void *p, void *p_raw) {
   QuietStdout q; /* env_map.h:209,217 print every prior cost unconditionally */
   ((RefPlanner *)p)->p->set_prior(((RefPlanner *)p_raw)->p);
 }
+void ref_map_set_cells(void *map, const int32_t *cells3, int n, int8_t value) { /* getMap / edit / setMap, like map_replanner_node.cpp:181-196 */
+  MapAny *m = (MapAny *)map;
+  if (m->dim == 2) {
+    auto &mu = m->m2.mu; auto d = mu->getMap(); const auto nd = mu->getDim();
+    for (int i = 0; i < n; i++) d[cells3[i * 3] + nd(0) * cells3[i * 3 + 1]] = value;
+    mu->setMap(mu->getOrigin(), nd, d, mu->getRes());
+  } else {
+    auto &mu = m->m3.mu; auto d = mu->getMap(); const auto nd = mu->getDim();
+    for (int i = 0; i < n; i++) d[cells3[i * 3] + nd(0) * cells3[i * 3 + 1] + nd(0) * nd(1) * cells3[i * 3 + 2]] = value;
+    mu->setMap(mu->getOrigin(), nd, d, mu->getRes());
+  }
+}
+void ref_lpa_reset(void *p) { ((RefPlanner *)p)->p->lpa_reset(); }
+int ref_lpa_plan(void *p, const orc_waypoint *s, const orc_waypoint *g, orc_result *out) { QuietStdout q; return ((RefPlanner *)p)->p->lpa_plan(*s, *g, out); }
+int ref_lpa_get_sub_state_space(void *p, int k) { QuietStdout q; return ((RefPlanner *)p)->p->lpa_sub_state_space(k); }
+int ref_lpa_get_linked_nodes(void *p, double *pts3, int cap) { return ((RefPlanner *)p)->p->lpa_linked_nodes(pts3, cap); }
+int ref_lpa_update_blocked_nodes(void *p, const int32_t *pns3, int n) { return ((RefPlanner *)p)->p->lpa_update(pns3, n, true); }
+int ref_lpa_update_cleared_nodes(void *p, const int32_t *pns3, int n) { return ((RefPlanner *)p)->p->lpa_update(pns3, n, false); }
+int ref_lpa_dump_nodes(void *p, orc_lpa_node *nodes, int cap) { return ((RefPlanner *)p)->p->lpa_dump_nodes(nodes, cap); }
+int ref_lpa_dump_heap(void *p, orc_lpa_heap_entry *e, int cap) { return ((RefPlanner *)p)->p->lpa_dump_heap(e, cap); }
+int ref_lpa_best_child_states(void *p, double *states13, int cap) { return ((RefPlanner *)p)->p->lpa_best_child_states(states13, cap); }
+int ref_lpa_best_child(void *p, int32_t *keys16, int cap) { return ((RefPlanner *)p)->p->lpa_best_child(keys16, cap); }
 int ref_get_traj_coeffs(void *p, double *out, int cap_seg) { return ((RefPlanner *)p)->p->get_traj_coeffs(out, cap_seg); }
 int ref_get_pop_keys(void *p, int32_t *keys16, int cap) { return ((RefPlanner *)p)->p->get_pop_keys(keys16, cap); }
 int ref_get_nodes(void *p, orc_node *nodes, int cap) { return ((RefPlanner *)p)->p->get_nodes(nodes, cap); }
