@@ -239,6 +239,54 @@ int mplb_traj_solve_batch(int dim, int control, int yaw_control, int n_traj, con
 int mplb_traj_solve_batch_device(int dim, int control, int yaw_control, int n_traj, const int32_t *wp_offsets, const void *d_wps,
                                  const void *d_dts, void *d_coefs, int32_t *n_segs, void *stream);
 
+/* ---- LPA* incremental replanning (mpl_test_node/src/map_replanner_node.cpp:107-241 is the caller).
+ * The search state of a planner with LPA* enabled stays on the device between plans; each call below is the member of the
+ * same name.  Plain occupancy maps only: a potential map, a search region, a prior trajectory or yaw controls make
+ * mplb_plan fail with MPLB_ERR_ARG while LPA* is on.  Where the reference iterates its hash map (getSubStateSpace re-pushing
+ * the open set, getLinkedNodes filling the voxel -> edge lists) the order is INSERTION order; Boost leaves it unspecified, and
+ * it only decides the order among exact key ties. */
+/* PlannerBase::setLPAstar (planner_base.h:170-176): from now on mplb_plan runs GraphSearch::LPAstar (graph_search.h:194-365)
+ * on the persistent state space; the per-plan outcome uses the same mplb_result (pops = expand_iteration of this call, pop_hash =
+ * over the nodes whose successors were generated in this call; cost = goal g - start_g_, graph_search.h:362).  One outcome is
+ * not the reference's: a plan that begins with an empty priority queue reports MPLB_PLAN_QUEUE_EMPTY where the reference reads
+ * pq_.top() of an empty heap. */
+int mplb_planner_set_lpastar(mplb_planner *p, int on);
+/* PlannerBase::reset (planner_base.h:164-167): drops the state space; the next plan starts from scratch. */
+int mplb_planner_reset(mplb_planner *p);
+/* MapUtil::setMap with an edited copy of getMap(), as add/clearCloudCallback do (map_replanner_node.cpp:181-196,221-229):
+ * n cells (rows of 3 ints, the third ignored in 2D) receive `value`; the occupancy bit-bricks are rebuilt. */
+int mplb_map_set_cells(mplb_map *m, const int32_t *cells3, int n, int value);
+/* StateSpace::getSubStateSpace (state_space.h:116-204) through PlannerBase::getSubStateSpace (planner_base.h:155): the node
+ * best_child_[time_step] of the last trajectory becomes the root.  Returns hm_.size() afterwards (>= 0) or an error. */
+int mplb_get_sub_state_space(mplb_planner *p, int time_step);
+/* MapPlanner::getLinkedNodes (map_planner.cpp:125-158): rebuilds the voxel -> (node, predecessor index) table from every
+ * stored edge and returns the number of linked points; pts3 (may be NULL) receives min(count, cap) rows of 3 doubles. */
+int mplb_get_linked_nodes(mplb_planner *p, double *pts3, int cap);
+/* MapPlanner::updateBlockedNodes / updateClearedNodes (map_planner.cpp:160-185 -> StateSpace::increaseCost / decreaseCost,
+ * state_space.h:207-240) for n changed cells, against the table of the LAST mplb_get_linked_nodes call (like lhm_).  The map
+ * must already hold the new values (mplb_map_set_cells).  Returns the number of (node, predecessor) pairs visited, or an error. */
+int mplb_update_blocked_nodes(mplb_planner *p, const int32_t *cells3, int n);
+int mplb_update_cleared_nodes(mplb_planner *p, const int32_t *cells3, int n);
+/* Many replanners in one launch (one CTA each; e.g. one per robot): every planner must have LPA* enabled and live on the same
+ * device; entry i behaves exactly like mplb_plan(planners[i], &starts[i], &goals[i], &results[i]). */
+int mplb_lpa_plan_batch(mplb_planner **planners, int n, const mplb_waypoint *starts, const mplb_waypoint *goals, mplb_result *results);
+/* State dumps (parity artefacts and getCloseSet / getOpenSet material): hm_ in iteration order, pq_ in its array order,
+ * best_child_ (start .. goal).  Two-call pattern: cap = 0 returns the size. */
+typedef struct mplb_lpa_node {
+  int32_t key[16];   /* lattice ints, key[15] = count */
+  double state[13];  /* the State's coord: pos3 vel3 acc3 jrk3 yaw */
+  double g, rhs, h;
+  int32_t opened, closed, n_succ, n_pred;
+  uint64_t succ_hash, pred_hash; /* order-dependent, over (key hash of the other end, action id, cost bits) of the stored lists */
+} mplb_lpa_node;
+typedef struct mplb_lpa_heap_entry {
+  double fval;       /* the stored key: min(g, rhs) + eps * h at push time (state_space.h:270-272) */
+  uint64_t key_hash; /* of the node's lattice key */
+} mplb_lpa_heap_entry;
+int mplb_lpa_get_nodes(mplb_planner *p, mplb_lpa_node *out, int cap);
+int mplb_lpa_get_heap(mplb_planner *p, mplb_lpa_heap_entry *out, int cap);
+int mplb_lpa_get_best_child(mplb_planner *p, mplb_lpa_node *out, int cap); /* succ_hash / pred_hash left 0 */
+
 /* Result getters of the retained single plan (two-call pattern: pass cap = 0 to get the size). */
 int mplb_get_actions(mplb_planner *p, int32_t *actions, int cap);      /* returns n_seg; recoverTraj graph_search.h:369-455 */
 int mplb_get_seg_states(mplb_planner *p, double *states13, int cap);   /* returns n_seg */

@@ -20,6 +20,9 @@ TRACE_DTYPE = np.dtype([("verdict", "i4"), ("n", "i4"), ("n_tested", "i4"), ("bl
                         ("succ", "f8", 13), ("key", "i4", 16)], align=True)
 NODE_DTYPE = np.dtype([("state", "f8", 13), ("g", "f8"), ("h", "f8"), ("key", "i4", 16), ("opened", "i4"),
                        ("closed", "i4"), ("parent", "i4"), ("action", "i4")], align=True)
+LPA_NODE_DTYPE = np.dtype([("key", "i4", 16), ("state", "f8", 13), ("g", "f8"), ("rhs", "f8"), ("h", "f8"), ("opened", "i4"),
+                           ("closed", "i4"), ("n_succ", "i4"), ("n_pred", "i4"), ("succ_hash", "u8"), ("pred_hash", "u8")], align=True)
+LPA_HEAP_DTYPE = np.dtype([("fval", "f8"), ("key_hash", "u8")], align=True)
 assert WAYPOINT_DTYPE.itemsize == 120 and RESULT_DTYPE.itemsize == 80
 
 # every symbol include/mplb.h declares: (restype, argtypes)
@@ -70,6 +73,17 @@ SYMBOLS = {
     "mplb_plan_batch_sharded_begin": (_I, [_VP, _VP, _VP, _VP, _I, _I]),
     "mplb_plan_batch_sharded_end": (_I, [_VP, _VP, _I, _VP, _VP, _I]),
     "mplb_sincos_cr": (_I, [_VP, _I, _VP, _VP]),
+    "mplb_planner_set_lpastar": (_I, [_VP, _I]),
+    "mplb_planner_reset": (_I, [_VP]),
+    "mplb_map_set_cells": (_I, [_VP, _VP, _I, _I]),
+    "mplb_get_sub_state_space": (_I, [_VP, _I]),
+    "mplb_get_linked_nodes": (_I, [_VP, _VP, _I]),
+    "mplb_update_blocked_nodes": (_I, [_VP, _VP, _I]),
+    "mplb_update_cleared_nodes": (_I, [_VP, _VP, _I]),
+    "mplb_lpa_plan_batch": (_I, [_VP, _I, _VP, _VP, _VP]),
+    "mplb_lpa_get_nodes": (_I, [_VP, _VP, _I]),
+    "mplb_lpa_get_heap": (_I, [_VP, _VP, _I]),
+    "mplb_lpa_get_best_child": (_I, [_VP, _VP, _I]),
     "mplb_traj_solve_batch": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "mplb_traj_solve_batch_device": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mplb_trajectory_msg_size": (C.c_size_t, [_I, C.c_char_p]),

@@ -388,6 +388,7 @@ struct mplb_planner {
   int last_launches = 0, last_tiers = 0;
   /* retained single plan */
   bool retained = false;
+  bool ret_lpa = false; /* the retained plan came from the LPA* unit: no A* arena behind the node getters */
   mplb_result ret_result;
   int ret_cap = 0, ret_ns = 0, ret_slot = 0;
   size_t ret_stride = 0, ret_off_state = 0, ret_off_heap = 0, ret_off_poplog = 0, ret_row_bytes = 0;
@@ -1025,6 +1026,37 @@ int map_alloc(int dim, const int32_t *ndim, const double *origin, double res, mp
 
 int mplb_internal_fail(int code, const char *msg) { return fail(code, msg ? msg : ""); }
 void mplb_internal_count_launches(int n) { g_launches += n; }
+int mplb_internal_planner_cfg(mplb_planner *p, MplbLpaHostCfg *o) {
+  std::memset(o, 0, sizeof(*o));
+  o->dim = p->dim; o->nU = p->nU; o->max_num = p->max_num; o->device = p->device; o->verbose = p->verbose;
+  o->v_max = p->v_max; o->a_max = p->a_max; o->j_max = p->j_max; o->dt = p->dt; o->w = p->w; o->eps = p->eps;
+  o->tol_pos = p->tol_pos; o->tol_vel = p->tol_vel; o->tol_acc = p->tol_acc;
+  o->U = p->U.data();
+  o->shaped = (p->pot_cells != 0 || !p->h_region.empty() || p->prior_nseg != 0 || !p->Uyaw.empty()) ? 1 : 0;
+  o->has_map = p->map != nullptr;
+  if (p->map) {
+    for (int i = 0; i < 3; i++) { o->nd[i] = p->map->nd[i]; o->origin[i] = p->map->origin[i]; }
+    o->res = p->map->res;
+    o->d_grid = p->map->d_grid;
+  }
+  return MPLB_OK;
+}
+void mplb_internal_set_retained(mplb_planner *p, const mplb_result *res, const int *actions, const double *segs13, int n_seg) {
+  p->ret_result = *res;
+  p->ret_actions.assign(actions, actions + n_seg);
+  p->ret_segs.assign(segs13, segs13 + (size_t)n_seg * 13);
+  p->retained = true;
+  p->ret_lpa = true;
+}
+
+/* one thread per edited cell (MapUtil::setMap with an edited copy of getMap(), map_replanner_node.cpp:181-196) */
+__global__ void k_set_cells(int8_t *g, const int *cells3, int n, int dim, int nx, int ny, int nz, int8_t value) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = cells3[i * 3], y = cells3[i * 3 + 1], z = dim == 3 ? cells3[i * 3 + 2] : 0;
+  if (x < 0 || x >= nx || y < 0 || y >= ny || z < 0 || z >= nz) return;
+  g[(size_t)x + (size_t)nx * y + (size_t)nx * ny * z] = value;
+}
 
 /* ================================================================== C ABI */
 extern "C" {
@@ -1082,6 +1114,27 @@ int mplb_map_free_unknown(mplb_map *m) {
   k_free_unknown<<<blocks, 256>>>(m->d_grid, m->ncell);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
+  int rc = m->rebuild_bricks(0);
+  if (rc != MPLB_OK) return rc;
+  CUDA_TRY(cudaStreamSynchronize(0));
+  return MPLB_OK;
+}
+
+int mplb_map_set_cells(mplb_map *m, const int32_t *cells3, int n, int value) {
+  if (!m || (n > 0 && !cells3)) return fail(MPLB_ERR_ARG, "null argument");
+  if (n <= 0) return MPLB_OK;
+  if (set_device_of(m->device)) return fail(MPLB_ERR_CUDA, "cannot select the map's device");
+  int *d = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d, (size_t)n * 3 * sizeof(int)));
+  cudaError_t e = cudaMemcpy(d, cells3, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_set_cells<<<(n + 255) / 256, 256>>>(m->d_grid, d, n, m->dim, m->nd[0], m->nd[1], m->nd[2], (int8_t)value);
+    g_launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(MPLB_ERR_CUDA, std::string("map_set_cells: ") + cudaGetErrorString(e));
   int rc = m->rebuild_bricks(0);
   if (rc != MPLB_OK) return rc;
   CUDA_TRY(cudaStreamSynchronize(0));
@@ -1149,6 +1202,7 @@ int mplb_planner_create(int dim, int verbose, mplb_planner **out) {
 
 void mplb_planner_destroy(mplb_planner *p) {
   if (!p) return;
+  mplb_internal_lpa_drop(p);
   p->d_U.release(); p->d_ttab.release(); p->d_toff.release(); p->d_tcnt.release(); p->arena.release();
   p->d_ctrl.release(); p->d_work.release(); p->d_over.release(); p->d_slot.release(); p->d_starts.release();
   p->d_goals.release(); p->d_results.release(); p->d_actions.release(); p->d_segs.release();
@@ -1477,6 +1531,7 @@ int mplb_plan_batch(mplb_planner *p, const mplb_waypoint *starts, const mplb_way
 
 int mplb_plan(mplb_planner *p, const mplb_waypoint *start, const mplb_waypoint *goal, mplb_result *out) {
   if (!p || !start || !goal || !out) return fail(MPLB_ERR_ARG, "null argument");
+  if (mplb_internal_lpa_enabled(p)) return mplb_internal_lpa_plan(p, start, goal, out); /* PlannerBase::plan with use_lpastar_, pb:308-311 */
   int max_seg = 4096;
   p->ret_actions.assign(max_seg, -1);
   p->ret_segs.assign((size_t)max_seg * 13, 0.0);
@@ -1493,6 +1548,7 @@ int mplb_plan(mplb_planner *p, const mplb_waypoint *start, const mplb_waypoint *
   p->ret_slot = 0;
   CUDA_TRY(cudaMemcpy(&p->ret_slot, p->d_slot.p, sizeof(int), cudaMemcpyDeviceToHost));
   p->retained = true;
+  p->ret_lpa = false;
   if (p->verbose) {
     if (out->status == MPLB_PLAN_START_NOT_FREE) std::printf("[PlannerBase] start is not free!\n");
     else if (out->status == MPLB_PLAN_MAX_EXPAND) std::printf("MaxExpandStep [%d] Reached!!!!!!\n\n", p->max_num);
@@ -1519,6 +1575,7 @@ int mplb_get_seg_states(mplb_planner *p, double *states13, int cap) {
 
 int mplb_get_nodes(mplb_planner *p, mplb_node *nodes, int cap) {
   if (!p || !p->retained) return fail(MPLB_ERR_STATE, "no retained plan");
+  if (p->ret_lpa) return fail(MPLB_ERR_STATE, "the retained plan is an LPA* plan: use mplb_lpa_get_nodes / mplb_lpa_get_heap");
   int n = p->ret_result.n_nodes;
   if (!nodes || cap <= 0) return n;
   if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
@@ -1554,6 +1611,7 @@ int mplb_get_nodes(mplb_planner *p, mplb_node *nodes, int cap) {
 
 int mplb_get_pop_log(mplb_planner *p, int32_t *node_ids, int cap) {
   if (!p || !p->retained) return fail(MPLB_ERR_STATE, "no retained plan");
+  if (p->ret_lpa) return fail(MPLB_ERR_STATE, "the retained plan is an LPA* plan: use mplb_lpa_get_nodes / mplb_lpa_get_heap");
   int n = std::min(p->ret_result.pops, p->ret_cap);
   if (!node_ids || cap <= 0) return n;
   if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");
@@ -1564,6 +1622,7 @@ int mplb_get_pop_log(mplb_planner *p, int32_t *node_ids, int cap) {
 
 int mplb_get_open(mplb_planner *p, int32_t *node_ids, int cap) {
   if (!p || !p->retained) return fail(MPLB_ERR_STATE, "no retained plan");
+  if (p->ret_lpa) return fail(MPLB_ERR_STATE, "the retained plan is an LPA* plan: use mplb_lpa_get_nodes / mplb_lpa_get_heap");
   int n = p->ret_result.n_open;
   if (!node_ids || cap <= 0) return n;
   if (set_device_of(p->device)) return fail(MPLB_ERR_CUDA, "cannot select the planner's device");

@@ -163,6 +163,14 @@ class MapUtil:
                                                 C.c_void_p(int(stream) if stream else None), C.byref(h)))
         self._h = h
 
+    def setCells(self, cells, value):
+        """The caller-side map edit of map_replanner_node.cpp:181-196,221-229 (getMap, write cells, setMap) done in place on
+        the device grid: `cells` rows of Dim ints receive `value` (100 occupied, 0 free)."""
+        c = np.asarray(cells, dtype=np.int32).reshape(len(cells), -1)
+        c3 = np.zeros((len(c), 3), dtype=np.int32)
+        c3[:, :c.shape[1]] = c
+        check(lib().mplb_map_set_cells(self._h, ptr(c3), len(c3), int(value)))
+
     def freeUnknown(self):  # map_util.h:259-276
         check(lib().mplb_map_free_unknown(self._h))
 
@@ -421,6 +429,54 @@ class MapPlanner:
             self.traj_ = Trajectory()
         return st in (PLAN_OK, PLAN_START_IS_GOAL)
 
+    # ---- LPA* (planner_base.h:155-176, map_planner.h:74-87; mpl_test_node/src/map_replanner_node.cpp is the caller)
+    def setLPAstar(self, use_lpastar):  # planner_base.h:170-176
+        check(lib().mplb_planner_set_lpastar(self._h, int(bool(use_lpastar))))
+
+    def getSubStateSpace(self, time_step):  # planner_base.h:155 -> state_space.h:116-204
+        return check(lib().mplb_get_sub_state_space(self._h, int(time_step)))
+
+    def getLinkedNodes(self):  # map_planner.cpp:125-158
+        n = check(lib().mplb_get_linked_nodes(self._h, None, 0))
+        pts = np.zeros((max(n, 1), 3), dtype=np.float64)
+        n = check(lib().mplb_get_linked_nodes(self._h, ptr(pts), pts.shape[0]))
+        return pts[:n, :self.dim]
+
+    def _cells3(self, pns):
+        c = np.asarray(pns, dtype=np.int32).reshape(len(pns), -1)
+        c3 = np.zeros((len(c), 3), dtype=np.int32)
+        c3[:, :c.shape[1]] = c
+        return c3
+
+    def updateBlockedNodes(self, blocked_pns):  # map_planner.cpp:160-171
+        c3 = self._cells3(blocked_pns)
+        return check(lib().mplb_update_blocked_nodes(self._h, ptr(c3), len(c3)))
+
+    def updateClearedNodes(self, cleared_pns):  # map_planner.cpp:173-185
+        c3 = self._cells3(cleared_pns)
+        return check(lib().mplb_update_cleared_nodes(self._h, ptr(c3), len(c3)))
+
+    def lpaNodes(self):
+        """hm_ in iteration order (state dump: key, coord, g, rhs, h, flags, list hashes)"""
+        n = check(lib().mplb_lpa_get_nodes(self._h, None, 0))
+        a = np.zeros(max(n, 1), dtype=_lib.LPA_NODE_DTYPE)
+        n = check(lib().mplb_lpa_get_nodes(self._h, ptr(a), a.size))
+        return a[:n]
+
+    def lpaHeap(self):
+        """pq_ in its internal array order"""
+        n = check(lib().mplb_lpa_get_heap(self._h, None, 0))
+        a = np.zeros(max(n, 1), dtype=_lib.LPA_HEAP_DTYPE)
+        n = check(lib().mplb_lpa_get_heap(self._h, ptr(a), a.size))
+        return a[:n]
+
+    def lpaBestChild(self):
+        """best_child_ of the last LPA* trajectory, start .. goal"""
+        n = check(lib().mplb_lpa_get_best_child(self._h, None, 0))
+        a = np.zeros(max(n, 1), dtype=_lib.LPA_NODE_DTYPE)
+        n = check(lib().mplb_lpa_get_best_child(self._h, ptr(a), a.size))
+        return a[:n]
+
     def result(self):
         return self._last
 
@@ -495,6 +551,7 @@ class MapPlanner:
         return self.getExpandedEdges()
 
     def reset(self):  # planner_base.h:164-167
+        check(lib().mplb_planner_reset(self._h))
         self._initialized = False
         self._last = None
         self.traj_cost_ = None

@@ -1,0 +1,80 @@
+"""Host build of the device LPA* core (tests/cpp/lpa_emul.cpp) behind the LpaMixin call shapes.  TEST INFRASTRUCTURE."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle.lpa import LpaMixin, map_set_cells
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "cpp", "lpa_emul.cpp")
+CORE = os.path.join(HERE, "..", "mpl_ros_b200", "csrc", "mplb_lpa_core.h")
+SO = os.path.join(HERE, "cpp", "_lpa_emul.so")
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(CORE)):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-o", SO + ".tmp", SRC])
+            os.replace(SO + ".tmp", SO)
+        L = C.CDLL(SO)
+        L.emu_map_create.restype = C.c_void_p
+        L.emu_map_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        L.emu_map_destroy.argtypes = [C.c_void_p]
+        L.emu_map_free_unknown.argtypes = [C.c_void_p]
+        L.emu_planner_create.restype = C.c_void_p
+        L.emu_planner_create.argtypes = [C.c_int]
+        L.emu_planner_destroy.argtypes = [C.c_void_p]
+        L.emu_planner_set_map.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_planner_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.emu_planner_set_controls.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.emu_grows.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class EmuMap:
+    def __init__(self, origin, dim, data, res):
+        origin = np.ascontiguousarray(origin, dtype=np.float64)
+        dim = np.ascontiguousarray(dim, dtype=np.int32)
+        data = np.ascontiguousarray(data, dtype=np.int8)
+        self.h = lib().emu_map_create(len(dim), _ptr(dim), _ptr(origin), float(res), _ptr(data))
+
+    def free_unknown(self):
+        lib().emu_map_free_unknown(self.h)
+
+    def set_cells(self, cells, value):
+        map_set_cells(lib(), "emu_", self.h, cells, value)
+
+
+class EmuPlanner(LpaMixin):
+    _lpa_prefix = "emu_"
+
+    @staticmethod
+    def _lpa_lib():
+        return lib()
+
+    def __init__(self, dim):
+        self.dim = dim
+        self.h = lib().emu_planner_create(dim)
+
+    def set_map(self, m):
+        self._map = m
+        lib().emu_planner_set_map(self.h, m.h)
+
+    def set_param(self, key, v):
+        assert lib().emu_planner_set_param(self.h, key.encode(), float(v)) == 0, key
+
+    def set_controls(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        lib().emu_planner_set_controls(self.h, _ptr(U), U.shape[0], U.shape[1])
+
+    def grows(self):
+        return lib().emu_grows(self.h)

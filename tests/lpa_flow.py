@@ -125,3 +125,65 @@ def assert_same(a, b, what=""):
         assert np.array_equal(x["best"], y["best"]), (what, i, "best_child")
         if x["linked"] is not None:
             assert np.array_equal(x["linked"], y["linked"]), (what, i, "linked points")
+
+
+VEL, ACC, JRK = 1, 3, 7
+# name -> (fixture config, control, extra planner parameters, rounds)
+FLOWS = {
+    "corridor_acc": ("corridor", ACC, {}, 3),
+    "skir_acc": ("skir", ACC, {}, 3),
+    "simple_acc": ("simple", ACC, {}, 2),
+    "corridor_eps2": ("corridor", ACC, {"epsilon": 2.0}, 3),
+    "skir_jrk": ("skir", JRK, {"max_num": 30000}, 1),      # 76 657 nodes: outgrows the initial 65 536-node arrays on the GPU
+    "corridor_jrk": ("corridor", JRK, {"max_num": 30000}, 2),
+    "skir_maxnum": ("skir", ACC, {"max_num": 120}, 2),  # the first plans stop at MaxExpandStep and continue from the kept state
+}
+
+
+def path_of_best_child(pl, res):
+    return pl.lpa_best_child_states()[:, :3]
+
+
+def run_flow(name, cls_map, cls_planner, extra=None):
+    cfg, control, params, rounds = FLOWS[name]
+    m, mp_, pl, dim, start, goal = build(cls_map, cls_planner, cfg, dict(params, **(extra or {})))
+    pl._lpa_control = control
+    if name == "skir_maxnum":  # keep planning until the search gets through, like a node that re-triggers the replan
+        return run_until_ok(pl, mp_, m, dim, start, goal, control)
+    return run(pl, mp_, m, dim, start, goal, control, path_of_best_child, n_rounds=rounds), pl
+
+
+def run_until_ok(pl, mp_, m, dim, start, goal, control):
+    snaps = []
+    s, g = oracle.make_waypoints(1), oracle.make_waypoints(1)
+    fill_waypoints(s, start, control)
+    fill_waypoints(g, goal, control)
+    for _ in range(6):
+        res = pl.lpa_plan(s, g)
+        snaps.append(snapshot(pl, res))
+        if res["status"] == 0:
+            break
+    linked = pl.lpa_get_linked_nodes()
+    snaps.append(snapshot(pl, None, linked))
+    return snaps, pl
+
+
+def digest(snaps):
+    """a compact, implementation-independent record of a flow for the committed fixture"""
+    import hashlib
+    rows = []
+    for x in snaps:
+        hsh = hashlib.blake2b(digest_size=8)
+        for f in ("key", "g", "rhs", "h", "opened", "closed", "n_succ", "n_pred", "succ_hash", "pred_hash"):
+            hsh.update(np.ascontiguousarray(x["nodes"][f]).tobytes())
+        hsh.update(np.ascontiguousarray(x["heap"]["fval"]).tobytes())
+        hsh.update(np.ascontiguousarray(x["heap"]["key_hash"]).tobytes())
+        hsh.update(np.ascontiguousarray(x["best"]).tobytes())
+        if x["linked"] is not None:
+            hsh.update(np.ascontiguousarray(x["linked"]).tobytes())
+        r = x["res"]
+        ok = r is not None and int(r["status"]) == 0
+        rows.append((int.from_bytes(hsh.digest(), "little"), len(x["nodes"]), len(x["heap"]), len(x["best"]),
+                     -9 if r is None else (0 if ok else (5 if int(r["status"]) == 5 else 1 if int(r["status"]) == 1 else -1)),
+                     float(r["cost"]) if ok else 0.0, int(r["pops"]) if ok else 0))
+    return np.array(rows, dtype=[("digest", "u8"), ("n_nodes", "i8"), ("n_heap", "i8"), ("n_best", "i8"), ("status", "i8"), ("cost", "f8"), ("pops", "i8")])
