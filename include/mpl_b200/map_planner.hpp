@@ -314,7 +314,17 @@ class MapUtil {
   MapUtil &operator=(const MapUtil &) = delete;
 
   void setMap(const Vecf<Dim> &ori, const Veci<Dim> &dim, const Tmap &map, decimal_t res) { /* map_util.h:84-90 */
-    if (h_) { mplb_map_destroy(h_); h_ = nullptr; }
+    if (h_) { /* same geometry (the replanner's getMap / edit / setMap, map_replanner_node.cpp:181-196): new cells in place, so
+                 that planners sharing this MapUtil keep seeing it, as they do through the reference's shared_ptr */
+      bool same = res == res_;
+      for (int i = 0; i < Dim; i++) same = same && dim(i) == dim_(i) && ori(i) == origin_d_(i);
+      if (same) {
+        if (mplb_map_set_data(h_, reinterpret_cast<const int8_t *>(map.data())) != MPLB_OK) std::printf("[MapUtil] setMap failed: %s\n", mplb_last_error());
+        return;
+      }
+      mplb_map_destroy(h_);
+      h_ = nullptr;
+    }
     int32_t nd[3] = {1, 1, 1};
     double o[3] = {0, 0, 0};
     for (int i = 0; i < Dim; i++) { nd[i] = dim(i); o[i] = ori(i); }
@@ -412,6 +422,7 @@ class MapPlanner {
 
   void setMapUtil(const std::shared_ptr<MapUtil<Dim>> &map_util) { /* map_planner.cpp:14-18 */
     map_util_ = map_util;
+    bound_map_ = map_util ? map_util->handle() : nullptr;
     if (h_ && map_util && mplb_planner_set_map(h_, map_util->handle()) != MPLB_OK) report();
   }
   bool initialized() { return initialized_; }
@@ -428,7 +439,29 @@ class MapPlanner {
   void setHeurIgnoreDynamics(bool ignore) { /* planner_base.h:233: only the default (true) is on this path */
     if (!ignore) std::printf("[MapPlanner] heur_ignore_dynamics = false is not supported (env_base.h:67-211 needs a polynomial root finder)\n");
   }
-  void reset() { traj_ = Trajectory<Dim>(); initialized_ = false; last_ = mplb_result{}; } /* planner_base.h:164-167 */
+  void reset() { /* planner_base.h:164-167 */
+    traj_ = Trajectory<Dim>(); initialized_ = false; last_ = mplb_result{};
+    if (h_) mplb_planner_reset(h_);
+  }
+  /* ---- LPA* (planner_base.h:155,170-176; map_planner.h:74-87; caller: mpl_test_node/src/map_replanner_node.cpp) */
+  void setLPAstar(bool use_lpastar) { /* planner_base.h:170-176 */
+    use_lpastar_ = use_lpastar;
+    if (h_ && mplb_planner_set_lpastar(h_, use_lpastar ? 1 : 0) != MPLB_OK) report();
+    if (use_lpastar_) std::printf("[PlannerBase] use Lifelong Planning A*\n");
+    else std::printf("[PlannerBase] use normal A*\n");
+  }
+  void getSubStateSpace(int time_step) { if (h_ && mplb_get_sub_state_space(h_, time_step) < 0) report(); } /* planner_base.h:155 */
+  vec_Vecf<Dim> getLinkedNodes() const { /* map_planner.cpp:125-158 */
+    vec_Vecf<Dim> pts;
+    const int n = h_ ? mplb_get_linked_nodes(h_, nullptr, 0) : 0;
+    if (n <= 0) return pts;
+    std::vector<double> p3((size_t)n * 3);
+    mplb_get_linked_nodes(h_, p3.data(), n);
+    for (int i = 0; i < n; i++) { Vecf<Dim> q; for (int k = 0; k < Dim; k++) q(k) = p3[(size_t)i * 3 + k]; pts.push_back(q); }
+    return pts;
+  }
+  void updateBlockedNodes(const vec_Veci<Dim> &blocked_pns) { update_nodes(blocked_pns, true); }  /* map_planner.cpp:160-171 */
+  void updateClearedNodes(const vec_Veci<Dim> &cleared_pns) { update_nodes(cleared_pns, false); } /* map_planner.cpp:173-185 */
   void setPriorTrajectory(const Trajectory<Dim> &traj) { /* planner_base.h:249-252 */
     const auto &segs = traj.segs;
     std::vector<double> cs(segs.size() * 24, 0.0), ts(segs.size(), 0.0);
@@ -455,6 +488,7 @@ class MapPlanner {
   bool plan(const Coord &start, const Coord &goal) {
     mplb_waypoint s = to_c(start), g = to_c(goal);
     control_ = start.control;
+    if (h_ && map_util_ && map_util_->handle() != bound_map_) setMapUtil(map_util_); /* the MapUtil re-created its grid since */
     /* traj_ is rewritten only where the reference writes it: recoverTraj's success or failure (graph_search.h:447-451);
      * start-not-free (planner_base.h:283-287), start-is-goal (graph_search.h:44), MaxExpandStep and the empty queue
      * (graph_search.h:149-161) leave the previous trajectory in place. */
@@ -481,8 +515,9 @@ class MapPlanner {
   Trajectory<Dim> getTraj() const { return traj_; }          /* planner_base.h:28 */
   decimal_t getTrajCost() const { return traj_cost_; }       /* planner_base.h:155 */
   int getExpandedNum() const { return last_.pops; }          /* planner_base.h:148 */
-  vec_Vecf<Dim> getCloseSet() const { return node_points(2, false); }     /* planner_base.h:84-91 */
+  vec_Vecf<Dim> getCloseSet() const { return use_lpastar_ ? lpa_points(0) : node_points(2, false); }     /* planner_base.h:84-91 */
   vec_Vecf<Dim> getOpenSet() const {                                       /* planner_base.h:77-81 */
+    if (use_lpastar_) return lpa_points(1);
     std::vector<mplb_node> nodes = fetch_nodes();
     std::vector<int32_t> ids(last_.n_open > 0 ? last_.n_open : 1);
     mplb_get_open(h_, ids.data(), (int)ids.size());
@@ -491,6 +526,7 @@ class MapPlanner {
     return ps;
   }
   vec_Vecf<Dim> getExpandedNodes() const {                                 /* planner_base.h:140, env_map.h:154 */
+    if (use_lpastar_) return vec_Vecf<Dim>(); /* the per-call expansion log is kept for A* plans only */
     std::vector<mplb_node> nodes = fetch_nodes();
     std::vector<int32_t> ids(last_.pops > 0 ? last_.pops : 1);
     int n = mplb_get_pop_log(h_, ids.data(), (int)ids.size());
@@ -627,6 +663,25 @@ class MapPlanner {
     return ps;
   }
 
+  /* LPA* state space through the dumps: which = 0 closed members of hm_ (planner_base.h:84-91), 1 = the open list */
+  vec_Vecf<Dim> lpa_points(int which) const {
+    vec_Vecf<Dim> ps;
+    const int n = h_ ? mplb_lpa_get_nodes(h_, nullptr, 0) : 0;
+    if (n <= 0) return ps;
+    std::vector<mplb_lpa_node> nodes(n);
+    mplb_lpa_get_nodes(h_, nodes.data(), n);
+    for (const auto &nd : nodes)
+      if ((which == 0 && nd.closed) || (which == 1 && nd.opened && !nd.closed)) { Vecf<Dim> q; for (int k = 0; k < Dim; k++) q(k) = nd.state[k]; ps.push_back(q); }
+    return ps;
+  }
+  void update_nodes(const vec_Veci<Dim> &pns, bool blocked) {
+    std::vector<int32_t> c3(pns.size() * 3, 0);
+    for (size_t i = 0; i < pns.size(); i++) for (int k = 0; k < Dim; k++) c3[i * 3 + k] = pns[i](k);
+    const int rc = blocked ? mplb_update_blocked_nodes(h_, c3.data(), (int)pns.size()) : mplb_update_cleared_nodes(h_, c3.data(), (int)pns.size());
+    if (rc < 0) report();
+  }
+  bool use_lpastar_ = false;
+  mplb_map *bound_map_ = nullptr;
   mplb_planner *h_ = nullptr;
   std::shared_ptr<MapUtil<Dim>> map_util_;
   vec_E<VecDf> U_;

@@ -246,8 +246,8 @@ int mplb_traj_solve_batch_device(int dim, int control, int yaw_control, int n_tr
  * the open set, getLinkedNodes filling the voxel -> edge lists) the order is INSERTION order; Boost leaves it unspecified, and
  * it only decides the order among exact key ties. */
 /* PlannerBase::setLPAstar (planner_base.h:170-176): from now on mplb_plan runs GraphSearch::LPAstar (graph_search.h:194-365)
- * on the persistent state space; the per-plan outcome uses the same mplb_result (pops = expand_iteration of this call, pop_hash =
- * over the nodes whose successors were generated in this call; cost = goal g - start_g_, graph_search.h:362).  One outcome is
+ * on the persistent state space; the per-plan outcome uses the same mplb_result record: pops = expand_iteration of this call, pop_hash =
+ * over the nodes whose successors were generated in this call, cost = goal g - start_g_ as graph_search.h:362.  One outcome is
  * not the reference's: a plan that begins with an empty priority queue reports MPLB_PLAN_QUEUE_EMPTY where the reference reads
  * pq_.top() of an empty heap. */
 int mplb_planner_set_lpastar(mplb_planner *p, int on);
@@ -256,6 +256,9 @@ int mplb_planner_reset(mplb_planner *p);
 /* MapUtil::setMap with an edited copy of getMap(), as add/clearCloudCallback do (map_replanner_node.cpp:181-196,221-229):
  * n cells (rows of 3 ints, the third ignored in 2D) receive `value`; the occupancy bit-bricks are rebuilt. */
 int mplb_map_set_cells(mplb_map *m, const int32_t *cells3, int n, int value);
+/* MapUtil::setMap again on a map of unchanged geometry: the whole int8 grid is replaced in place, so planners that share the
+ * map (setMapUtil keeps a shared pointer in the reference) see the new cells without being re-pointed. */
+int mplb_map_set_data(mplb_map *m, const int8_t *data);
 /* StateSpace::getSubStateSpace (state_space.h:116-204) through PlannerBase::getSubStateSpace (planner_base.h:155): the node
  * best_child_[time_step] of the last trajectory becomes the root.  Returns hm_.size() afterwards (>= 0) or an error. */
 int mplb_get_sub_state_space(mplb_planner *p, int time_step);

@@ -76,6 +76,7 @@ SYMBOLS = {
     "mplb_planner_set_lpastar": (_I, [_VP, _I]),
     "mplb_planner_reset": (_I, [_VP]),
     "mplb_map_set_cells": (_I, [_VP, _VP, _I, _I]),
+    "mplb_map_set_data": (_I, [_VP, _VP]),
     "mplb_get_sub_state_space": (_I, [_VP, _I]),
     "mplb_get_linked_nodes": (_I, [_VP, _VP, _I]),
     "mplb_update_blocked_nodes": (_I, [_VP, _VP, _I]),

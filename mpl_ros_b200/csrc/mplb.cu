@@ -1120,6 +1120,16 @@ int mplb_map_free_unknown(mplb_map *m) {
   return MPLB_OK;
 }
 
+int mplb_map_set_data(mplb_map *m, const int8_t *data) {
+  if (!m || !data) return fail(MPLB_ERR_ARG, "null argument");
+  if (set_device_of(m->device)) return fail(MPLB_ERR_CUDA, "cannot select the map's device");
+  CUDA_TRY(cudaMemcpy(m->d_grid, data, m->ncell, cudaMemcpyHostToDevice));
+  int rc = m->rebuild_bricks(0);
+  if (rc != MPLB_OK) return rc;
+  CUDA_TRY(cudaStreamSynchronize(0));
+  return MPLB_OK;
+}
+
 int mplb_map_set_cells(mplb_map *m, const int32_t *cells3, int n, int value) {
   if (!m || (n > 0 && !cells3)) return fail(MPLB_ERR_ARG, "null argument");
   if (n <= 0) return MPLB_OK;
