@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -242,9 +243,12 @@ struct Session {
   }
 };
 
-std::unordered_map<mplb_planner *, Session *> g_sessions;
+std::unordered_map<mplb_planner *, Session *> g_sessions; /* planner -> its replanning session; the registry is locked, a
+                                                              session itself is as non-re-entrant as its planner (env_base.h:402-404) */
+std::mutex g_sessions_mu;
 
 Session *session_of(mplb_planner *p, bool create) {
+  std::lock_guard<std::mutex> lock(g_sessions_mu);
   auto it = g_sessions.find(p);
   if (it != g_sessions.end()) return it->second;
   if (!create) return nullptr;
@@ -367,7 +371,7 @@ int plan_sessions(std::vector<mplb_planner *> &ps, const mplb_waypoint *starts, 
   /* the batch's contexts, contiguous */
   Session *lead = ss[0];
   const int max_seg = 4096;
-  Buf<Ctx> ctxs;
+  struct CtxArray : Buf<Ctx> { ~CtxArray() { release(); } } ctxs; /* freed on every return path */
   LPA_CUDA(ctxs.grow(n, 0));
   for (int i = 0; i < n; i++) LPA_CUDA(cudaMemcpy(ctxs.p + i, &ss[i]->h, sizeof(Ctx), cudaMemcpyHostToDevice));
   LPA_CUDA(lead->wps.grow((size_t)2 * n, 0));
@@ -376,33 +380,32 @@ int plan_sessions(std::vector<mplb_planner *> &ps, const mplb_waypoint *starts, 
   LPA_CUDA(lead->segs.grow((size_t)n * max_seg * 13, 0));
   LPA_CUDA(cudaMemcpy(lead->wps.p, starts, (size_t)n * sizeof(mplb_waypoint), cudaMemcpyHostToDevice));
   LPA_CUDA(cudaMemcpy(lead->wps.p + n, goals, (size_t)n * sizeof(mplb_waypoint), cudaMemcpyHostToDevice));
-  for (int i = 0; i < n; i++) { Hdr hd; int rc = read_hdr(ss[i], &hd); if (rc) { ctxs.release(); return rc; } hd.resume = 0; hd.status = 0; rc = write_hdr(ss[i], hd); if (rc) { ctxs.release(); return rc; } }
+  for (int i = 0; i < n; i++) { Hdr hd; int rc = read_hdr(ss[i], &hd); if (rc) return rc; hd.resume = 0; hd.status = 0; rc = write_hdr(ss[i], hd); if (rc) return rc; }
   for (int round = 0; round < 64; round++) {
     k_lpa_plan<<<n, 32>>>(ctxs.p, lead->wps.p, lead->wps.p + n, lead->res.p, lead->acts.p, lead->segs.p, max_seg);
     mplb_internal_count_launches(1);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { ctxs.release(); return mplb_internal_fail(MPLB_ERR_CUDA, (std::string("k_lpa_plan: ") + cudaGetErrorString(e)).c_str()); }
+    if (e != cudaSuccess) return mplb_internal_fail(MPLB_ERR_CUDA, (std::string("k_lpa_plan: ") + cudaGetErrorString(e)).c_str());
     bool again = false;
     for (int i = 0; i < n; i++) {
       Hdr hd;
       int rc = read_hdr(ss[i], &hd);
-      if (rc) { ctxs.release(); return rc; }
+      if (rc) return rc;
       if (hd.status == LPA_NEED_GROW) { /* stopped before a pop that could overflow: double and resume */
         rc = ensure_capacity(ss[i], ss[i]->cap_nodes * 2, ss[i]->cap_pred * 2, true);
-        if (rc) { ctxs.release(); return rc; }
+        if (rc) return rc;
         LPA_CUDA(cudaMemcpy(ctxs.p + i, &ss[i]->h, sizeof(Ctx), cudaMemcpyHostToDevice));
         again = true;
       }
     }
     if (!again) break;
   }
-  ctxs.release();
   LPA_CUDA(cudaMemcpy(results, lead->res.p, (size_t)n * sizeof(mplb_result), cudaMemcpyDeviceToHost));
   std::vector<int> acts;
   std::vector<double> segs;
   for (int i = 0; i < n; i++) { /* retained trajectory for mplb_get_actions / mplb_get_seg_states (traj_ stays as it was on failure) */
-    ss[i]->have_links = ss[i]->have_links; /* lhm_ is NOT refreshed by plan(): it is whatever getLinkedNodes built last */
+    /* lhm_ is NOT refreshed by plan(): the link table stays whatever getLinkedNodes built last (map_planner.cpp:127) */
     if (results[i].status != MPLB_PLAN_OK) continue;
     const int ns = std::min(results[i].n_seg, max_seg);
     acts.resize(std::max(ns, 1));
@@ -503,6 +506,7 @@ int mplb_internal_lpa_plan(mplb_planner *p, const mplb_waypoint *start, const mp
   return plan_sessions(ps, start, goal, out);
 }
 void mplb_internal_lpa_drop(mplb_planner *p) {
+  std::lock_guard<std::mutex> lock(g_sessions_mu);
   auto it = g_sessions.find(p);
   if (it == g_sessions.end()) return;
   it->second->release();
