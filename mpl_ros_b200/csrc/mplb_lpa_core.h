@@ -728,8 +728,11 @@ MPLB_HDN int recover(const Ctx &x, int *n_seg, double *cost) {
   *cost = LPA_INF;
   if (h.goal_node < 0) return LPA_TRACEBACK_FAILED; /* the detached goal State has no predecessors */
   int cur = h.goal_node, na = 0;
-  bool found = false;
+  bool found = false, cycle = false;
   while (x.nodes[cur].pred_head >= 0) {
+    if (h.n_best > h.n_order) { cycle = true; break; } /* more steps than hm_ has members: a cycle of best predecessors.  The
+                                                          reference's loop (gs:377-438) would never return; the trace-back fails
+                                                          and best_child_ is left empty */
     x.best[h.n_best++] = cur;
     int min_p = -1;
     double min_rhs = LPA_INF, min_g = LPA_INF;
@@ -745,8 +748,8 @@ MPLB_HDN int recover(const Ctx &x, int *n_seg, double *cost) {
     x.traj_act[na++] = x.preds[min_p].act;
     cur = x.preds[min_p].node;
     if (key_eq(x.nodes[cur].key, h.start_key, c.nkey)) { x.best[h.n_best++] = cur; found = true; break; }
-    if (na >= h.cap_nodes - 1 || h.n_best >= h.cap_nodes - 1) break; /* a predecessor cycle: the reference would not return */
   }
+  if (cycle) { h.n_best = 0; h.fault |= 2; return LPA_TRACEBACK_FAILED; }
   for (int i = 0; i < h.n_best / 2; i++) { const int t = x.best[i]; x.best[i] = x.best[h.n_best - 1 - i]; x.best[h.n_best - 1 - i] = t; }
   if (!found) return LPA_TRACEBACK_FAILED;
   for (int i = 0; i < na / 2; i++) { const int t = x.traj_act[i]; x.traj_act[i] = x.traj_act[na - 1 - i]; x.traj_act[na - 1 - i] = t; }

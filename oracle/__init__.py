@@ -123,6 +123,9 @@ class OraclePlanner(LpaMixin):
     def _lpa_lib():
         return lib()
 
+    def lpa_last_fault(self):
+        return lib().orc_lpa_last_fault(self.h)
+
     def lpa_actions(self):
         L = lib()
         L.orc_lpa_get_actions.argtypes = [C.c_void_p, C.c_void_p, C.c_int]

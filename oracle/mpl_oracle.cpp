@@ -916,6 +916,7 @@ struct Planner {
   std::vector<int> ltraj_actions, ltraj_nodes;
   std::vector<Key> l_explored; /* nodes whose successors were generated in the last call */
   bool lpa_fault = false;      /* a step the reference leaves undefined was reached (see lpa_sub_state_space) */
+  bool lpa_cycle = false;      /* the last trace-back ran into a predecessor cycle (the reference would not terminate) */
   /* lhm_ of MapPlanner: voxel index -> (node coord, pred index) in insertion order */
   std::unordered_map<int, std::vector<std::pair<Key, int>>> linked;
 
@@ -968,6 +969,7 @@ struct Planner {
     std::memset(&last, 0, sizeof(last));
     last.cost = kInf;
     l_explored.clear();
+    lpa_cycle = false;
     int pn[3] = {0, 0, 0};
     map->float_to_int(start.pos, pn);
     if (!map->is_free(pn)) { last.status = 1; return 1; } /* pb:283-287 */
@@ -1061,6 +1063,11 @@ struct Planner {
     int c = goal_node;
     std::vector<int> acts, parents;
     while (!ln[c].pred_coord.empty()) {
+      if (best_child.size() > lorder.size()) { /* more steps than hm_ has members: a cycle of best predecessors.  The reference's loop
+                                                  (gs:377-438) would never return; here the trace-back fails and best_child_ is left empty */
+        lpa_cycle = true;
+        break;
+      }
       best_child.push_back(c);
       int min_id = -1;
       double min_rhs = kInf, min_g = kInf;
@@ -1080,6 +1087,7 @@ struct Planner {
       if (ln[c].key == skey) { best_child.push_back(c); found = true; break; }
     }
     std::reverse(best_child.begin(), best_child.end());
+    if (lpa_cycle) { best_child.clear(); found = false; }
     fill();
     if (!found) { last.status = 4; return 4; }
     std::reverse(acts.begin(), acts.end());
@@ -1497,6 +1505,7 @@ int orc_lpa_best_child_states(void *pp, double *states13, int cap) {
   }
   return (int)p->best_child.size();
 }
+int orc_lpa_last_fault(void *pp) { Planner *p = (Planner *)pp; return (p->lpa_fault ? 1 : 0) | (p->lpa_cycle ? 2 : 0); }
 int orc_lpa_get_actions(void *pp, int32_t *actions, int cap) {
   Planner *p = (Planner *)pp;
   for (int i = 0; i < (int)p->ltraj_actions.size() && i < cap; i++) actions[i] = p->ltraj_actions[i];

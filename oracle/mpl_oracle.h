@@ -149,6 +149,8 @@ int orc_lpa_dump_nodes(void *p, orc_lpa_node *nodes, int cap);                 /
 int orc_lpa_dump_heap(void *p, orc_lpa_heap_entry *entries, int cap);          /* pq_ array order; returns pq_.size() */
 int orc_lpa_best_child(void *p, int32_t *keys16, int cap);                     /* best_child_ (start .. goal); returns its length */
 int orc_lpa_best_child_states(void *p, double *states13, int cap);             /* stored coords of best_child_ (pos3 vel3 acc3 jrk3 yaw) */
+int orc_lpa_last_fault(void *p); /* bit 0: getSubStateSpace met a successor that is no longer in hm_ (state_space.h:160-163 dereferences null);
+                                    bit 1: the last trace-back met a predecessor cycle (graph_search.h:377-438 would not terminate) */
 int orc_lpa_get_actions(void *p, int32_t *actions, int cap);                   /* action ids of the last LPA* trajectory; returns n_seg */
 
 #ifdef __cplusplus
