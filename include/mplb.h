@@ -239,6 +239,19 @@ int mplb_traj_solve_batch(int dim, int control, int yaw_control, int n_traj, con
 int mplb_traj_solve_batch_device(int dim, int control, int yaw_control, int n_traj, const int32_t *wp_offsets, const void *d_wps,
                                  const void *d_dts, void *d_coefs, int32_t *n_segs, void *stream);
 
+/* The refinement step of map_planner_node.cpp:216-227 for a whole batch without leaving the device: for every successful plan of
+ * mplb_plan_batch(_device) (same max_seg; results, actions and seg_states are all required) the waypoints of its trajectory
+ * (Trajectory::getWaypoints, trajectory.h:277-289: the stored coord of every segment's parent and the last primitive evaluated at
+ * its duration), the interior ones re-flagged Control::VEL, the two ends keeping plan_control (the control flags the batch was planned
+ * with), the planner's dt as every segment time, then TrajSolver<Dim>(control, yaw_control)::solve.  coefs: n * max_seg segments of
+ * (dim + 1) rows x 6 coefficients (plan i at i * max_seg; zero where nothing was refined); n_segs (HOST, may be NULL): refined segments
+ * per plan, 0 for failed or truncated plans.  A gather kernel (one thread per waypoint) followed by the batched solve. */
+int mplb_refine_trajectories_device(mplb_planner *p, const void *d_results, const void *d_actions, const void *d_seg_states, int n,
+                                    int max_seg, int plan_control, int control, int yaw_control, void *d_coefs, int32_t *n_segs,
+                                    void *stream);
+int mplb_refine_trajectories(mplb_planner *p, const mplb_result *results, const int32_t *actions, const double *seg_states, int n,
+                             int max_seg, int plan_control, int control, int yaw_control, double *coefs, int32_t *n_segs);
+
 /* ---- LPA* incremental replanning (mpl_test_node/src/map_replanner_node.cpp:107-241 is the caller).
  * The search state of a planner with LPA* enabled stays on the device between plans; each call below is the member of the
  * same name.  Plain occupancy maps only: a potential map, a search region, a prior trajectory or yaw controls make

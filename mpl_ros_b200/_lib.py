@@ -85,6 +85,8 @@ SYMBOLS = {
     "mplb_lpa_get_nodes": (_I, [_VP, _VP, _I]),
     "mplb_lpa_get_heap": (_I, [_VP, _VP, _I]),
     "mplb_lpa_get_best_child": (_I, [_VP, _VP, _I]),
+    "mplb_refine_trajectories_device": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP]),
+    "mplb_refine_trajectories": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _VP]),
     "mplb_traj_solve_batch": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "mplb_traj_solve_batch_device": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mplb_trajectory_msg_size": (C.c_size_t, [_I, C.c_char_p]),

@@ -1032,6 +1032,7 @@ int mplb_internal_planner_cfg(mplb_planner *p, MplbLpaHostCfg *o) {
   o->v_max = p->v_max; o->a_max = p->a_max; o->j_max = p->j_max; o->dt = p->dt; o->w = p->w; o->eps = p->eps;
   o->tol_pos = p->tol_pos; o->tol_vel = p->tol_vel; o->tol_acc = p->tol_acc;
   o->U = p->U.data();
+  o->Uyaw = p->Uyaw.empty() ? nullptr : p->Uyaw.data();
   o->shaped = (p->pot_cells != 0 || !p->h_region.empty() || p->prior_nseg != 0 || !p->Uyaw.empty()) ? 1 : 0;
   o->has_map = p->map != nullptr;
   if (p->map) {

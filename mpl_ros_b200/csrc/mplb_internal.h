@@ -25,6 +25,7 @@ struct MplbLpaHostCfg {
   double res;
   const int8_t *d_grid; /* the map's int8 cells on the planner's device */
   const double *U;      /* host, nU rows of 3 */
+  const double *Uyaw;   /* host, nU yaw rates, or NULL when the control rows carry none */
 };
 MPLB_HIDDEN int mplb_internal_planner_cfg(mplb_planner *p, MplbLpaHostCfg *out);
 /* the retained single plan the getters mplb_get_actions / mplb_get_seg_states serve */

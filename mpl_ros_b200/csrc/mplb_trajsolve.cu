@@ -367,28 +367,15 @@ thread_local TsScratch g_jobs, g_ws, g_wps, g_dts, g_coefs;
     if (e__ != cudaSuccess) return mplb_internal_fail(MPLB_ERR_CUDA, (std::string(#expr) + ": " + cudaGetErrorString(e__)).c_str()); \
   } while (0)
 
-int ts_launch(int dim, int control, int yaw_control, int n_traj, const int32_t *wp_offsets, const mplb_waypoint *d_wps,
-              const double *d_dts, double *d_coefs, int32_t *n_segs, cudaStream_t stream) {
-  int Np, Rp, Ny, Ry;
-  const bool ok = ts_orders(control, &Np, &Rp) && (yaw_control == 1 || yaw_control == 3 || yaw_control == 7) &&
-                  ts_orders(yaw_control, &Ny, &Ry);
-  std::vector<TsJob> jobs;
+/* launches the solve for `jobs` (wp_off / n_wp / seg_off filled by the caller; ws_off is assigned here) */
+int ts_run(int dim, int Np, int Rp, int Ny, int Ry, int yaw_control, std::vector<TsJob> &jobs, const mplb_waypoint *d_wps,
+           const double *d_dts, double *d_coefs, cudaStream_t stream) {
   size_t ws_total = 0, ws_max = 0;
-  int seg_off = 0;
-  for (int i = 0; i < n_traj; i++) {
-    const int W = wp_offsets[i + 1] - wp_offsets[i];
-    const int slots = std::max(W - 1, 0);
-    const int nseg = ok ? slots : 0; /* an uninitialised solver or < 2 waypoints give an empty Trajectory */
-    if (n_segs) n_segs[i] = nseg;
-    const int my_off = seg_off;
-    seg_off += slots;
-    if (!nseg) continue;
-    TsJob j;
-    j.wp_off = wp_offsets[i] - wp_offsets[0]; j.n_wp = W; j.seg_off = my_off; j.pad = 0; j.ws_off = (long long)ws_total;
-    const size_t a = ts_ws_doubles(W, Np, dim), b = ts_ws_doubles(W, Ny, 1);
+  for (TsJob &j : jobs) {
+    j.ws_off = (long long)ws_total;
+    const size_t a = ts_ws_doubles(j.n_wp, Np, dim), b = ts_ws_doubles(j.n_wp, Ny, 1);
     ws_total += a + b;
     ws_max = std::max(ws_max, std::max(a, b));
-    jobs.push_back(j);
   }
   if (jobs.empty()) return MPLB_OK;
   int dev = 0, smem_optin = 0;
@@ -400,7 +387,11 @@ int ts_launch(int dim, int control, int yaw_control, int n_traj, const int32_t *
   for (const TsJob &j : jobs)
     if (std::max(ts_ws_doubles(j.n_wp, Np, dim), ts_ws_doubles(j.n_wp, Ny, 1)) * sizeof(double) > smem_bytes) need_global = true;
   TS_CUDA(g_jobs.reserve(jobs.size() * sizeof(TsJob)));
-  if (need_global) TS_CUDA(g_ws.reserve(ws_total * sizeof(double)));
+  if (need_global) {
+    /* the dense formulation is O(W^2) memory per trajectory like the reference's (segments*N)^2 matrices: refuse absurd sizes */
+    if (ws_total * sizeof(double) > ((size_t)8 << 30)) return mplb_internal_fail(MPLB_ERR_NOMEM, "traj_solve: work space above 8 GiB (waypoint lists this long are out of this solver's range)");
+    TS_CUDA(g_ws.reserve(ws_total * sizeof(double)));
+  }
   TS_CUDA(cudaMemcpyAsync(g_jobs.p, jobs.data(), jobs.size() * sizeof(TsJob), cudaMemcpyHostToDevice, stream));
   TS_CUDA(cudaFuncSetAttribute(k_traj_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   k_traj_solve<<<dim3((unsigned)jobs.size(), 2), TS_THREADS, smem_bytes, stream>>>(
@@ -410,6 +401,93 @@ int ts_launch(int dim, int control, int yaw_control, int n_traj, const int32_t *
   TS_CUDA(cudaStreamSynchronize(stream)); /* the job list is reused by the next call */
   return MPLB_OK;
 }
+
+int ts_launch(int dim, int control, int yaw_control, int n_traj, const int32_t *wp_offsets, const mplb_waypoint *d_wps,
+              const double *d_dts, double *d_coefs, int32_t *n_segs, cudaStream_t stream) {
+  int Np = 0, Rp = 0, Ny = 0, Ry = 0;
+  const bool ok = ts_orders(control, &Np, &Rp) && (yaw_control == 1 || yaw_control == 3 || yaw_control == 7) &&
+                  ts_orders(yaw_control, &Ny, &Ry);
+  std::vector<TsJob> jobs;
+  int seg_off = 0;
+  for (int i = 0; i < n_traj; i++) {
+    const int W = wp_offsets[i + 1] - wp_offsets[i];
+    const int slots = std::max(W - 1, 0);
+    const int nseg = ok ? slots : 0; /* an uninitialised solver or < 2 waypoints give an empty Trajectory */
+    if (n_segs) n_segs[i] = nseg;
+    const int my_off = seg_off;
+    seg_off += slots;
+    if (!nseg) continue;
+    TsJob j;
+    j.wp_off = wp_offsets[i] - wp_offsets[0]; j.n_wp = W; j.seg_off = my_off; j.pad = 0; j.ws_off = 0;
+    jobs.push_back(j);
+  }
+  return ts_run(dim, Np, Rp, Ny, Ry, yaw_control, jobs, d_wps, d_dts, d_coefs, stream);
+}
+
+/* Trajectory::getWaypoints (trajectory.h:277-289) of every plan of a batch, written as the waypoint lists the solver reads:
+ * waypoint j < n_seg = the stored coord of segment j's parent (Primitive::evaluate(0) returns the coefficients c5, c4, c3, c2
+ * = that state exactly), waypoint n_seg = the last primitive evaluated at its duration (pr:321-331 in the reference's term
+ * order); the two ends keep the plan's control flags, the interior ones become Control::VEL (map_planner_node.cpp:217-219).
+ * One thread per (plan, waypoint); plan i owns slots [i * (max_seg + 1), ...). */
+__global__ void k_gather_waypoints(const mplb_result *res, const int *actions, const double *segs, int n, int max_seg, int dim,
+                                   int plan_control, const double *U, const double *Uyaw, double dt, mplb_waypoint *wps, double *dts) {
+  const int per = max_seg + 1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * per) return;
+  const int i = (int)(idx / per), j = (int)(idx % per);
+  const int ns = res[i].n_seg;
+  if (res[i].status != MPLB_PLAN_OK || ns < 1 || ns > max_seg || j > ns) return;
+  mplb_waypoint w;
+  memset(&w, 0, sizeof(w));
+  const int cc = plan_control & 15;
+  const int ord = cc == 1 ? 1 : cc == 3 ? 2 : cc == 7 ? 3 : 4;
+  if (j < ns) {
+    const double *st = segs + ((size_t)i * max_seg + j) * 13;
+    for (int k = 0; k < 3; k++) { w.pos[k] = st[k]; w.vel[k] = st[3 + k]; w.acc[k] = st[6 + k]; w.jrk[k] = st[9 + k]; }
+    w.yaw = st[12];
+    dts[(size_t)i * max_seg + j] = dt;
+  } else {
+    const double *st = segs + ((size_t)i * max_seg + ns - 1) * 13;
+    const int a = actions[(size_t)i * max_seg + ns - 1];
+    const double t = dt;
+    for (int k = 0; k < dim; k++) { /* c = (0, [u | 0], ..., v, p) by control order, evaluated like pr:128-145 */
+      double c[6] = {0, 0, 0, 0, 0, 0};
+      const double u = U[a * 3 + k];
+      if (ord == 4) { c[1] = u; c[2] = st[9 + k]; c[3] = st[6 + k]; c[4] = st[3 + k]; c[5] = st[k]; }
+      else if (ord == 3) { c[2] = u; c[3] = st[6 + k]; c[4] = st[3 + k]; c[5] = st[k]; }
+      else if (ord == 2) { c[3] = u; c[4] = st[3 + k]; c[5] = st[k]; }
+      else { c[4] = u; c[5] = st[k]; }
+      const double t2 = __dmul_rn(t, t), t3 = __dmul_rn(t2, t), t4 = __dmul_rn(t3, t), t5 = __dmul_rn(t4, t);
+      double p = __dmul_rn(__ddiv_rn(c[0], 120), t5);
+      p = __dadd_rn(p, __dmul_rn(__ddiv_rn(c[1], 24), t4));
+      p = __dadd_rn(p, __dmul_rn(__ddiv_rn(c[2], 6), t3));
+      p = __dadd_rn(p, __dmul_rn(__dmul_rn(__ddiv_rn(c[3], 2), t), t));
+      p = __dadd_rn(p, __dmul_rn(c[4], t));
+      w.pos[k] = __dadd_rn(p, c[5]);
+      double v = __dmul_rn(__ddiv_rn(c[0], 24), t4);
+      v = __dadd_rn(v, __dmul_rn(__ddiv_rn(c[1], 6), t3));
+      v = __dadd_rn(v, __dmul_rn(__dmul_rn(__ddiv_rn(c[2], 2), t), t));
+      v = __dadd_rn(v, __dmul_rn(c[3], t));
+      w.vel[k] = __dadd_rn(v, c[4]);
+      double ac = __dmul_rn(__ddiv_rn(c[0], 6), t3);
+      ac = __dadd_rn(ac, __dmul_rn(__dmul_rn(__ddiv_rn(c[1], 2), t), t));
+      ac = __dadd_rn(ac, __dmul_rn(c[2], t));
+      w.acc[k] = __dadd_rn(ac, c[3]);
+      w.jrk[k] = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(__ddiv_rn(c[0], 2), t), t), __dmul_rn(c[1], t)), c[2]);
+    }
+    if ((plan_control & 16) && Uyaw) { /* pr_yaw_.p(t) = c4 t + c5 with the zero terms in front, then normalize_angle (math.h:15-19) */
+      double y = __dadd_rn(__dmul_rn(Uyaw[a], t), st[12]);
+      while (y > 3.14159265358979323846) y = __dsub_rn(y, __dmul_rn(2.0, 3.14159265358979323846));
+      while (y < -3.14159265358979323846) y = __dadd_rn(y, __dmul_rn(2.0, 3.14159265358979323846));
+      w.yaw = y;
+    }
+  }
+  w.t = __dmul_rn((double)j, dt);
+  w.control = (j == 0 || j == ns) ? plan_control : MPLB_CONTROL_VEL;
+  wps[(size_t)i * per + j] = w;
+}
+
+thread_local TsScratch g_pwps, g_pdts, g_pU, g_pres;
 
 }  // namespace
 
@@ -424,6 +502,72 @@ int mplb_traj_solve_batch_device(int dim, int control, int yaw_control, int n_tr
     if (wp_offsets[i + 1] < wp_offsets[i]) return mplb_internal_fail(MPLB_ERR_ARG, "traj_solve: offsets must not decrease");
   return ts_launch(dim, control, yaw_control, n_traj, wp_offsets, (const mplb_waypoint *)d_wps, (const double *)d_dts,
                    (double *)d_coefs, n_segs, (cudaStream_t)stream);
+}
+
+int mplb_refine_trajectories_device(mplb_planner *p, const void *d_results, const void *d_actions, const void *d_seg_states, int n,
+                                    int max_seg, int plan_control, int control, int yaw_control, void *d_coefs, int32_t *n_segs,
+                                    void *stream_) {
+  if (!p || !d_results || !d_actions || !d_seg_states || !d_coefs || n < 0 || max_seg < 1) return mplb_internal_fail(MPLB_ERR_ARG, "refine: bad argument");
+  if (n == 0) return MPLB_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MplbLpaHostCfg hc;
+  mplb_internal_planner_cfg(p, &hc);
+  if (hc.nU <= 0) return mplb_internal_fail(MPLB_ERR_STATE, "refine: no controls set");
+  TS_CUDA(cudaSetDevice(hc.device));
+  int Np = 0, Rp = 0, Ny = 0, Ry = 0;
+  const bool ok = ts_orders(control, &Np, &Rp) && (yaw_control == 1 || yaw_control == 3 || yaw_control == 7) && ts_orders(yaw_control, &Ny, &Ry);
+  std::vector<mplb_result> res(n);
+  TS_CUDA(cudaMemcpyAsync(res.data(), d_results, (size_t)n * sizeof(mplb_result), cudaMemcpyDeviceToHost, stream));
+  TS_CUDA(cudaStreamSynchronize(stream));
+  const int per = max_seg + 1;
+  std::vector<TsJob> jobs;
+  for (int i = 0; i < n; i++) {
+    const bool good = ok && res[i].status == MPLB_PLAN_OK && res[i].n_seg >= 1 && res[i].n_seg <= max_seg;
+    if (n_segs) n_segs[i] = good ? res[i].n_seg : 0;
+    if (!good) continue;
+    TsJob j;
+    j.wp_off = i * per; j.n_wp = res[i].n_seg + 1; j.seg_off = i * max_seg; j.pad = 0; j.ws_off = 0;
+    jobs.push_back(j);
+  }
+  TS_CUDA(g_pwps.reserve((size_t)n * per * sizeof(mplb_waypoint)));
+  TS_CUDA(g_pdts.reserve((size_t)n * max_seg * sizeof(double)));
+  TS_CUDA(g_pU.reserve((size_t)hc.nU * 4 * sizeof(double)));
+  TS_CUDA(cudaMemcpyAsync(g_pU.p, hc.U, (size_t)hc.nU * 3 * sizeof(double), cudaMemcpyHostToDevice, stream));
+  double *d_Uyaw = nullptr;
+  if (hc.Uyaw) {
+    d_Uyaw = (double *)g_pU.p + (size_t)hc.nU * 3;
+    TS_CUDA(cudaMemcpyAsync(d_Uyaw, hc.Uyaw, (size_t)hc.nU * sizeof(double), cudaMemcpyHostToDevice, stream));
+  }
+  TS_CUDA(cudaMemsetAsync(d_coefs, 0, (size_t)n * max_seg * (hc.dim + 1) * 6 * sizeof(double), stream));
+  const long long total = (long long)n * per;
+  k_gather_waypoints<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const mplb_result *)d_results, (const int *)d_actions,
+                                                                           (const double *)d_seg_states, n, max_seg, hc.dim, plan_control,
+                                                                           (const double *)g_pU.p, d_Uyaw, hc.dt, (mplb_waypoint *)g_pwps.p,
+                                                                           (double *)g_pdts.p);
+  mplb_internal_count_launches(1);
+  TS_CUDA(cudaGetLastError());
+  return ts_run(hc.dim, Np, Rp, Ny, Ry, yaw_control, jobs, (const mplb_waypoint *)g_pwps.p, (const double *)g_pdts.p, (double *)d_coefs, stream);
+}
+
+int mplb_refine_trajectories(mplb_planner *p, const mplb_result *results, const int32_t *actions, const double *seg_states, int n,
+                             int max_seg, int plan_control, int control, int yaw_control, double *coefs, int32_t *n_segs) {
+  if (!p || !results || !actions || !seg_states || !coefs || n < 0 || max_seg < 1) return mplb_internal_fail(MPLB_ERR_ARG, "refine: bad argument");
+  if (n == 0) return MPLB_OK;
+  MplbLpaHostCfg hc;
+  mplb_internal_planner_cfg(p, &hc);
+  TS_CUDA(cudaSetDevice(hc.device));
+  const size_t nc = (size_t)n * max_seg * (hc.dim + 1) * 6;
+  TS_CUDA(g_pres.reserve((size_t)n * sizeof(mplb_result)));
+  TS_CUDA(g_wps.reserve((size_t)n * max_seg * sizeof(int)));         /* staging: actions */
+  TS_CUDA(g_dts.reserve((size_t)n * max_seg * 13 * sizeof(double))); /* staging: segment states */
+  TS_CUDA(g_coefs.reserve(nc * sizeof(double)));
+  TS_CUDA(cudaMemcpy(g_pres.p, results, (size_t)n * sizeof(mplb_result), cudaMemcpyHostToDevice));
+  TS_CUDA(cudaMemcpy(g_wps.p, actions, (size_t)n * max_seg * sizeof(int), cudaMemcpyHostToDevice));
+  TS_CUDA(cudaMemcpy(g_dts.p, seg_states, (size_t)n * max_seg * 13 * sizeof(double), cudaMemcpyHostToDevice));
+  const int rc = mplb_refine_trajectories_device(p, g_pres.p, g_wps.p, g_dts.p, n, max_seg, plan_control, control, yaw_control, g_coefs.p, n_segs, nullptr);
+  if (rc != MPLB_OK) return rc;
+  TS_CUDA(cudaMemcpy(coefs, g_coefs.p, nc * sizeof(double), cudaMemcpyDeviceToHost));
+  return MPLB_OK;
 }
 
 int mplb_traj_solve_batch(int dim, int control, int yaw_control, int n_traj, const int32_t *wp_offsets, const mplb_waypoint *wps,

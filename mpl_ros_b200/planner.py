@@ -571,6 +571,20 @@ class MapPlanner:
         check(lib().mplb_plan_batch_device(self._h, vp(d_starts), vp(d_goals), n, vp(d_results), vp(d_actions), vp(d_segs),
                                            max_seg, vp(stream)))
 
+    def refine_trajectories(self, results, actions, seg_states, plan_control, control=JRK, yaw_control=VEL):
+        """map_planner_node.cpp:216-227 for every plan of a batch (waypoints of the planned trajectory, interior ones flagged
+        Control::VEL, the planner's dt per segment, TrajSolver<Dim>(control, yaw_control)) — gathered and solved on the GPU.
+        Returns (coefs [n, max_seg, dim + 1, 6], n_segs [n])."""
+        n, max_seg = int(actions.shape[0]), int(actions.shape[1])
+        results = np.ascontiguousarray(results)
+        actions = np.ascontiguousarray(actions, dtype=np.int32)
+        seg_states = np.ascontiguousarray(seg_states, dtype=np.float64)
+        coefs = np.zeros((n, max_seg, self.dim + 1, 6), dtype=np.float64)
+        nseg = np.zeros(max(n, 1), dtype=np.int32)
+        check(lib().mplb_refine_trajectories(self._h, ptr(results), ptr(actions), ptr(seg_states), n, max_seg, int(plan_control),
+                                             int(control), int(yaw_control), ptr(coefs), ptr(nseg)))
+        return coefs, nseg[:n]
+
     def serialize_trajectories(self, results, actions, seg_states, z=0.0, frame_id="map", seq=0, stamp=(0, 0)):
         """toTrajectoryROSMsg + ROS 1 serialisation of planning_ros_msgs/Trajectory for every plan of a batch
         (primitive_ros_utils.h:62-113, map_planner_node.cpp:55-57,206-208), written by the GPU.  Returns a list of

@@ -122,3 +122,56 @@ def test_conditioning_margin():
     pert = traj_solver.solve_batch(3, JRK, [w2], [d2])[0]
     rel = np.abs(pert - base).max() / np.abs(base).max()
     assert rel < 1e-9, rel
+
+
+def test_refine_batch_on_device():
+    """plan_batch -> mplb_refine_trajectories (gather kernel + batched solve): every successful plan's refined trajectory equals
+    the oracle's TrajSolver on the waypoints the reference's node would build (map_planner_node.cpp:216-227); the end waypoint is
+    the last primitive evaluated at dt, taken here from the oracle's get_succ row of the last parent state."""
+    from mpl_ros_b200 import maps
+    m = maps.load_fixture("skir")
+    U = maps.make_U(1.0, 1, 3)
+    mu = mp.VoxelMapUtil()
+    mu.setMap(m.origin, m.dim, m.data, m.res)
+    mu.freeUnknown()
+    pl = mp.VoxelMapPlanner(False)
+    pl.setMapUtil(mu)
+    pl.setVmax(2.0); pl.setAmax(1.0); pl.setDt(1.0); pl.setU(U); pl.setTol(0.5)
+    om = oracle.OracleMap(m.origin, m.dim, m.data, m.res)
+    om.free_unknown()
+    op = oracle.OraclePlanner(3)
+    op.set_map(om)
+    for k, v in dict(v_max=2.0, a_max=1.0, dt=1.0, tol_pos=0.5).items():
+        op.set_param(k, v)
+    op.set_controls(U)
+    starts, goals = maps.sample_queries(m, 24, seed=5, min_dist=1.5)
+    s, g = mp.waypoints_array(24), mp.waypoints_array(24)
+    s["pos"], g["pos"] = starts, goals
+    s["control"] = g["control"] = mp.ACC
+    max_seg = 16
+    res, acts, segs = pl.plan_batch(s, g, max_seg=max_seg, want_states=True)
+    coefs, nseg = pl.refine_trajectories(res, acts, segs, mp.ACC, mp.JRK)
+    n_ok = 0
+    for i in range(24):
+        good = res[i]["status"] == 0 and 1 <= res[i]["n_seg"] <= max_seg
+        assert nseg[i] == (res[i]["n_seg"] if good else 0)
+        if not good:
+            assert not coefs[i].any()
+            continue
+        ns = int(res[i]["n_seg"])
+        w = oracle.make_waypoints(ns + 1)
+        for j in range(ns):
+            st = segs[i, j]
+            w["pos"][j], w["vel"][j], w["acc"][j], w["jrk"][j], w["yaw"][j] = st[0:3], st[3:6], st[6:9], st[9:12], st[12]
+        last = oracle.make_waypoints(1)
+        last["pos"][0], last["vel"][0], last["acc"][0] = segs[i, ns - 1, 0:3], segs[i, ns - 1, 3:6], segs[i, ns - 1, 6:9]
+        last["control"] = mp.ACC
+        end = op.succ_trace(last)[acts[i, ns - 1]]["succ"]
+        w["pos"][ns], w["vel"][ns], w["acc"][ns], w["jrk"][ns], w["yaw"][ns] = end[0:3], end[3:6], end[6:9], end[9:12], end[12]
+        w["control"] = mp.VEL
+        w["control"][0] = w["control"][ns] = mp.ACC
+        want = oracle.traj_solve(3, mp.JRK, w, np.ones(ns))
+        assert np.array_equal(coefs[i, :ns], want), i
+        assert not coefs[i, ns:].any()
+        n_ok += 1
+    assert n_ok >= 5
