@@ -66,13 +66,17 @@ def workload(name):
                 mem_fraction=0.85)
 
 
+SEARCH_UNITS = ("mplb.cu", "mplb_device.cuh", "mplb_search.cuh", "mplb_trig.cuh")  # the search kernel and its launch code
+
+
 def src_sha():
-    """Hash of the kernel sources: profiles/traffic.json entries are only trusted for the code they were captured on."""
+    """Hash of the sources of the search kernel and of the host code that launches it: profiles/traffic.json entries are
+    only trusted for the code they were captured on (the LPA* and TrajSolver units are separate translation units that the
+    bench launch never touches)."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "mpl_ros_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
-            h.update(open(os.path.join(d, f), "rb").read())
+    for f in SEARCH_UNITS:
+        h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 
 

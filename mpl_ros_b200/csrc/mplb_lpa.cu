@@ -54,7 +54,8 @@ k_lpa_plan(Ctx *ctxs, const mplb_waypoint *starts, const mplb_waypoint *goals, m
   if (lane == 0) {
     x = ctxs[b];
     int st = -1;
-    if (!x.h->resume) {
+    if (x.h->resume == 2) st = -3; /* this session finished in an earlier launch of the same batch (another one had to grow) */
+    else if (!x.h->resume) {
       double sst[13], gst[13];
       wp_to_state(starts[b], sst);
       wp_to_state(goals[b], gst);
@@ -64,6 +65,7 @@ k_lpa_plan(Ctx *ctxs, const mplb_waypoint *starts, const mplb_waypoint *goals, m
   }
   __syncwarp();
   int code = s_code;
+  if (code == -3) return;
   const int nU = x.cfg.nU;
   while (code == -1) {
     if (lane == 0) s_code = pop_begin(x);
@@ -90,7 +92,7 @@ k_lpa_plan(Ctx *ctxs, const mplb_waypoint *starts, const mplb_waypoint *goals, m
   __shared__ int s_nseg;
   __shared__ double s_cost;
   if (lane == 0) {
-    h.resume = 0;
+    h.resume = 2; /* done: a relaunch of the batch for a growing neighbour must not plan this one again */
     int n_seg = 0;
     double cost = LPA_INF;
     if (code == LPA_OK) code = recover(x, &n_seg, &cost);

@@ -137,17 +137,19 @@ def test_trajectory_actions_and_reset():
 def test_batch_of_replanners():
     """one CTA per robot: mplb_lpa_plan_batch over independent planners equals planning them one by one"""
     import ctypes as C
-    names = ["skir", "skir", "skir", "skir"]
-    goals = [(1.5, 1.5, 5.5), (5.5, 1.5, 0.5), (1.5, 5.5, 0.5), (3.5, 3.5, 3.5)]
-    planners, singles = [], []
-    for nm in names:
-        planners.append(lpa_flow.build(GpuMap, GpuPlanner, nm))
-        singles.append(lpa_flow.build(GpuMap, GpuPlanner, nm))
+    names = ["skir", "skir", "skir", "skir", "skir"]
+    goals = [(1.5, 1.5, 5.5), (5.5, 1.5, 0.5), (1.5, 5.5, 0.5), (3.5, 3.5, 3.5), (1.5, 1.5, 5.5)]
+    controls = [mp.ACC, mp.ACC, mp.ACC, mp.ACC, mp.JRK]  # the jerk replanner outgrows its arrays (76 657 nodes): the launch is
+    planners, singles = [], []                             # repeated for it while the finished neighbours must stay untouched
+    for nm, c in zip(names, controls):
+        extra = {"max_num": 30000} if c == mp.JRK else None
+        planners.append(lpa_flow.build(GpuMap, GpuPlanner, nm, extra))
+        singles.append(lpa_flow.build(GpuMap, GpuPlanner, nm, extra))
     n = len(names)
     s, g = mp.waypoints_array(n), mp.waypoints_array(n)
     for i in range(n):
         s["pos"][i], g["pos"][i] = planners[i][4], goals[i]
-    s["control"] = g["control"] = mp.ACC
+        s["control"][i] = g["control"][i] = controls[i]
     res = np.zeros(n, dtype=_lib.RESULT_DTYPE)
     handles = (C.c_void_p * n)(*[p[2].pl._h for p in planners])
     _lib.check(_lib.lib().mplb_lpa_plan_batch(handles, n, _lib.ptr(s), _lib.ptr(g), _lib.ptr(res)))
@@ -157,6 +159,7 @@ def test_batch_of_replanners():
             assert res[i][f] == r1[f], (i, f)
         assert np.array_equal(planners[i][2].lpa_nodes()["g"], singles[i][2].lpa_nodes()["g"])
     assert len({float(r["cost"]) for r in res}) > 1
+    assert res[4]["n_nodes"] > 65536 and res[4]["pops"] == 11945 and res[0]["pops"] == 348
 
 
 def test_shaping_is_rejected_under_lpastar():
