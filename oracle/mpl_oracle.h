@@ -18,6 +18,11 @@
  * machine's libm (what pin 2 exercises), trig_mode 1 evaluates them correctly rounded (the definition the CUDA path
  * uses); tests/test_oracle_yaw.py relates the two.
  *
+ * The LPA* branch (lpa_* below; graph_search.h:194-365, state_space.h:116-282, map_planner.cpp:125-185) is pinned the same way:
+ * tests/test_oracle_lpa.py and tests/test_oracle_lpa_fuzz.py compare it step by step with the reference's own sources (whole state
+ * space in hm_ order, priority-queue array, best_child_, linked points); hm_ iteration order is insertion order on both sides
+ * (oracle/shim/boost/unordered_map.hpp).  The TrajSolver restatement lives in oracle/poly_oracle.cpp (pins stated in its header).
+ *
  * Third-party pieces that are NOT under /root/reference and are restated from their published
  * behaviour: Boost.Heap d_ary_heap<arity 2, mutable> (sift rules, see heap section of the .cpp),
  * Boost.Unordered (keyed here by the integer lattice tuple instead of boost::hash_combine),
