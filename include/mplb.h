@@ -267,7 +267,8 @@ int mplb_planner_set_lpastar(mplb_planner *p, int on);
 /* PlannerBase::reset (planner_base.h:164-167): drops the state space; the next plan starts from scratch. */
 int mplb_planner_reset(mplb_planner *p);
 /* MapUtil::setMap with an edited copy of getMap(), as add/clearCloudCallback do (map_replanner_node.cpp:181-196,221-229):
- * n cells (rows of 3 ints, the third ignored in 2D) receive `value`; the occupancy bit-bricks are rebuilt. */
+ * n cells (rows of 3 ints, the third ignored in 2D) receive `value`; cells outside the grid are ignored; the occupancy bit-bricks are
+ * rebuilt. */
 int mplb_map_set_cells(mplb_map *m, const int32_t *cells3, int n, int value);
 /* MapUtil::setMap again on a map of unchanged geometry: the whole int8 grid is replaced in place, so planners that share the
  * map (setMapUtil keeps a shared pointer in the reference) see the new cells without being re-pointed. */
