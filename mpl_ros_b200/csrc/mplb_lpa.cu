@@ -9,7 +9,9 @@
  * the split between the lane-parallel successor generation and the order-defining serial part.
  *
  * Kernels (all HBM/L2 latency bound pointer work except the successor rows, which are FP64):
- *   k_lpa_plan        the LPA* loop; 32 lanes generate the |U| successor rows of a popped node, lane 0 does the graph update
+ *   k_lpa_plan        the LPA* loop; 32 lanes generate the |U| successor rows of a popped node and then share its graph update
+ *                     (key-table probes, new States, predecessor appends, rhs recomputation); lane 0 keeps what defines order:
+ *                     ids, iteration-order slots and the priority-queue operations
  *   k_lpa_subtree     getSubStateSpace (a Dijkstra-like sweep over stored successor lists, serial by nature)
  *   k_lpa_link_count / k_lpa_link_scan / k_lpa_link_fill    the voxel -> edge table in insertion order (count, scan, fill)
  *   k_lpa_match       one thread per link against the changed voxels;  k_lpa_apply  sort + increaseCost / decreaseCost
@@ -50,6 +52,7 @@ __global__ void __launch_bounds__(32)
 k_lpa_plan(Ctx *ctxs, const mplb_waypoint *starts, const mplb_waypoint *goals, mplb_result *results, int *acts, double *segs, int max_seg) {
   __shared__ Ctx x;
   __shared__ int s_code;
+  __shared__ PopScratch s_pop;
   const int lane = threadIdx.x, b = blockIdx.x;
   if (lane == 0) {
     x = ctxs[b];
@@ -78,10 +81,16 @@ k_lpa_plan(Ctx *ctxs, const mplb_waypoint *starts, const mplb_waypoint *goals, m
       __syncwarp();
     }
     if (r == -1 || r == -2) {
+#ifdef MPLB_LPA_SERIAL_FINISH /* the one-lane tail, kept for A/B runs */
       if (lane == 0) s_code = pop_finish(x);
       __syncwarp();
       code = s_code;
       __syncwarp();
+#else /* probes, new States, predecessor appends and rhs over the lanes; ids, slots and queue operations on lane 0 */
+      pop_finish_warp(x, &s_pop);
+      code = s_pop.ret;
+      __syncwarp();
+#endif
     } else code = r;
   }
   Hdr &h = *x.h;
@@ -300,7 +309,7 @@ int ensure_capacity(Session *s, int cap, int cap_pred, bool keep) {
     s->cap_pred = cap_pred;
   }
   LPA_CUDA(s->d_hdr.grow(1, 1));
-  LPA_CUDA(s->rows.grow(std::max(s->nU, 1), 0));
+  LPA_CUDA(s->rows.grow(std::max(s->nU, 32), 0)); /* >= one staging row per lane (re-created successors of a stored list) */
   s->h.h = s->d_hdr.p; s->h.nodes = s->nodes.p; s->h.succ = s->succ.p; s->h.preds = s->preds.p; s->h.table = s->table.p;
   s->h.order = s->order.p; s->h.order2 = s->order2.p; s->h.heap_f = s->heap_f.p; s->h.heap_node = s->heap_node.p;
   s->h.best = s->best.p; s->h.traj_act = s->traj_act.p; s->h.rows = s->rows.p; s->h.mark = s->mark.p;

@@ -719,6 +719,207 @@ MPLB_HDN int pop_finish(const Ctx &x) {
   if (h.n_heap == 0) return LPA_QUEUE_EMPTY;                                     /* gs:331-336 */
   return -1;
 }
+/* ------------------------------------------------------------------ the same tail, spread over the warp
+ * pop_finish walks the successors one by one on lane 0.  Most of what it does per successor is independent of the other
+ * successors of the same pop: the key-table probe, building a new State, the scan of the successor's predecessor list for the
+ * popped node, the append, and the recomputation of rhs over that list (it reads g of predecessors, and g changes only at the head
+ * of a pop).  Only three things are order-defining: the ids / iteration-order slots / pool records handed out to new objects,
+ * and the priority-queue operations.  pop_finish_warp therefore runs chunks of 32 successors: the lanes probe and detect
+ * siblings with equal keys (the later one must see the earlier one's node, exactly as `hm_[coord]` would), lane 0 hands out ids
+ * and slots in control order, the lanes build nodes / append predecessor records / recompute rhs for the first occurrence of
+ * each node, and lane 0 then applies rhs and the heap operations in control order (a repeated sibling takes the plain serial
+ * updateNode).  Statement for statement this leaves every array as pop_finish leaves it; the host build (tests/cpp/lpa_emul.cpp)
+ * runs the same source with the lane loops serialised and is compared with the checker.
+ * Written once for both builds: LPA_LANES(l) is the lane loop (one iteration per thread on the device), LPA_SYNC a warp barrier. */
+#ifdef __CUDA_ARCH__
+#define LPA_LANES(l) for (int l = (int)threadIdx.x, l##_go = 1; l##_go; l##_go = 0)
+#define LPA_SYNC() __syncwarp()
+#define LPA_LANE0 (threadIdx.x == 0)
+#else
+#ifdef LPA_REVERSE_LANES /* test builds: the result must not depend on the order in which lanes run inside a phase */
+#define LPA_LANES(l) for (int l = 31; l >= 0; l--)
+#else
+#define LPA_LANES(l) for (int l = 0; l < 32; l++)
+#endif
+#define LPA_SYNC() ((void)0)
+#define LPA_LANE0 true
+#endif
+
+struct PopScratch { /* per-warp staging (shared memory on the device) */
+  int sid[32], state[32], leader[32], item[32], opos[32], prec[32];
+  unsigned char active[32], need_append[32], has_rhs[32];
+  double new_rhs[32];
+  int ret;
+};
+
+MPLB_HD void table_insert_shared(const Ctx &x, int id) { /* several lanes insert different ids at once */
+#ifdef __CUDA_ARCH__
+  const int mask = x.h->tsize - 1;
+  int s = (int)(key_hash(x.nodes[id].key, x.cfg.nkey) & (unsigned long long)mask);
+  while (atomicCAS(&x.table[s], -1, id) != -1) s = (s + 1) & mask;
+#else
+  table_insert(x, id);
+#endif
+}
+MPLB_HD void update_node_heap(const Ctx &x, int id) { /* the queue half of updateNode (ss:256-266) */
+  Node &n = x.nodes[id];
+  if (n.opened && !n.closed) { pq_erase(x, id); n.closed = 1; }
+  if (n.g != n.rhs) {
+    pq_push(x, calc_key(x, id), id);
+    n.opened = 1;
+    n.closed = 0;
+  }
+}
+/* Called by all lanes of the warp (device) / once (host).  Result in S->ret: -1 to continue, else the final status. */
+MPLB_HDN void pop_finish_warp(const Ctx &x, PopScratch *S) {
+  Hdr &h = *x.h;
+  const Cfg &c = x.cfg;
+  const int curr = h.curr;
+  const bool fresh = h.has_rows != 0;
+  Succ *sl = x.succ + (size_t)curr * c.nU;
+  const int n_in = fresh ? c.nU : x.nodes[curr].n_succ; /* controls (fresh) or stored entries */
+  int gkey[12];
+  make_key(c, h.goal, gkey);
+  int ns = 0; /* lane 0's running count of stored entries (fresh case) */
+  for (int base = 0; base < n_in; base += 32) {
+    /* ---- 1: probe.  state 0 = member of hm_, 1 = known key whose State was dropped, 2 = never seen */
+    LPA_LANES(l) {
+      const int i = base + l;
+      S->active[l] = 0; S->need_append[l] = 0; S->has_rhs[l] = 0; S->leader[l] = l; S->sid[l] = -1; S->state[l] = 0;
+      if (i < n_in) {
+        if (fresh) {
+          const Row &r = x.rows[i];
+          if (r.verdict) {
+            S->active[l] = 1;
+            const int id = table_find(x, r.key, r.hash);
+            S->sid[l] = id;
+            S->state[l] = id < 0 ? 2 : (x.nodes[id].in_hm ? 0 : 1);
+          }
+        } else {
+          S->active[l] = 1;
+          const int id = sl[i].node;
+          S->sid[l] = id;
+          S->state[l] = x.nodes[id].in_hm ? 0 : 1;
+          if (S->state[l] == 1) { /* hm_[succ_coord[s]] will build a new State from the stored coordinate: recompute it */
+            Row &r = x.rows[l];
+            Prim pr;
+            prim_build(c, x.nodes[curr].st, c.U + 3 * sl[i].act, pr);
+            prim_eval(c, pr, c.dt, r.st);
+            make_key(c, r.st, r.key);
+            r.t = fA(x.nodes[curr].t, c.dt);
+            r.hash = key_hash(r.key, c.nkey);
+          }
+        }
+      }
+    }
+    LPA_SYNC();
+    /* ---- 2: the first sibling of this chunk with the same key (ids for stored entries) */
+    LPA_LANES(l) {
+      if (S->active[l]) {
+        for (int k = 0; k < l; k++) {
+          if (!S->active[k]) continue;
+          bool same;
+          if (fresh) same = x.rows[base + k].hash == x.rows[base + l].hash && key_eq(x.rows[base + k].key, x.rows[base + l].key, c.nkey);
+          else same = S->sid[k] == S->sid[l];
+          if (same) { S->leader[l] = k; break; }
+        }
+      }
+    }
+    LPA_SYNC();
+    /* ---- 3: lane 0 hands out node ids, iteration-order slots and list positions in control order */
+    if (LPA_LANE0) {
+      for (int l = 0; l < 32; l++) {
+        const int i = base + l;
+        if (fresh && i < n_in) h.n_samples += x.rows[i].n_samples;
+        if (!S->active[l]) continue;
+        if (fresh) { if (!fIsInf(x.rows[i].cost)) h.n_valid++; S->item[l] = ns++; }
+        if (S->leader[l] != l) continue;
+        if (S->state[l] == 2) S->sid[l] = h.n_nodes++;
+        if (S->state[l] != 0) S->opos[l] = h.n_order++;
+      }
+    }
+    LPA_SYNC();
+    /* ---- 4: the lanes build the new States */
+    LPA_LANES(l) {
+      if (S->active[l] && S->leader[l] == l && S->state[l] != 0) {
+        const Row &r = fresh ? x.rows[base + l] : x.rows[l];
+        Node &n = x.nodes[S->sid[l]];
+        node_init(n, r.st, r.t, r.key);
+        n.in_hm = 1;
+        n.h = h.eps == 0 ? 0 : heur(c, h.goal, gkey, r.st, r.key); /* gs:279-281 */
+        x.order[S->opos[l]] = S->sid[l];
+        if (S->state[l] == 2) table_insert_shared(x, S->sid[l]);
+      }
+    }
+    LPA_SYNC();
+    /* ---- 5: stored list entry, and does the successor already list the popped node as a predecessor? (gs:296-303) */
+    LPA_LANES(l) {
+      if (S->active[l]) {
+        if (S->leader[l] != l) S->sid[l] = S->sid[S->leader[l]];
+        const int i = base + l;
+        if (fresh) { Succ &e = sl[S->item[l]]; e.node = S->sid[l]; e.act = i; e.cost = x.rows[i].cost; }
+        if (S->leader[l] == l) S->need_append[l] = pred_find(x, S->sid[l], curr) < 0;
+      }
+    }
+    LPA_SYNC();
+    if (LPA_LANE0)
+      for (int l = 0; l < 32; l++)
+        if (S->active[l] && S->need_append[l]) S->prec[l] = h.n_pred++;
+    LPA_SYNC();
+    /* ---- 6: append (one lane per node, so the lists never collide), then rhs over the node's own list (ss:245-253) */
+    LPA_LANES(l) {
+      if (S->active[l] && S->leader[l] == l) {
+        const int sid = S->sid[l];
+        Node &n = x.nodes[sid];
+        if (S->need_append[l]) {
+          const int i = base + l;
+          const int r = S->prec[l];
+          x.preds[r].cost = fresh ? x.rows[i].cost : sl[i].cost;
+          x.preds[r].node = curr;
+          x.preds[r].act = fresh ? i : sl[i].act;
+          x.preds[r].next = -1; x.preds[r].pad = 0;
+          if (n.pred_tail >= 0) x.preds[n.pred_tail].next = r; else n.pred_head = r;
+          n.pred_tail = r;
+          n.n_pred++;
+        }
+        if (n.rhs != h.start_rhs) {
+          double v = LPA_INF;
+          for (int p = n.pred_head; p >= 0; p = x.preds[p].next) {
+            const double w = fA(x.nodes[x.preds[p].node].g, x.preds[p].cost);
+            if (v > w) v = w;
+          }
+          S->new_rhs[l] = v;
+          S->has_rhs[l] = 1;
+        }
+      }
+    }
+    LPA_SYNC();
+    /* ---- 7: lane 0 commits rhs and runs the queue operations in control order */
+    if (LPA_LANE0) {
+      for (int l = 0; l < 32; l++) {
+        if (!S->active[l]) continue;
+        const int sid = S->sid[l];
+        if (S->leader[l] == l) {
+          if (S->has_rhs[l]) x.nodes[sid].rhs = S->new_rhs[l];
+          update_node_heap(x, sid);
+        } else {
+          update_node(x, sid); /* a repeated sibling: the plain serial statement */
+        }
+      }
+    }
+    LPA_SYNC();
+  }
+  if (LPA_LANE0) {
+    if (fresh) x.nodes[curr].n_succ = ns;
+    int ret = -1;
+    if (is_goal(c, h.goal, x.nodes[curr].st)) h.goal_node = curr;            /* gs:319 */
+    if (c.max_num > 0 && h.expand_iteration >= c.max_num) ret = LPA_MAX_EXPAND; /* gs:322-328 */
+    else if (h.n_heap == 0) ret = LPA_QUEUE_EMPTY;                              /* gs:331-336 */
+    S->ret = ret;
+  }
+  LPA_SYNC();
+}
+
 /* recoverTraj (gs:369-455); returns LPA_OK or LPA_TRACEBACK_FAILED; cost = goal g - start_g_ (gs:362) */
 MPLB_HDN int recover(const Ctx &x, int *n_seg, double *cost) {
   Hdr &h = *x.h;

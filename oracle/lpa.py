@@ -26,9 +26,9 @@ _DONE = set()
 
 def _fn(lib, prefix, name):
     f = getattr(lib, prefix + name)
-    if (prefix, name) not in _DONE:
+    if (id(lib), prefix, name) not in _DONE:
         f.restype, f.argtypes = _SIGS[name]
-        _DONE.add((prefix, name))
+        _DONE.add((id(lib), prefix, name))
     return f
 
 

@@ -37,6 +37,7 @@ struct Emu {
   int control = 0;
   int init_cap = 1 << 16, init_pred = 1 << 20;
   int grows = 0;
+  int serial_finish = 0;
   /* "device" arrays */
   Hdr hdr{};
   std::vector<Node> nodes; std::vector<Succ> succ; std::vector<Pred> preds; std::vector<int> table, order, order2, heap_node, best, traj_act, epq_node, link_count;
@@ -73,7 +74,7 @@ struct Emu {
       for (int i = 0; i < hdr.n_nodes; i++) table_insert(x, i); /* k_lpa_rehash */
     }
     if (cpred > cap_pred) { preds.resize(cpred); cap_pred = cpred; }
-    rows.resize(std::max(nU, 1));
+    rows.resize(std::max(nU, 32));
     hdr.cap_nodes = cap_nodes; hdr.cap_pred = cap_pred; hdr.tsize = tsize;
   }
   void reset() {
@@ -117,7 +118,7 @@ int emu_planner_set_param(void *pp, const char *key, double v) {
   if (k == "v_max") p->v_max = v; else if (k == "a_max") p->a_max = v; else if (k == "j_max") p->j_max = v; else if (k == "dt") p->dt = v;
   else if (k == "w") p->w = v; else if (k == "epsilon") p->eps = v; else if (k == "max_num") p->max_num = (int)v; else if (k == "tol_pos") p->tol_pos = v;
   else if (k == "tol_vel") p->tol_vel = v; else if (k == "tol_acc") p->tol_acc = v; else if (k == "init_cap") p->init_cap = (int)v;
-  else if (k == "init_pred") p->init_pred = (int)v; else return -1;
+  else if (k == "init_pred") p->init_pred = (int)v; else if (k == "serial_finish") p->serial_finish = (int)v; else return -1;
   return 0;
 }
 void emu_planner_set_controls(void *pp, const double *U, int n, int udim) {
@@ -149,7 +150,10 @@ int emu_lpa_plan(void *pp, const orc_waypoint *start, const orc_waypoint *goal, 
         const Node &n = x.nodes[x.h->curr];
         for (int lane = 0; lane < 32; lane++) for (int u = lane; u < x.cfg.nU; u += 32) succ_row(x.cfg, n.st, n.t, n.key, u, &x.rows[u]);
       }
-      if (r == -1 || r == -2) code = pop_finish(x); else code = r;
+      if (r == -1 || r == -2) {
+        if (p->serial_finish) code = pop_finish(x);                      /* the one-lane tail */
+        else { PopScratch S; pop_finish_warp(x, &S); code = S.ret; }     /* the warp-wide tail, lane loops serialised */
+      } else code = r;
     }
     if (code == LPA_NEED_GROW) { p->hdr.resume = 1; p->grows++; p->ensure(p->cap_nodes * 2, p->cap_pred * 2); continue; }
     break;

@@ -45,6 +45,17 @@ def test_oracle_and_device_core_equal_the_fixture(name):
             assert np.array_equal(d[f], gold[f]), (name, f)
 
 
+@pytest.mark.parametrize("name", ["skir_acc", "corridor_jrk"])
+def test_device_core_variants(name):
+    """(a) the one-lane tail (pop_finish) and the warp-wide tail (pop_finish_warp) leave identical states; (b) the warp-wide tail
+    does not depend on the order in which the lanes of a phase run (build with the lane loops reversed)."""
+    a, _ = lpa_flow.run_flow(name, oracle.OracleMap, oracle.OraclePlanner)
+    for cm, cp, extra in ((lpa_emul.EmuMap, lpa_emul.EmuPlanner, dict(serial_finish=1)),
+                          (lpa_emul.EmuMapRev, lpa_emul.EmuPlannerRev, dict(init_cap=512, init_pred=4096))):
+        b, _ = lpa_flow.run_flow(name, cm, cp, extra)
+        lpa_flow.assert_same(a, b, name + " " + cp.__name__)
+
+
 def test_known_answer_corridor():
     snaps, _ = lpa_flow.run_flow("corridor_acc", oracle.OracleMap, oracle.OraclePlanner)
     r = snaps[0]["res"]
